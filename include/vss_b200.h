@@ -1,0 +1,212 @@
+/*
+ * vss_b200.h — C-ABI of libvss_b200.so, the B200-native VSS (3v3 robot soccer)
+ * hot path: fused env step, masked reset, agent views, GAE, PPO MLP.
+ *
+ * This is the drop-in boundary UNDER the reference's Python seam (envs/vss.py
+ * class VSS, envs/wrappers.py views, ppo_continuous_action_isaacgym.py loop).
+ * The reference has no FFI of its own: every entry point below replaces a run of
+ * IsaacGym `gymapi`/`gymtorch` calls plus torch-jit code, cited per function as
+ * `file:line` into the reference tree.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types. All `float*`/`int64_t*`/`uint8_t*`
+ *     data pointers are DEVICE pointers owned by the caller (torch); the engine
+ *     borrows them for the duration of the call. Layouts are the reference's
+ *     row-major tensor layouts, stated per argument.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream).
+ *     Every call only enqueues work; there is NO host synchronisation inside.
+ *   - return 0 on success, negative `VSS_E_*` on failure; `vss_last_error()` gives
+ *     the message (thread-local).
+ *   - one handle per device; a handle is not thread-safe.
+ *   - there is no CPU fallback: `vss_create` fails if the device is not sm_100.
+ */
+#ifndef VSS_B200_H
+#define VSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSS_API __attribute__((visibility("default")))
+
+/* ---- fixed problem shape (envs/vss.py:24-25,80-92; vss.yaml:4-5) ---- */
+#define VSS_NUM_TEAMS 2
+#define VSS_NUM_ROBOTS 3
+#define VSS_NUM_OBS 52
+#define VSS_NUM_ACTIONS 2
+#define VSS_NUM_REW 4
+#define VSS_OBS_PER_FIELD (VSS_NUM_TEAMS * VSS_NUM_ROBOTS * VSS_NUM_OBS) /* 312 */
+#define VSS_ACT_PER_FIELD (VSS_NUM_TEAMS * VSS_NUM_ROBOTS * VSS_NUM_ACTIONS) /* 12 */
+#define VSS_REW_PER_FIELD (VSS_NUM_TEAMS * VSS_NUM_ROBOTS * VSS_NUM_REW) /* 24 */
+
+/* Engine state, SoA in HBM: word w of field e lives at state[w * ld + e].
+ * Words 0..3   ball x, y, vx, vy
+ * Words 4+9r+k robot r = team*3 + idx; k: x, y, vx, vy, cos(yaw), sin(yaw), yaw-rate,
+ *              last action left, last action right      (= vss.py:541-551 feature order)
+ * Word 58      progress counter (int32 bit pattern)     (vss.py:95 progress_buf)
+ * Word 59      episode counter  (uint32 bit pattern; keys the reset RNG)            */
+#define VSS_STATE_FLOATS 58
+#define VSS_STATE_WORDS 60
+#define VSS_W_PROGRESS 58
+#define VSS_W_EPISODE 59
+
+/* error codes */
+#define VSS_OK 0
+#define VSS_E_INVALID (-1)   /* bad argument */
+#define VSS_E_CUDA (-2)      /* CUDA runtime error */
+#define VSS_E_NODEVICE (-3)  /* no sm_100 device / no CPU fallback */
+#define VSS_E_NOMEM (-4)
+
+/* agent views, envs/wrappers.py:89-180 */
+#define VSS_VIEW_SA 0  /* SingleAgent: controls blue robot 0          */
+#define VSS_VIEW_CMA 1 /* CMA: one 6-dim action for blue robots 0-2   */
+#define VSS_VIEW_DMA 2 /* DMA: blue robots 0-2 as 3 separate agents   */
+
+typedef struct vss_engine* vss_handle;
+
+/* Physical + task constants. Defaults (vss_default_params) are extracted from the
+ * reference scene code: envs/vss.py:48-49,342-345,368-434,436-522, vss_robot.urdf,
+ * vss.yaml. The physics model itself is new (PhysX is closed); see DESIGN.md §3. */
+typedef struct vss_params {
+  /* simulation, vss.yaml:16, vss.yaml:6 */
+  float dt;                   /* 0.05 s control step */
+  int32_t substeps;           /* physics substeps per control step (4) */
+  int32_t max_episode_length; /* 400 */
+  /* field, vss.py:342-345 */
+  float field_half_length;    /* 0.75  (field_width / 2) */
+  float field_half_width;     /* 0.65  (field_height / 2) */
+  float goal_half_width;      /* 0.2   (goal_height / 2) */
+  float goal_depth;           /* 0.1   (goal_width) */
+  /* ball, vss.py:380-389 */
+  float ball_radius;          /* 0.02134 */
+  float ball_mass;            /* 0.046 kg (density 1130) */
+  float ball_drag;            /* 1/s: rolling sphere under PhysX angular damping 0.5 -> 2/7*0.5 */
+  /* robot, vss_robot.urdf:3-68 */
+  float robot_half_size;      /* 0.035 (0.07 collision box) */
+  float robot_mass;           /* 0.44 kg = body 0.4 + 2 wheels 0.02 */
+  float robot_inertia;        /* yaw inertia, kg m^2 */
+  float wheel_radius;         /* 0.024 */
+  float wheel_half_track;     /* 0.03375 */
+  float wheel_coll_radius;    /* 0.024 wheel collision sphere (robot-robot only) */
+  /* wheel drive, vss.py:47,427-434, urdf:59,67 */
+  float max_wheel_rad_s;      /* 42.0 */
+  float drive_damping;        /* 0.01 N m s/rad velocity-drive gain */
+  float drive_max_torque;     /* 0.1 N m effort limit */
+  float wheel_inertia;        /* armature 2e-4 + sphere 0.4 m r^2 */
+  float mu_traction;          /* 0.7 longitudinal traction limit */
+  float mu_lateral;           /* 0.55 lateral sliding friction */
+  float gravity;              /* 9.81 */
+  /* contacts */
+  float restitution;          /* 0 (PhysX default materials) */
+  float mu_ball_robot;        /* 0.5 */
+  float mu_ball_wall;         /* 1.0 */
+  float mu_robot_wall;        /* 0.5 */
+  /* reset distribution, vss.py:49,142-147,267-327 */
+  float reset_scale_x;        /* 1.5 - 0.14 */
+  float reset_scale_y;        /* 1.3 - 0.14 */
+  float min_placement_dist;   /* 0.07 */
+  float ball_reset_speed;     /* 1.0: ball velocity ~ (U-0.5)*this */
+  /* reward weights, vss.yaml:8-12 (mutable at run time, ppo...:389-392) */
+  float w_goal, w_grad, w_move, w_energy;
+  /* OU noise of uncontrolled robots, wrappers.py:5-19 */
+  float ou_theta;             /* 0.1 */
+  float ou_sigma;             /* 0.15 */
+} vss_params;
+
+/* Fill `p` with the reference's constants. */
+VSS_API int vss_default_params(vss_params* p);
+
+/* Replaces VSS.__init__ -> create_sim / allocate_buffers / _acquire_tensors
+ * (envs/vss.py:32-175, 341-522): allocates the SoA state for `num_envs` fields on
+ * CUDA device `device`. `global_env_offset` is the global id of local field 0 (keys
+ * the counter-based RNG so results do not depend on how fields are sharded). All
+ * fields start flagged for reset, like reset_buf = ones (vss.py:93). */
+VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs,
+                       int64_t global_env_offset, int device, uint64_t seed);
+VSS_API int vss_destroy(vss_handle h);
+
+VSS_API int64_t vss_num_envs(vss_handle h);
+/* leading dimension (in fields) of the SoA state: num_envs rounded up to 32 */
+VSS_API int64_t vss_state_ld(vss_handle h);
+
+/* w = {goal, grad, move, energy}; replaces attribute writes at ppo...:389-392. */
+VSS_API int vss_set_reward_weights(vss_handle h, const float w[4]);
+
+/* Replaces reset_dones() + compute_observations() (envs/vss.py:72-73, 267-333,
+ * 205-216): re-randomise every field whose reset_buf entry is != 0 (reset_buf is
+ * NOT cleared, as in the reference), then write obs (N,2,3,52) for all fields.
+ * reset_buf: (N) int64, device. */
+VSS_API int vss_reset_dones(vss_handle h, const int64_t* reset_buf, float* obs, void* stream);
+
+/* Replaces VecTask.step -> pre_physics_step / gym.simulate / post_physics_step
+ * (envs/vss.py:180-203, 218-333 and the six jit functions :530-655).
+ *   actions   in  (N,2,3,2) f32, clamped to [-1,1] inside (vss.yaml:7)
+ *   reset_buf io  (N) int64: flags from the previous step in, this step's dones out
+ *   obs       out (N,2,3,52) post-reset observation          (vss.py:203)
+ *   term_obs  out (N,2,3,52) pre-reset "terminal_observation" (vss.py:195-196); may be NULL
+ *   rew       out (N,2,3,4)  {goal,grad,move,energy} * weights (vss.py:223-255)
+ *   timeout   out (N) uint8  (progress >= max_len-1) & reset  (VecTask.step)
+ *   progress_f out (N) f32   un-reset progress counter         (vss.py:198-200); may be NULL */
+VSS_API int vss_step(vss_handle h, const float* actions, int64_t* reset_buf, float* obs,
+                     float* term_obs, float* rew, uint8_t* timeout, float* progress_f,
+                     void* stream);
+
+/* Parity hook ("identical input states"): same as vss_step, but the physics phase
+ * is replaced by loading the post-physics state from `post_state` (58 x ld floats,
+ * SoA as above; the two last-action words are ignored and taken from `actions`).
+ * Everything else (progress, rewards, dones, obs, masked reset, timeouts) runs
+ * through the same code as vss_step. */
+VSS_API int vss_step_injected(vss_handle h, const float* actions, const float* post_state,
+                              int64_t* reset_buf, float* obs, float* term_obs, float* rew,
+                              uint8_t* timeout, float* progress_f, void* stream);
+
+/* Fused agent-view step: replaces SingleAgent/CMA/DMA.step (envs/wrappers.py:101-115,
+ * 133-148, 163-180) + random_ou (:5-19) + VSS.step + RecordEpisodeStatisticsTorch.step
+ * (:66-87) in ONE launch. N' = N (sa, cma) or 3N (dma); A = 2 (sa, dma) or 6 (cma).
+ *   policy_action in  (N',A) f32
+ *   action_buf    io  (N,2,3,2) f32 persistent OU state of the view (wrappers.py:94)
+ *   reset_buf     io  (N) int64 (the VSS reset_buf)
+ *   obs_v         out (N',52)  view observation after reset
+ *   term_obs_v    out (N',52)  view terminal observation
+ *   rews_v        out (N',4)   infos['rews']
+ *   reward_v      out (N')     rews.sum(-1)
+ *   done_v        out (N') int64
+ *   timeout_v     out (N') uint8
+ *   progress_v    out (N') f32
+ *   ep_ret/ep_len io  (N',4) f32 / (N') int32 running episode statistics, or NULL
+ *   ret_ret/ret_len out (N',4) f32 / (N') int32 statistics snapshot before masking, or NULL */
+VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, float* action_buf,
+                          int64_t* reset_buf, float* obs_v, float* term_obs_v, float* rews_v,
+                          float* reward_v, int64_t* done_v, uint8_t* timeout_v, float* progress_v,
+                          float* ep_ret, int32_t* ep_len, float* ret_ret, int32_t* ret_len,
+                          void* stream);
+
+/* State access for parity tests and checkpointing: copies the SoA state
+ * (VSS_STATE_WORDS x ld 32-bit words) device->device. */
+VSS_API int vss_get_state(vss_handle h, float* state_out, void* stream);
+VSS_API int vss_set_state(vss_handle h, const float* state_in, void* stream);
+/* number of vss_step/vss_step_view calls so far (keys the OU-noise RNG) */
+VSS_API uint64_t vss_step_count(vss_handle h);
+VSS_API int vss_set_step_count(vss_handle h, uint64_t n);
+
+/* Replaces the GAE loop, ppo_continuous_action_isaacgym.py:282-296. All arrays (T,N) f32
+ * row-major, device. adv and ret are outputs. gamma/lambda are the python doubles; they are
+ * rounded to f32 exactly where torch rounds them (gamma, gamma*lambda). */
+VSS_API int vss_gae(const float* rewards, const float* values, const float* next_values,
+                    const float* next_dones, const float* next_timeouts, float* advantages,
+                    float* returns, int32_t T, int64_t N, double gamma, double gae_lambda,
+                    void* stream);
+
+/* Philox4x32-10 known-answer hook (host side; same code as the device generator). */
+VSS_API void vss_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+VSS_API const char* vss_last_error(void);
+VSS_API const char* vss_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSS_B200_H */

@@ -1,0 +1,334 @@
+"""Generate golden vectors by EXECUTING THE REFERENCE'S OWN CODE.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU
+box):   python tests/golden/make_golden.py
+Outputs (committed): tests/golden/jit_functions.npz, gae.npz, wrappers.npz, agent.npz
+
+Nothing from the reference is copied into the repo: the source ranges below are read from
+/root/reference at generation time and exec'd in a scratch namespace.
+  - envs/vss.py:530-655       the six @torch.jit.script functions (obs, 4 rewards, dones);
+                              `device="cuda:0"` at :536 is rewritten to "cpu" (no GPU here), and
+                              isaacgym.torch_utils.get_euler_xyz (un-vendored) is supplied by a
+                              stand-in restating its published formula.
+  - ppo_continuous_action_isaacgym.py:282-296   the GAE loop, verbatim.
+  - ppo_continuous_action_isaacgym.py:121-164   layer_init + Agent, verbatim.
+  - envs/wrappers.py (whole file)  executed against a 20-line `gym` shim (gym 0.23.1 is
+                              un-vendored) and a fake task that replays fixed VSS.step outputs.
+"""
+import os
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("VSS_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _lines(path, lo, hi):
+    with open(os.path.join(REF, path)) as f:
+        src = f.readlines()
+    return "".join(src[lo - 1:hi])
+
+
+# ------------------------------------------------------------------ reference jit functions
+def load_ref_jit():
+    src = _lines("envs/vss.py", 526, 655).replace('device="cuda:0"', 'device="cpu"')
+    prelude = textwrap.dedent('''
+        import numpy as np
+        import torch
+        from torch import Tensor
+        from typing import Tuple
+
+        @torch.jit.script
+        def get_euler_xyz(q):
+            # type: (Tensor) -> Tuple[Tensor, Tensor, Tensor]
+            qx, qy, qz, qw = 0, 1, 2, 3
+            sinr_cosp = 2.0 * (q[:, qw] * q[:, qx] + q[:, qy] * q[:, qz])
+            cosr_cosp = q[:, qw] * q[:, qw] - q[:, qx] * q[:, qx] - q[:, qy] * q[:, qy] + q[:, qz] * q[:, qz]
+            roll = torch.atan2(sinr_cosp, cosr_cosp)
+            sinp = 2.0 * (q[:, qw] * q[:, qy] - q[:, qz] * q[:, qx])
+            pitch = torch.where(torch.abs(sinp) >= 1, torch.sign(sinp) * (3.141592653589793 / 2.0), torch.asin(sinp))
+            siny_cosp = 2.0 * (q[:, qw] * q[:, qz] + q[:, qx] * q[:, qy])
+            cosy_cosp = q[:, qw] * q[:, qw] + q[:, qx] * q[:, qx] - q[:, qy] * q[:, qy] - q[:, qz] * q[:, qz]
+            yaw = torch.atan2(siny_cosp, cosy_cosp)
+            return roll % (2 * 3.141592653589793), pitch % (2 * 3.141592653589793), yaw % (2 * 3.141592653589793)
+    ''')
+    # torch.jit.script needs real source files -> write a scratch module outside the repo
+    import importlib.util
+    import tempfile
+    d = tempfile.mkdtemp(prefix="vss_ref_jit_")
+    path = os.path.join(d, "ref_jit_scratch.py")
+    with open(path, "w") as f:
+        f.write(prelude + "\n" + src)
+    spec = importlib.util.spec_from_file_location("ref_jit_scratch", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_states(rng, n):
+    """Random field states in the reference's tensor layouts, with edge cases."""
+    ball_pos = rng.uniform(-1, 1, (n, 2)).astype(np.float32) * np.float32([0.85, 0.65])
+    prev_ball_pos = (ball_pos + rng.normal(0, 0.03, (n, 2))).astype(np.float32)
+    # edge cases: balls inside both goals, on the goal line, just outside the mouth, at the origin
+    ball_pos[0] = [0.80, 0.05]
+    ball_pos[1] = [-0.78, -0.19]
+    ball_pos[2] = [0.75, 0.0]       # on the line: not > 0.75 -> no goal
+    ball_pos[3] = [0.76, 0.2]       # |y| == 0.2 -> no goal
+    ball_pos[4] = [-0.7500001, 0.1]
+    ball_pos[5] = [0.0, 0.0]
+    ball_pos[6] = [0.8, 0.3]        # behind the end wall, outside the mouth
+    ball_vel = rng.uniform(-1.5, 1.5, (n, 2)).astype(np.float32)
+    ball_vel[5] = 0.0               # exercises the -0.0 of the mirrored view
+    r_pos = (rng.uniform(-1, 1, (n, 2, 3, 2)) * [0.85, 0.65]).astype(np.float32)
+    prev_r_pos = (r_pos + rng.normal(0, 0.03, (n, 2, 3, 2))).astype(np.float32)
+    r_vel = rng.uniform(-1.2, 1.2, (n, 2, 3, 2)).astype(np.float32)
+    yaw = rng.uniform(-np.pi, np.pi, (n, 2, 3))
+    yaw[5] = 0.0
+    yaw[6, 0, 0] = np.pi / 2
+    yaw[6, 0, 1] = -np.pi
+    quats = np.zeros((n, 2, 3, 4), np.float32)  # xyzw, rotation about z (vss.py:313-315)
+    quats[..., 2] = np.sin(yaw / 2)
+    quats[..., 3] = np.cos(yaw / 2)
+    r_w = rng.uniform(-30, 30, (n, 2, 3, 1)).astype(np.float32)
+    r_w[5] = 0.0
+    acts = rng.uniform(-1, 1, (n, 2, 3, 2)).astype(np.float32)
+    acts[5] = 0.0
+    progress = rng.integers(0, 405, (n,)).astype(np.int64)
+    progress[7], progress[8], progress[9] = 399, 400, 401
+    reset_buf = rng.integers(0, 2, (n,)).astype(np.int64)
+    return dict(ball_pos=ball_pos, prev_ball_pos=prev_ball_pos, ball_vel=ball_vel, r_pos=r_pos,
+                prev_r_pos=prev_r_pos, r_vel=r_vel, quats=quats, r_w=r_w, acts=acts, progress=progress,
+                reset_buf=reset_buf)
+
+
+def gen_jit(mod):
+    rng = np.random.default_rng(20261018)
+    s = make_states(rng, 96)
+    t = {k: torch.from_numpy(v) for k, v in s.items()}
+    perms = torch.tensor([[0, 1, 2], [1, 2, 0], [2, 0, 1]])      # vss.py:173-175
+    mirror = torch.tensor([-1.0] * 6 + [1.0] * 3)                # vss.py:166-171
+    yellow_goal = torch.tensor([1.5 / 2, 0.0])                   # vss.py:154-159
+    out = dict(s)
+    out["obs"] = mod.compute_obs(t["ball_pos"], t["ball_vel"], t["r_pos"], t["r_vel"], t["quats"], t["r_w"],
+                                 t["acts"], perms, mirror).numpy()
+    out["goal_rew"] = mod.compute_goal_rew(t["reset_buf"], t["ball_pos"], 1.5, 0.4).numpy()
+    out["grad_rew"] = mod.compute_grad_rew(t["prev_ball_pos"], t["ball_pos"], yellow_goal).numpy()
+    out["move_rew"] = mod.compute_move_rew(t["prev_r_pos"], t["r_pos"], t["prev_ball_pos"], t["ball_pos"]).numpy()
+    out["energy_rew"] = mod.compute_energy_rew(t["acts"]).numpy()
+    out["dones"] = mod.compute_vss_dones(t["ball_pos"], t["reset_buf"], t["progress"], 400.0, 1.5, 0.4).numpy()
+    # (cos, sin) of the yaw the engine stores instead of quaternions, from the same quats in f64
+    q = s["quats"].astype(np.float64)
+    c = q[..., 3] ** 2 + q[..., 0] ** 2 - q[..., 1] ** 2 - q[..., 2] ** 2
+    sn = 2.0 * (q[..., 3] * q[..., 2] + q[..., 0] * q[..., 1])
+    nrm = np.sqrt(c * c + sn * sn)
+    out["r_rot"] = np.stack([c / nrm, sn / nrm], -1).astype(np.float32)
+    assert out["obs"].shape == (96, 2, 3, 52) and out["goal_rew"].dtype == np.int64
+    np.savez_compressed(os.path.join(OUT, "jit_functions.npz"), **out)
+    print("jit_functions.npz", {k: v.shape for k, v in out.items() if k in ("obs", "goal_rew", "dones")})
+
+
+# ------------------------------------------------------------------ GAE loop
+def gen_gae():
+    src = textwrap.dedent(_lines("ppo_continuous_action_isaacgym.py", 282, 296))
+    assert src.startswith("with torch.no_grad():") and "returns = advantages + values" in src
+    rng = np.random.default_rng(7)
+    cases = {}
+    for name, (T, N) in {"a": (16, 8), "b": (128, 33), "c": (1, 5)}.items():
+        rewards = rng.normal(0, 1, (T, N)).astype(np.float32)
+        values = rng.normal(0, 2, (T, N)).astype(np.float32)
+        next_values = rng.normal(0, 2, (T, N)).astype(np.float32)
+        next_dones = (rng.uniform(size=(T, N)) < 0.15).astype(np.float32)
+        next_timeouts = ((rng.uniform(size=(T, N)) < 0.5) * next_dones).astype(np.float32)
+        next_timeouts[0, 0] = 1.0  # timeout flag without done (cannot happen, but defined)
+        ns = dict(torch=torch, device="cpu", args=types.SimpleNamespace(num_steps=T, gamma=0.99, gae_lambda=0.95),
+                  rewards=torch.from_numpy(rewards), values=torch.from_numpy(values),
+                  next_values=torch.from_numpy(next_values), next_dones=torch.from_numpy(next_dones),
+                  next_timeouts=torch.from_numpy(next_timeouts))
+        exec(src, ns)
+        for k, v in dict(rewards=rewards, values=values, next_values=next_values, next_dones=next_dones,
+                         next_timeouts=next_timeouts, advantages=ns["advantages"].numpy(),
+                         returns=ns["returns"].numpy()).items():
+            cases[f"{name}_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "gae.npz"), **cases)
+    print("gae.npz", sorted(cases)[:3], "...")
+
+
+# ------------------------------------------------------------------ wrappers against a fake task
+def _gym_shim():
+    gym = types.ModuleType("gym")
+
+    class Box:
+        def __init__(self, low, high, shape):
+            self.low, self.high, self.shape = low, high, tuple(shape)
+
+    class Wrapper:
+        def __init__(self, env):
+            self.env = env
+
+        def __getattr__(self, name):
+            if name.startswith("_"):
+                raise AttributeError(name)
+            return getattr(self.env, name)
+
+        def reset(self, **kw):
+            return self.env.reset(**kw)
+
+        def step(self, action):
+            return self.env.step(action)
+
+    gym.Wrapper = Wrapper
+    gym.spaces = types.SimpleNamespace(Box=Box)
+    return gym
+
+
+class FakeTask:
+    """Replays fixed VSS.step outputs; records the action buffer it is stepped with."""
+
+    def __init__(self, steps):
+        self.steps = steps
+        self.num_envs = steps[0]["obs"].shape[0]
+        self.num_obs, self.num_actions = 52, 2
+        self.device = "cpu"
+        self.dof_velocity_buf = torch.zeros((self.num_envs, 2, 3, 2))
+        self.t = 0
+        self.seen_actions = []
+
+    def reset(self):
+        return {"obs": torch.from_numpy(self.steps[0]["obs0"]).clone()}
+
+    def step(self, actions):
+        self.seen_actions.append(actions.clone().numpy())
+        s = self.steps[self.t]
+        self.t += 1
+        infos = {"time_outs": torch.from_numpy(s["timeout"]).clone(),
+                 "terminal_observation": torch.from_numpy(s["term_obs"]).clone(),
+                 "progress_buffer": torch.from_numpy(s["progress_f"]).clone()}
+        return ({"obs": torch.from_numpy(s["obs"]).clone()}, torch.from_numpy(s["rew"]).clone(),
+                torch.from_numpy(s["reset"]).clone(), infos)
+
+
+def gen_wrappers():
+    sys.modules["gym"] = _gym_shim()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_wrappers", os.path.join(REF, "envs/wrappers.py"))
+    W = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(W)
+    rng = np.random.default_rng(11)
+    n, T = 7, 4
+    steps = []
+    for t in range(T):
+        reset = (rng.uniform(size=n) < 0.4).astype(np.int64)
+        steps.append(dict(
+            obs0=rng.normal(size=(n, 2, 3, 52)).astype(np.float32),
+            obs=rng.normal(size=(n, 2, 3, 52)).astype(np.float32),
+            term_obs=rng.normal(size=(n, 2, 3, 52)).astype(np.float32),
+            rew=rng.normal(size=(n, 2, 3, 4)).astype(np.float32),
+            reset=reset, timeout=((rng.uniform(size=n) < 0.5) & (reset != 0)),
+            progress_f=rng.integers(1, 400, n).astype(np.float32)))
+    out = {"n": np.int64(n), "T": np.int64(T)}
+    for t, s in enumerate(steps):
+        for k, v in s.items():
+            out[f"in{t}_{k}"] = v
+    for name, cls, adim in (("sa", W.SingleAgent, 2), ("cma", W.CMA, 6), ("dma", W.DMA, 2)):
+        torch.manual_seed(5)
+        task = FakeTask(steps)
+        env = W.RecordEpisodeStatisticsTorch(_ExtractObs(cls(task)), "cpu")
+        nv = n * 3 if name == "dma" else n
+        env.num_envs = nv  # the PPO script sizes the statistics by args.num_envs (= 3*fields for dma)
+        o0 = env.reset()
+        out[f"{name}_obs0"] = o0.numpy()
+        for t in range(T):
+            act = torch.from_numpy(rng.uniform(-1, 1, (nv, adim)).astype(np.float32))
+            obs, reward, dones, infos = env.step(act)
+            out[f"{name}{t}_policy_action"] = act.numpy()
+            out[f"{name}{t}_stepped_actions"] = task.seen_actions[t]
+            out[f"{name}{t}_action_buf_after"] = _view_action_buf(env).clone().numpy()
+            out[f"{name}{t}_obs"] = obs.numpy().copy()
+            out[f"{name}{t}_reward"] = reward.numpy().copy()
+            out[f"{name}{t}_done"] = dones.numpy().copy()
+            out[f"{name}{t}_term_obs"] = infos["terminal_observation"].numpy().copy()
+            out[f"{name}{t}_rews"] = infos["rews"].numpy().copy()
+            out[f"{name}{t}_timeout"] = infos["time_outs"].numpy().copy()
+            out[f"{name}{t}_progress"] = infos["progress_buffer"].numpy().copy()
+            out[f"{name}{t}_ret_ret"] = env.returned_episode_returns.numpy().copy()
+            out[f"{name}{t}_ret_len"] = env.returned_episode_lengths.numpy().copy()
+            out[f"{name}{t}_ep_ret"] = env.episode_returns.numpy().copy()
+            out[f"{name}{t}_ep_len"] = env.episode_lengths.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "wrappers.npz"), **out)
+    print("wrappers.npz", len(out), "arrays")
+
+
+class _ExtractObs:
+    """ExtractObsWrapper (ppo...:167-169) over the gym shim."""
+
+    def __init__(self, env):
+        self.env = env
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.env, name)
+
+    def reset(self, **kw):
+        return self.env.reset(**kw)["obs"]
+
+    def step(self, a):
+        o, r, d, i = self.env.step(a)
+        return o["obs"], r, d, i
+
+
+def _view_action_buf(env):
+    e = env
+    while not hasattr(e, "action_buf") or "action_buf" not in vars(e):
+        e = e.env
+    return e.action_buf
+
+
+# ------------------------------------------------------------------ Agent (MLPs)
+def gen_agent():
+    sys.modules.setdefault("gym", _gym_shim())
+    src = _lines("ppo_continuous_action_isaacgym.py", 121, 164)
+    ns = dict(torch=torch, nn=torch.nn, np=np)
+    exec("from torch.distributions.normal import Normal\n" + src, ns)
+    out = {}
+    for name, adim in (("a2", 2),):
+        torch.manual_seed(3)
+        envs = types.SimpleNamespace(single_observation_space=types.SimpleNamespace(shape=(52,)),
+                                     single_action_space=types.SimpleNamespace(shape=(adim,)))
+        agent = ns["Agent"](envs)
+        with torch.no_grad():
+            agent.actor_logstd.copy_(torch.linspace(-0.5, 0.3, adim).view(1, adim))
+        x = torch.randn(40, 52)
+        action = torch.randn(40, adim)
+        _, logp, ent, value = agent.get_action_and_value(x, action)
+        mean = agent.actor_mean(x)
+        # one PPO-style scalar loss to pin the backward pass
+        adv = torch.randn(40)
+        ret = torch.randn(40)
+        loss = (-(adv * logp.exp())).mean() - 0.005 * ent.mean() + 4 * 0.5 * ((value.view(-1) - ret) ** 2).mean()
+        agent.zero_grad()
+        loss.backward()
+        for k, v in agent.state_dict().items():
+            out[f"{name}_sd_{k}"] = v.detach().numpy().copy()
+        for k, p in agent.named_parameters():
+            g = p.grad.detach().numpy()
+            out[f"{name}_gradnorm_{k}"] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+            if g.size <= 52 * 256:  # full gradients only for the small layers (keeps the fixture small)
+                out[f"{name}_grad_{k}"] = g.copy()
+        for k, v in dict(x=x, action=action, logp=logp, ent=ent, value=value, mean=mean, adv=adv, ret=ret,
+                         loss=loss).items():
+            out[f"{name}_{k}"] = v.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "agent.npz"), **out)
+    print("agent.npz", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    gen_jit(load_ref_jit())
+    gen_gae()
+    gen_wrappers()
+    gen_agent()
