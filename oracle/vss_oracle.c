@@ -496,19 +496,27 @@ static void substep(const phys_t* q, body_t* ball, body_t R[NB], const double ac
   /* B. ball */
   ball->vx *= q->ball_decay; ball->vy *= q->ball_decay;
   ball->x += ball->vx * q->h; ball->y += ball->vy * q->h;
-  /* C. pair contacts in fixed order: (ball, r0..r5), then robot pairs i<j */
-  const double br_reach = q->rb + q->H * 1.4142135623730951;
+  /* C. pair contacts. Broadphase flags are taken ONCE, from the positions right after
+   * integration; flagged pairs are then resolved in fixed order: (ball, r0..r5), then the
+   * robot pairs i<j in lexicographic order. */
+  const double br_reach = q->rb + q->H * 1.4142135623730951 + 0.005;
+  const double rr = q->H * 1.4142135623730951, wr = q->b + q->rwc;
+  const double rr_reach = 2.0 * (rr > wr ? rr : wr) + 0.01;
+  int near_ball[NB], near_pair[NB][NB];
   for (int k = 0; k < NB; ++k) {
     const double dx = ball->x - R[k].x, dy = ball->y - R[k].y;
-    if (dx * dx + dy * dy < br_reach * br_reach) ball_robot(q, ball, &R[k]);
+    near_ball[k] = dx * dx + dy * dy < br_reach * br_reach;
   }
-  const double rr = q->H * 1.4142135623730951, wr = q->b + q->rwc;
-  const double rr_reach = 2.0 * (rr > wr ? rr : wr);
   for (int i = 0; i < NB; ++i)
     for (int j = i + 1; j < NB; ++j) {
       const double dx = R[i].x - R[j].x, dy = R[i].y - R[j].y;
-      if (dx * dx + dy * dy < rr_reach * rr_reach) robot_robot(q, &R[i], &R[j]);
+      near_pair[i][j] = dx * dx + dy * dy < rr_reach * rr_reach;
     }
+  for (int k = 0; k < NB; ++k)
+    if (near_ball[k]) ball_robot(q, ball, &R[k]);
+  for (int i = 0; i < NB; ++i)
+    for (int j = i + 1; j < NB; ++j)
+      if (near_pair[i][j]) robot_robot(q, &R[i], &R[j]);
   /* D. robots vs walls, E. ball vs walls */
   for (int k = 0; k < NB; ++k) robot_walls(q, &R[k]);
   body_vs_walls(q, ball, 0.0, 0.0, q->rb, q->mu_bw, 2.5 * ball->invm);
@@ -724,6 +732,14 @@ ORC_API void orc_gae(const float* rewards, const float* values, const float* nex
       returns[i] = lastgaelam + values[i];
     }
   }
+}
+
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
 
 ORC_API int orc_num_threads(void) {

@@ -330,3 +330,7 @@ def view_outputs(view, obs, term_obs, rew, reset_buf, timeout, progress_f, actio
                            _p(out["rews"]), _p(out["reward"]), _p(out["done"]), _p(out["timeout"]),
                            _p(out["progress"]), _p(ep_ret), _p(ep_len), _p(ret_ret), _p(ret_len))
     return out
+
+
+def set_num_threads(n: int):
+    lib().orc_set_num_threads(C.c_int(int(n)))

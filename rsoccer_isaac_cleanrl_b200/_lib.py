@@ -1,0 +1,114 @@
+"""ctypes binding of libvss_b200.so (C-ABI declared in include/vss_b200.h).
+
+The library is built in-tree by `csrc/Makefile` (nvcc, sm_100a) so that it travels with the
+repo snapshot to the GPU box. Loading never falls back to anything else: a missing library
+or a missing B200 raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libvss_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+VIEW_SA, VIEW_CMA, VIEW_DMA = 0, 1, 2
+STATE_FLOATS, STATE_WORDS = 58, 60
+W_PROGRESS, W_EPISODE = 58, 59
+
+
+class VssParams(C.Structure):
+    """`vss_params` of include/vss_b200.h."""
+
+    _fields_ = [
+        ("dt", C.c_float), ("substeps", C.c_int32), ("max_episode_length", C.c_int32),
+        ("field_half_length", C.c_float), ("field_half_width", C.c_float),
+        ("goal_half_width", C.c_float), ("goal_depth", C.c_float),
+        ("ball_radius", C.c_float), ("ball_mass", C.c_float), ("ball_drag", C.c_float),
+        ("robot_half_size", C.c_float), ("robot_mass", C.c_float), ("robot_inertia", C.c_float),
+        ("wheel_radius", C.c_float), ("wheel_half_track", C.c_float), ("wheel_coll_radius", C.c_float),
+        ("max_wheel_rad_s", C.c_float), ("drive_damping", C.c_float), ("drive_max_torque", C.c_float),
+        ("wheel_inertia", C.c_float), ("mu_traction", C.c_float), ("mu_lateral", C.c_float),
+        ("gravity", C.c_float),
+        ("restitution", C.c_float), ("mu_ball_robot", C.c_float), ("mu_ball_wall", C.c_float),
+        ("mu_robot_wall", C.c_float),
+        ("reset_scale_x", C.c_float), ("reset_scale_y", C.c_float), ("min_placement_dist", C.c_float),
+        ("ball_reset_speed", C.c_float),
+        ("w_goal", C.c_float), ("w_grad", C.c_float), ("w_move", C.c_float), ("w_energy", C.c_float),
+        ("ou_theta", C.c_float), ("ou_sigma", C.c_float),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/vss_b200.h declares: name -> (restype, argtypes)
+_VP = C.c_void_p
+_SYMBOLS = {
+    "vss_default_params": (C.c_int, [C.POINTER(VssParams)]),
+    "vss_create": (C.c_int, [C.POINTER(_VP), C.POINTER(VssParams), C.c_int64, C.c_int64, C.c_int, C.c_uint64]),
+    "vss_destroy": (C.c_int, [_VP]),
+    "vss_num_envs": (C.c_int64, [_VP]),
+    "vss_state_ld": (C.c_int64, [_VP]),
+    "vss_set_reward_weights": (C.c_int, [_VP, C.POINTER(C.c_float)]),
+    "vss_reset_dones": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "vss_step": (C.c_int, [_VP] * 9),
+    "vss_step_injected": (C.c_int, [_VP] * 10),
+    "vss_step_view": (C.c_int, [_VP, C.c_int] + [_VP] * 15),
+    "vss_get_state": (C.c_int, [_VP, _VP, _VP]),
+    "vss_set_state": (C.c_int, [_VP, _VP, _VP]),
+    "vss_step_count": (C.c_uint64, [_VP]),
+    "vss_set_step_count": (C.c_int, [_VP, C.c_uint64]),
+    "vss_gae": (C.c_int, [_VP] * 7 + [C.c_int32, C.c_int64, C.c_double, C.c_double, _VP]),
+    "vss_philox4x32_10": (None, [_VP, _VP, _VP]),
+    "vss_last_error": (C.c_char_p, []),
+    "vss_version": (C.c_char_p, []),
+}
+
+
+def declared_symbols():
+    return sorted(_SYMBOLS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libvss_b200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("building libvss_b200.so failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """Load libvss_b200.so; raises if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension is not built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                "This package has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load_library().vss_last_error().decode()
+        raise RuntimeError(f"libvss_b200 error {rc}: {msg}")
+
+
+def default_params() -> VssParams:
+    p = VssParams()
+    check(load_library().vss_default_params(C.byref(p)))
+    return p

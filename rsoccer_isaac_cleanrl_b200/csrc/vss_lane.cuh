@@ -1,0 +1,743 @@
+// vss_lane.cuh — per-field ("lane") logic of the fused VSS step.
+//
+// One thread owns one field. Its 60 state words live in a shared-memory column
+// S[w * LDS] (LDS = 33: conflict-free both for "every lane reads its own column"
+// and for the cooperative row-major observation write). Everything here is plain
+// per-lane code with no warp collectives, so the same source also compiles for the
+// host (tests/emu) to check the logic without a GPU. The warp-cooperative parts
+// (coalesced obs writes, ballots) live in vss_step.cu.
+//
+// Reference behaviour replaced (file:line in the reference tree):
+//   pre_physics_step            envs/vss.py:180-187
+//   gym.simulate (PhysX)        new 2-D model, DESIGN.md §3 (scene spec vss.py:341-522)
+//   compute_rewards_and_dones   envs/vss.py:218-265, jit :578-655
+//   compute_obs                 envs/vss.py:530-575 (obs_entry table below)
+//   reset_dones                 envs/vss.py:267-333
+//   random_ou                   envs/wrappers.py:5-19
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/vss_b200.h"
+
+#if defined(__CUDACC__)
+#define VSS_HD __host__ __device__ __forceinline__
+#else
+#define VSS_HD inline
+#endif
+
+namespace vss {
+
+constexpr int LDS = 33;       // shared-memory column stride in words
+constexpr int W_PREV = 60;    // 14 words: ball xy, then robot xy x6, before physics
+constexpr int SM_WORDS = 74;  // words per field staged in shared memory
+constexpr int F4_PER_FIELD = VSS_OBS_PER_FIELD / 4;  // 78 float4 per (2,3,52) observation
+constexpr int F4_PER_ROW = VSS_NUM_OBS / 4;          // 13
+constexpr int RESET_MAX_ATTEMPTS = 64;
+
+// Constants derived once on the host (double precision) from vss_params.
+struct DevParams {
+  float h, H, rb, b, rw, rwc, inv_rw;
+  float kd_imp, tmax, wmax, fv, fw, dv_max, du_max, ball_decay;
+  float inv_mr, inv_ir, inv_mb, e1, mu_br, mu_bw, mu_rw;
+  float HL, HW, GH, GD, br_reach2, rr_reach2, wall_rej_x, wall_rej_y;
+  float reset_sx, reset_sy, min_d2, ball_speed;
+  float w_goal, w_grad, w_move, w_energy;
+  float ou_theta, ou_sigma;
+  int substeps, max_len;
+};
+
+inline DevParams derive_params(const vss_params& p) {
+  DevParams q;
+  const double h = (double)p.dt / (double)p.substeps, rw = p.wheel_radius, b = p.wheel_half_track;
+  const double jw_lin = (double)p.wheel_inertia / (rw * rw);
+  const double m_eff = p.robot_mass + 2.0 * jw_lin, i_eff = p.robot_inertia + 2.0 * jw_lin * b * b;
+  const double j_wheel_eq = 0.5 * m_eff * rw * rw;
+  const double sq2 = 1.4142135623730951, H = p.robot_half_size;
+  q.h = (float)h; q.H = (float)H; q.rb = p.ball_radius; q.b = (float)b; q.rw = (float)rw;
+  q.rwc = p.wheel_coll_radius; q.inv_rw = (float)(1.0 / rw);
+  q.kd_imp = (float)(p.drive_damping / (1.0 + h * p.drive_damping / j_wheel_eq));
+  q.tmax = p.drive_max_torque; q.wmax = p.max_wheel_rad_s;
+  q.fv = (float)(h / (rw * m_eff)); q.fw = (float)(b * h / (rw * i_eff));
+  q.dv_max = (float)((double)p.mu_traction * p.gravity * h);
+  q.du_max = (float)((double)p.mu_lateral * p.gravity * h);
+  q.ball_decay = (float)exp(-(double)p.ball_drag * h);
+  q.inv_mr = (float)(1.0 / p.robot_mass); q.inv_ir = (float)(1.0 / p.robot_inertia);
+  q.inv_mb = (float)(1.0 / p.ball_mass); q.e1 = 1.0f + p.restitution;
+  q.mu_br = p.mu_ball_robot; q.mu_bw = p.mu_ball_wall; q.mu_rw = p.mu_robot_wall;
+  q.HL = p.field_half_length; q.HW = p.field_half_width; q.GH = p.goal_half_width; q.GD = p.goal_depth;
+  const double br = p.ball_radius + H * sq2 + 0.005;
+  const double rr0 = H * sq2, wr0 = b + p.wheel_coll_radius;
+  const double rr = 2.0 * (rr0 > wr0 ? rr0 : wr0) + 0.01;
+  q.br_reach2 = (float)(br * br); q.rr_reach2 = (float)(rr * rr);
+  q.wall_rej_x = (float)(p.field_half_length - H * sq2); q.wall_rej_y = (float)(p.field_half_width - H * sq2);
+  q.reset_sx = p.reset_scale_x; q.reset_sy = p.reset_scale_y;
+  q.min_d2 = p.min_placement_dist * p.min_placement_dist; q.ball_speed = p.ball_reset_speed;
+  q.w_goal = p.w_goal; q.w_grad = p.w_grad; q.w_move = p.w_move; q.w_energy = p.w_energy;
+  q.ou_theta = p.ou_theta; q.ou_sigma = p.ou_sigma;
+  q.substeps = p.substeps; q.max_len = p.max_episode_length;
+  return q;
+}
+
+// ---- IEEE single ops that must not be contracted into FMAs (bit parity with the oracle) ----
+#if defined(__CUDA_ARCH__)
+VSS_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+VSS_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+VSS_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+VSS_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+VSS_HD float fsqrt(float a) { return __fsqrt_rn(a); }
+VSS_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+VSS_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+VSS_HD int ffs32(uint32_t m) { return __ffs((int)m); }
+VSS_HD uint32_t fbits(float f) { return __float_as_uint(f); }
+VSS_HD float bitsf(uint32_t u) { return __uint_as_float(u); }
+#else
+VSS_HD float fadd(float a, float b) { return a + b; }  // host build uses -ffp-contract=off
+VSS_HD float fsub(float a, float b) { return a - b; }
+VSS_HD float fmul(float a, float b) { return a * b; }
+VSS_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+VSS_HD float fsqrt(float a) { return sqrtf(a); }
+VSS_HD float fdiv(float a, float b) { return a / b; }
+VSS_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+VSS_HD int ffs32(uint32_t m) { return __builtin_ffs((int)m); }
+VSS_HD uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+VSS_HD float bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+#endif
+
+VSS_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+VSS_HD float sgnf(float v) { return v < 0.0f ? -1.0f : 1.0f; }
+
+// ---- Philox4x32-10 (Salmon et al. 2011) ----
+struct U4 { uint32_t x, y, z, w; };
+
+VSS_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+constexpr uint32_t STREAM_RESET_POS = 0, STREAM_RESET_MISC = 1, STREAM_OU = 2;
+
+struct RngKey { uint32_t seed_lo, seed_hi, gid_lo, gid_hi; };
+
+VSS_HD U4 rng_block(const RngKey& k, uint32_t a, uint32_t stream, uint32_t b) {
+  return philox4x32_10(U4{k.gid_lo, k.gid_hi, a, (stream << 28) | b}, k.seed_lo, k.seed_hi);
+}
+VSS_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+VSS_HD float u01_open(uint32_t x) { return (float)((x >> 8) + 1u) * (1.0f / 16777216.0f); }
+
+// ---- observation table: output element (team t, robot i, slot k) -> state word, sign ----
+// Layout restated from envs/vss.py:539-574. bit 7 = negate.
+constexpr uint32_t obs_entry(int t, int i, int k) {
+  int team = 0, robot = 0, f = 0, word = 0;
+  bool ball = false;
+  if (k < 4) { ball = true; word = k; f = 0; }
+  else if (k < 31) { const int m = (k - 4) / 9; f = (k - 4) % 9; team = t; robot = (i + m) % 3; }
+  else { const int m = (k - 31) / 7; f = (k - 31) % 7; team = 1 - t; robot = m; }
+  if (!ball) word = 4 + 9 * (team * 3 + robot) + f;
+  const bool neg = (t == 1) && (ball || f < 6);
+  return (uint32_t)word | (neg ? 0x80u : 0u);
+}
+struct ObsTable { uint32_t v[F4_PER_FIELD]; };
+constexpr ObsTable make_obs_table() {
+  ObsTable tab{};
+  for (int j = 0; j < F4_PER_FIELD; ++j) {
+    const int row = j / F4_PER_ROW, q = j % F4_PER_ROW, t = row / 3, i = row % 3;
+    uint32_t e = 0;
+    for (int c = 0; c < 4; ++c) e |= obs_entry(t, i, 4 * q + c) << (8 * c);
+    tab.v[j] = e;
+  }
+  return tab;
+}
+
+struct F4 { float x, y, z, w; };
+
+// One float4 of the observation of field column `e` of the tile whose staging area starts
+// at T (T = warp base, NOT lane-offset).
+VSS_HD F4 obs_gather(const float* T, uint32_t entry, int e) {
+  float v[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t by = (entry >> (8 * c)) & 0xFFu;
+    v[c] = bitsf(fbits(T[(by & 0x7Fu) * LDS + e]) ^ ((by >> 7) << 31));
+  }
+  return F4{v[0], v[1], v[2], v[3]};
+}
+
+// ---- rigid bodies -------------------------------------------------------------------
+struct Body { float x, y, vx, vy, c, s, w, invm, invi; };
+
+VSS_HD Body load_robot(const float* S, int r, const DevParams& P) {
+  const float* b = S + (4 + 9 * r) * LDS;
+  return Body{b[0], b[LDS], b[2 * LDS], b[3 * LDS], b[4 * LDS], b[5 * LDS], b[6 * LDS], P.inv_mr, P.inv_ir};
+}
+VSS_HD void store_robot(float* S, int r, const Body& B) {
+  float* b = S + (4 + 9 * r) * LDS;
+  b[0] = B.x; b[LDS] = B.y; b[2 * LDS] = B.vx; b[3 * LDS] = B.vy; b[4 * LDS] = B.c; b[5 * LDS] = B.s;
+  b[6 * LDS] = B.w;
+}
+VSS_HD Body load_ball(const float* S, const DevParams& P) {
+  return Body{S[0], S[LDS], S[2 * LDS], S[3 * LDS], 1.0f, 0.0f, 0.0f, P.inv_mb, 0.0f};
+}
+VSS_HD void store_ball(float* S, const Body& B) {
+  S[0] = B.x; S[LDS] = B.y; S[2 * LDS] = B.vx; S[3 * LDS] = B.vy;
+}
+VSS_HD Body static_body() { return Body{0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f}; }
+
+// Inelastic contact; unit normal n points from P to Q; cp = contact point (world).
+VSS_HD void resolve(Body& P, Body& Q, float nx, float ny, float depth, float cpx, float cpy, float e1,
+                    float mu, float kt_extra) {
+  const float rpx = cpx - P.x, rpy = cpy - P.y, rqx = cpx - Q.x, rqy = cpy - Q.y;
+  const float wsum = P.invm + Q.invm;
+  if (!(wsum > 0.0f)) return;
+  const float wp = P.invm / wsum, wq = Q.invm / wsum;
+  P.x -= nx * depth * wp; P.y -= ny * depth * wp;
+  Q.x += nx * depth * wq; Q.y += ny * depth * wq;
+  float vrx = (Q.vx - Q.w * rqy) - (P.vx - P.w * rpy);
+  float vry = (Q.vy + Q.w * rqx) - (P.vy + P.w * rpx);
+  const float vn = vrx * nx + vry * ny;
+  if (vn >= 0.0f) return;
+  const float rnp = rpx * ny - rpy * nx, rnq = rqx * ny - rqy * nx;
+  const float kn = wsum + rnp * rnp * P.invi + rnq * rnq * Q.invi;
+  const float jn = -e1 * vn / kn;
+  P.vx -= jn * nx * P.invm; P.vy -= jn * ny * P.invm; P.w -= jn * rnp * P.invi;
+  Q.vx += jn * nx * Q.invm; Q.vy += jn * ny * Q.invm; Q.w += jn * rnq * Q.invi;
+  if (mu > 0.0f) {
+    const float tx = -ny, ty = nx;
+    vrx = (Q.vx - Q.w * rqy) - (P.vx - P.w * rpy);
+    vry = (Q.vy + Q.w * rqx) - (P.vy + P.w * rpx);
+    const float vt = vrx * tx + vry * ty;
+    const float rtp = rpx * ty - rpy * tx, rtq = rqx * ty - rqy * tx;
+    const float kt = wsum + rtp * rtp * P.invi + rtq * rtq * Q.invi + kt_extra;
+    const float jt = clampf(-vt / kt, -mu * jn, mu * jn);
+    P.vx -= jt * tx * P.invm; P.vy -= jt * ty * P.invm; P.w -= jt * rtp * P.invi;
+    Q.vx += jt * tx * Q.invm; Q.vy += jt * ty * Q.invm; Q.w += jt * rtq * Q.invi;
+  }
+}
+
+struct Hit { bool hit; float nx, ny, depth, cpx, cpy; };
+
+// Circle (centre px,py, radius rho; rho = 0 -> point) against the oriented box of B.
+// Normal points out of B towards the circle.
+VSS_HD Hit circle_vs_box(const Body& B, float H, float px, float py, float rho) {
+  Hit r;
+  r.hit = false; r.nx = r.ny = r.depth = r.cpx = r.cpy = 0.0f;
+  const float dx = px - B.x, dy = py - B.y;
+  const float lx = dx * B.c + dy * B.s, ly = -dx * B.s + dy * B.c;
+  float nlx, nly, clx, cly;
+  if (fabsf(lx) < H && fabsf(ly) < H) {
+    const float pxd = H - fabsf(lx), pyd = H - fabsf(ly);
+    if (pxd < pyd) { nlx = sgnf(lx); nly = 0.0f; r.depth = pxd + rho; clx = sgnf(lx) * H; cly = ly; }
+    else { nlx = 0.0f; nly = sgnf(ly); r.depth = pyd + rho; clx = lx; cly = sgnf(ly) * H; }
+  } else {
+    const float qx = clampf(lx, -H, H), qy = clampf(ly, -H, H);
+    const float ex = lx - qx, ey = ly - qy;
+    const float d2 = ex * ex + ey * ey;
+    if (d2 >= rho * rho) return r;
+    const float d = sqrtf(d2);
+    nlx = ex / d; nly = ey / d; r.depth = rho - d; clx = qx; cly = qy;
+  }
+  r.hit = true;
+  r.nx = nlx * B.c - nly * B.s; r.ny = nlx * B.s + nly * B.c;
+  r.cpx = B.x + clx * B.c - cly * B.s; r.cpy = B.y + clx * B.s + cly * B.c;
+  return r;
+}
+
+VSS_HD void corner_xy(int k, float H, float& lx, float& ly) {
+  lx = (k == 0 || k == 3) ? H : -H;  // (+,+) (-,+) (-,-) (+,-)
+  ly = (k < 2) ? H : -H;
+}
+
+VSS_HD void ball_robot(float* S, int r, const DevParams& P) {
+  Body ball = load_ball(S, P), R = load_robot(S, r, P);
+  const Hit h = circle_vs_box(R, P.H, ball.x, ball.y, P.rb);
+  if (h.hit) {
+    resolve(R, ball, h.nx, h.ny, h.depth, h.cpx, h.cpy, P.e1, P.mu_br, 2.5f * P.inv_mb);
+    store_ball(S, ball);
+    store_robot(S, r, R);
+  }
+}
+
+// 12 features in fixed order: corners of A in B, corners of B in A, wheels of A, wheels of B.
+VSS_HD void robot_robot(float* S, int i, int j, const DevParams& P) {
+  Body A = load_robot(S, i, P), B = load_robot(S, j, P);
+  bool dirty = false;
+#pragma unroll 1
+  for (int k = 0; k < 12; ++k) {
+    const bool a_owns = (k < 8) ? (k < 4) : (k < 10);
+    float lx, ly, rho;
+    if (k < 8) { corner_xy(k & 3, P.H, lx, ly); rho = 0.0f; }
+    else { lx = 0.0f; ly = (k & 1) ? -P.b : P.b; rho = P.rwc; }
+    Body F = a_owns ? A : B;  // feature owner
+    Body G = a_owns ? B : A;  // box
+    const float px = F.x + lx * F.c - ly * F.s, py = F.y + lx * F.s + ly * F.c;
+    const Hit h = circle_vs_box(G, P.H, px, py, rho);
+    if (h.hit) {
+      resolve(G, F, h.nx, h.ny, h.depth, h.cpx, h.cpy, P.e1, 0.0f, 0.0f);
+      if (a_owns) { A = F; B = G; } else { B = F; A = G; }
+      dirty = true;
+    }
+  }
+  if (dirty) { store_robot(S, i, A); store_robot(S, j, B); }
+}
+
+// Point (rho = 0) or circle of body Q at local offset (lx,ly) against the static walls.
+// Three wall families, each resolved at once with the position re-evaluated.
+VSS_HD bool point_vs_walls(Body& Q, float lx, float ly, float rho, float mu, float kt_extra,
+                           const DevParams& P) {
+  bool any = false;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const float px = Q.x + lx * Q.c - ly * Q.s, py = Q.y + lx * Q.s + ly * Q.c;
+    const float ax = fabsf(px), ay = fabsf(py), sx = sgnf(px), sy = sgnf(py);
+    float nx = 0.0f, ny = 0.0f, depth = 0.0f;
+    bool hit = false;
+    if (pass == 0) {  // side walls y = +-HW
+      if (ay > P.HW - rho) { nx = 0.0f; ny = -sy; depth = ay - (P.HW - rho); hit = true; }
+    } else if (pass == 1) {  // end-wall blocks [HL,inf) x [GH,inf) in each quadrant
+      if (ax >= P.HL && ay >= P.GH) {
+        const float dx = ax - P.HL, dy = ay - P.GH;
+        if (dx < dy) { nx = -sx; ny = 0.0f; depth = dx + rho; }
+        else { nx = 0.0f; ny = -sy; depth = dy + rho; }
+        hit = true;
+      } else {
+        const float qx = fmaxf(ax, P.HL), qy = fmaxf(ay, P.GH);
+        const float ex = ax - qx, ey = ay - qy;
+        const float d2 = ex * ex + ey * ey;
+        if (d2 < rho * rho) {
+          const float d = sqrtf(d2);
+          nx = sx * ex / d; ny = sy * ey / d; depth = rho - d; hit = true;
+        }
+      }
+    } else {  // goal back wall x = +-(HL+GD)
+      if (ax > P.HL + P.GD - rho) { nx = -sx; ny = 0.0f; depth = ax - (P.HL + P.GD - rho); hit = true; }
+    }
+    if (hit) {
+      Body wall = static_body();
+      resolve(wall, Q, nx, ny, depth, px - nx * rho, py - ny * rho, P.e1, mu, kt_extra);
+      any = true;
+    }
+  }
+  return any;
+}
+
+VSS_HD void robot_walls(float* S, int r, const DevParams& P) {
+  const float* b = S + (4 + 9 * r) * LDS;
+  if (fabsf(b[0]) < P.wall_rej_x && fabsf(b[LDS]) < P.wall_rej_y) return;
+  Body R = load_robot(S, r, P);
+  bool dirty = false;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    float lx, ly;
+    corner_xy(k, P.H, lx, ly);
+    dirty |= point_vs_walls(R, lx, ly, 0.0f, P.mu_rw, 0.0f, P);
+  }
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {  // goal-post corners (+-HL, +-GH) against the box faces
+    float cx, cy;
+    corner_xy(k, 1.0f, cx, cy);
+    const Hit h = circle_vs_box(R, P.H, cx * P.HL, cy * P.GH, 0.0f);
+    if (h.hit) {
+      Body wall = static_body();
+      resolve(R, wall, h.nx, h.ny, h.depth, h.cpx, h.cpy, P.e1, P.mu_rw, 0.0f);
+      dirty = true;
+    }
+  }
+  if (dirty) store_robot(S, r, R);
+}
+
+// sin/cos of the small per-substep yaw increment
+VSS_HD void sincos_small(float a, float& sa, float& ca) {
+#if defined(__CUDA_ARCH__)
+  sincosf(a, &sa, &ca);
+#else
+  sa = sinf(a); ca = cosf(a);
+#endif
+}
+
+VSS_HD void substep_lane(float* S, const DevParams& P) {
+  // A. wheel drive + integration
+#pragma unroll 2
+  for (int r = 0; r < 6; ++r) {
+    float* b = S + (4 + 9 * r) * LDS;
+    float x = b[0], y = b[LDS], vx = b[2 * LDS], vy = b[3 * LDS], c = b[4 * LDS], s = b[5 * LDS];
+    float w = b[6 * LDS];
+    const float al = b[7 * LDS], ar = b[8 * LDS];
+    float v = vx * c + vy * s, u = -vx * s + vy * c;
+    const float wl = (v - w * P.b) * P.inv_rw, wr = (v + w * P.b) * P.inv_rw;
+    const float tl = clampf(P.kd_imp * (P.wmax * al - wl), -P.tmax, P.tmax);
+    const float tr = clampf(P.kd_imp * (P.wmax * ar - wr), -P.tmax, P.tmax);
+    v += clampf((tl + tr) * P.fv, -P.dv_max, P.dv_max);
+    w += (tr - tl) * P.fw;
+    u -= clampf(u, -P.du_max, P.du_max);
+    vx = v * c - u * s; vy = v * s + u * c;
+    x += vx * P.h; y += vy * P.h;
+    float sa, ca;
+    sincos_small(w * P.h, sa, ca);
+    const float c2 = c * ca - s * sa, s2 = s * ca + c * sa;
+    const float inv = 1.0f / sqrtf(c2 * c2 + s2 * s2);
+    b[0] = x; b[LDS] = y; b[2 * LDS] = vx; b[3 * LDS] = vy; b[4 * LDS] = c2 * inv; b[5 * LDS] = s2 * inv;
+    b[6 * LDS] = w;
+  }
+  // B. ball: exponential rolling drag
+  {
+    const float vx = S[2 * LDS] * P.ball_decay, vy = S[3 * LDS] * P.ball_decay;
+    S[2 * LDS] = vx; S[3 * LDS] = vy;
+    S[0] += vx * P.h; S[LDS] += vy * P.h;
+  }
+  // C. broadphase once, then flagged pairs in fixed order
+  uint32_t mask = 0;
+  {
+    const float bx = S[0], by = S[LDS];
+    float rx[6], ry[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { rx[r] = S[(4 + 9 * r) * LDS]; ry[r] = S[(5 + 9 * r) * LDS]; }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const float dx = bx - rx[r], dy = by - ry[r];
+      if (dx * dx + dy * dy < P.br_reach2) mask |= 1u << r;
+    }
+    int bit = 6;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 6; ++j) {
+        const float dx = rx[i] - rx[j], dy = ry[i] - ry[j];
+        if (dx * dx + dy * dy < P.rr_reach2) mask |= 1u << bit;
+        ++bit;
+      }
+  }
+  uint32_t mb = mask & 63u;
+  while (mb) {
+    const int r = ffs32(mb) - 1;
+    mb &= mb - 1;
+    ball_robot(S, r, P);
+  }
+  uint32_t mr = mask >> 6;
+  while (mr) {
+    const int p = ffs32(mr) - 1;
+    mr &= mr - 1;
+    // lexicographic pair index -> (i, j), 3 bits each
+    const uint64_t PI = 0x0 | (0ull << 0) | (0ull << 3) | (0ull << 6) | (0ull << 9) | (0ull << 12) | (1ull << 15) |
+                        (1ull << 18) | (1ull << 21) | (1ull << 24) | (2ull << 27) | (2ull << 30) | (2ull << 33) |
+                        (3ull << 36) | (3ull << 39) | (4ull << 42);
+    const uint64_t PJ = (1ull << 0) | (2ull << 3) | (3ull << 6) | (4ull << 9) | (5ull << 12) | (2ull << 15) |
+                        (3ull << 18) | (4ull << 21) | (5ull << 24) | (3ull << 27) | (4ull << 30) | (5ull << 33) |
+                        (4ull << 36) | (5ull << 39) | (5ull << 42);
+    robot_robot(S, (int)((PI >> (3 * p)) & 7), (int)((PJ >> (3 * p)) & 7), P);
+  }
+  // D. robots vs walls, E. ball vs walls
+#pragma unroll 1
+  for (int r = 0; r < 6; ++r) robot_walls(S, r, P);
+  {
+    Body ball = load_ball(S, P);
+    if (point_vs_walls(ball, 0.0f, 0.0f, P.rb, P.mu_bw, 2.5f * P.inv_mb, P)) store_ball(S, ball);
+  }
+}
+
+// ---- rewards and dones: envs/vss.py:218-265, 578-655 -----------------------------------
+VSS_HD float norm2(float x, float y) { return fsqrt(fadd(fmul(x, x), fmul(y, y))); }
+VSS_HD float ball_potential(float bx, float by, float gx) {
+  return fsub(norm2(fadd(bx, gx), by), norm2(fsub(bx, gx), by));
+}
+VSS_HD bool is_goal(float bx, float by, const DevParams& P) { return fabsf(bx) > P.HL && fabsf(by) < P.GH; }
+
+// rew[r*4 + c] for r = team*3 + idx. Uses the pre-physics positions staged at W_PREV.
+VSS_HD void rewards_lane(const float* S, const DevParams& P, float rew[VSS_REW_PER_FIELD]) {
+  const float bx = S[0], by = S[LDS], pbx = S[W_PREV * LDS], pby = S[(W_PREV + 1) * LDS];
+#pragma unroll
+  for (int k = 0; k < VSS_REW_PER_FIELD; ++k) rew[k] = 0.0f;
+  if (P.w_goal > 0.0f) {
+    const bool g = is_goal(bx, by, P);
+    // the reference's goal term is an int64 in {-1,0,1} (vss.py:589-594): no negative zero
+    float gv = 0.0f, gy = 0.0f;
+    if (g && bx > 0.0f) { gv = 1.0f; gy = -1.0f; }
+    if (g && bx < 0.0f) { gv = -1.0f; gy = 1.0f; }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) rew[4 * r + 0] = fmul(r < 3 ? gv : gy, P.w_goal);
+  }
+  if (P.w_grad > 0.0f) {
+    const float grad = fsub(ball_potential(bx, by, P.HL), ball_potential(pbx, pby, P.HL));
+#pragma unroll
+    for (int r = 0; r < 6; ++r) rew[4 * r + 1] = fmul(r < 3 ? grad : -grad, P.w_grad);
+  }
+  if (P.w_move > 0.0f) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const float px = S[(W_PREV + 2 + 2 * r) * LDS], py = S[(W_PREV + 3 + 2 * r) * LDS];
+      const float x = S[(4 + 9 * r) * LDS], y = S[(5 + 9 * r) * LDS];
+      const float p_dist = norm2(fsub(px, pbx), fsub(py, pby));
+      const float dist = norm2(fsub(x, bx), fsub(y, by));
+      rew[4 * r + 2] = fmul(fsub(p_dist, dist), P.w_move);
+    }
+  }
+  if (P.w_energy > 0.0f) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const float al = S[(11 + 9 * r) * LDS], ar = S[(12 + 9 * r) * LDS];
+      rew[4 * r + 3] = fmul(-fmul(fadd(fabsf(al), fabsf(ar)), 0.5f), P.w_energy);
+    }
+  }
+}
+
+// ---- masked reset of one field: envs/vss.py:267-333 ---------------------------------------
+VSS_HD void reset_lane(float* S, const DevParams& P, const RngKey& key) {
+  const uint32_t ep = fbits(S[VSS_W_EPISODE * LDS]);
+  float px[7], py[7];
+#pragma unroll 1
+  for (uint32_t attempt = 0; attempt < (uint32_t)RESET_MAX_ATTEMPTS; ++attempt) {
+    uint32_t u[16];
+#pragma unroll
+    for (uint32_t b = 0; b < 4; ++b) {
+      const U4 g = rng_block(key, ep, STREAM_RESET_POS, (attempt << 2) | b);
+      u[4 * b] = g.x; u[4 * b + 1] = g.y; u[4 * b + 2] = g.z; u[4 * b + 3] = g.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 7; ++e) {
+      px[e] = fmul(fsub(u01(u[2 * e]), 0.5f), P.reset_sx);
+      py[e] = fmul(fsub(u01(u[2 * e + 1]), 0.5f), P.reset_sy);
+    }
+    bool too_close = false;
+#pragma unroll
+    for (int a = 0; a < 7; ++a)
+#pragma unroll
+      for (int b = a + 1; b < 7; ++b) {
+        const float dx = fsub(px[a], px[b]), dy = fsub(py[a], py[b]);
+        too_close |= ffma(dy, dy, fmul(dx, dx)) < P.min_d2;
+      }
+    if (!too_close) break;
+  }
+  const U4 m0 = rng_block(key, ep, STREAM_RESET_MISC, 0), m1 = rng_block(key, ep, STREAM_RESET_MISC, 1);
+  const uint32_t m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+  S[0] = px[0]; S[LDS] = py[0];
+  S[2 * LDS] = fmul(fsub(u01(m[6]), 0.5f), P.ball_speed);
+  S[3 * LDS] = fmul(fsub(u01(m[7]), 0.5f), P.ball_speed);
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    float* b = S + (4 + 9 * r) * LDS;
+    const float yaw = fsub(fmul(u01(m[r]), 6.283185307179586f), 3.141592653589793f);
+    b[0] = px[1 + r]; b[LDS] = py[1 + r];
+    b[2 * LDS] = 0.0f; b[3 * LDS] = 0.0f;
+    b[4 * LDS] = cosf(yaw); b[5 * LDS] = sinf(yaw);
+    b[6 * LDS] = 0.0f; b[7 * LDS] = 0.0f; b[8 * LDS] = 0.0f;
+  }
+  S[VSS_W_EPISODE * LDS] = bitsf(ep + 1u);
+}
+
+// ---- OU noise on the 12 action slots of one field: envs/wrappers.py:5-19 -------------------
+VSS_HD void ou_lane(float a[VSS_ACT_PER_FIELD], const DevParams& P, const RngKey& key, uint32_t step) {
+#pragma unroll
+  for (uint32_t b = 0; b < 3; ++b) {
+    const U4 g = rng_block(key, step, STREAM_OU, b);
+    const uint32_t u[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float rad = fsqrt(fmul(-2.0f, logf(u01_open(u[2 * h]))));
+      const float ang = fmul(6.283185307179586f, u01(u[2 * h + 1]));
+      const float z[2] = {fmul(rad, cosf(ang)), fmul(rad, sinf(ang))};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float& v = a[4 * b + 2 * h + c];
+        v = clampf(fadd(fsub(v, fmul(P.ou_theta, v)), fmul(P.ou_sigma, z[c])), -1.0f, 1.0f);
+      }
+    }
+  }
+}
+
+
+// ---- 128-bit / 64-bit global accesses -------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+VSS_HD F4 ld4(const float* p) { const float4 v = *reinterpret_cast<const float4*>(p); return F4{v.x, v.y, v.z, v.w}; }
+VSS_HD void st4(float* p, const F4& v) { *reinterpret_cast<float4*>(p) = make_float4(v.x, v.y, v.z, v.w); }
+VSS_HD float ldg(const float* p) { return __ldg(p); }
+#else
+VSS_HD F4 ld4(const float* p) { return F4{p[0], p[1], p[2], p[3]}; }
+VSS_HD void st4(float* p, const F4& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
+VSS_HD float ldg(const float* p) { return *p; }
+#endif
+
+constexpr int VIEW_FULL = -1;
+
+struct StepArgs {
+  float* state; long long n, ld; unsigned long long goff;
+  uint32_t seed_lo, seed_hi, step;
+  const float* actions;        // full: (N,2,3,2)
+  const float* inject;         // injected post-physics state (58 x ld) or null
+  long long* reset_buf;        // (N) io
+  float* obs;                  // full: (N,2,3,52); view: (N',52)
+  float* term_obs;             // may be null
+  float* rew;                  // full: (N,2,3,4); view: rews_v (N',4)
+  uint8_t* timeout;            // (N) or (N')
+  float* progress_f;           // (N) or (N'), may be null
+  // view mode only
+  const float* policy_action; float* action_buf; float* reward_v; long long* done_v;
+  float* ep_ret; int* ep_len; float* ret_ret; int* ret_len;
+};
+
+template <int VIEW>
+struct ViewShape {
+  static constexpr int F4_PER = VIEW == VIEW_FULL ? F4_PER_FIELD : (VIEW == VSS_VIEW_DMA ? 3 * F4_PER_ROW : F4_PER_ROW);
+  static constexpr int AGENTS = VIEW == VSS_VIEW_DMA ? 3 : 1;  // view "envs" per field
+};
+
+VSS_HD RngKey make_key(const StepArgs& a, long long env) {
+  const unsigned long long gid = a.goff + (unsigned long long)env;
+  return RngKey{a.seed_lo, a.seed_hi, (uint32_t)gid, (uint32_t)(gid >> 32)};
+}
+
+VSS_HD void load_state(float* S, const float* state, long long ld, long long env) {
+  const float* src = state + env;
+#pragma unroll
+  for (int w = 0; w < VSS_STATE_WORDS; ++w) S[w * LDS] = ldg(src + (long long)w * ld);
+}
+VSS_HD void store_state(const float* S, float* state, long long ld, long long env) {
+  float* dst = state + env;
+#pragma unroll
+  for (int w = 0; w < VSS_STATE_WORDS; ++w) dst[(long long)w * ld] = S[w * LDS];
+}
+
+// Phase 1 of a step for one field: everything up to (not including) the observation write.
+// Returns the done flag of this step.
+template <int VIEW, bool INJECT>
+VSS_HD bool lane_phase1(float* S, long long env, const StepArgs& a, const DevParams& P, const RngKey& key) {
+  constexpr int AGENTS = ViewShape<VIEW>::AGENTS;
+  // 1a. state in: 60 coalesced loads in flight per lane
+  load_state(S, a.state, a.ld, env);
+  // 1b. actions (vss.py:180-187; wrappers.py:102-103)
+  float act[VSS_ACT_PER_FIELD];
+  {
+    const float* ap = (VIEW == VIEW_FULL ? a.actions : a.action_buf) + env * VSS_ACT_PER_FIELD;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const F4 v = ld4(ap + 4 * q);
+      act[4 * q] = v.x; act[4 * q + 1] = v.y; act[4 * q + 2] = v.z; act[4 * q + 3] = v.w;
+    }
+  }
+  if (VIEW != VIEW_FULL) {
+    ou_lane(act, P, key, a.step);  // action_buf = random_ou(action_buf)
+    if (VIEW == VSS_VIEW_SA) {     // act_view[:] = action
+      act[0] = a.policy_action[2 * env]; act[1] = a.policy_action[2 * env + 1];
+    } else {  // cma (N,6) and dma (3N,2): the same 6 contiguous floats per field
+#pragma unroll
+      for (int q = 0; q < 6; ++q) act[q] = a.policy_action[6 * env + q];
+    }
+    // the view keeps the un-clamped buffer (wrappers.py:102-103); done rows are zeroed in phase 5
+    float* ap = a.action_buf + env * VSS_ACT_PER_FIELD;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) st4(ap + 4 * q, F4{act[4 * q], act[4 * q + 1], act[4 * q + 2], act[4 * q + 3]});
+  }
+  int progress = (int)fbits(S[VSS_W_PROGRESS * LDS]);
+  if (a.reset_buf[env] != 0) progress = 0;  // flags of the previous step, vss.py:182-183
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {  // dof_velocity_buf[:] = clamp(actions), vss.py:184 + VecTask clip
+    S[(11 + 9 * r) * LDS] = clampf(act[2 * r], -1.0f, 1.0f);
+    S[(12 + 9 * r) * LDS] = clampf(act[2 * r + 1], -1.0f, 1.0f);
+  }
+  // prev_* clones, vss.py:219-220
+  S[W_PREV * LDS] = S[0]; S[(W_PREV + 1) * LDS] = S[LDS];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    S[(W_PREV + 2 + 2 * r) * LDS] = S[(4 + 9 * r) * LDS];
+    S[(W_PREV + 3 + 2 * r) * LDS] = S[(5 + 9 * r) * LDS];
+  }
+  // 1c. physics (replaces gym.simulate)
+  if (INJECT) {
+    const float* inj = a.inject + env;
+#pragma unroll
+    for (int w = 0; w < VSS_STATE_FLOATS; ++w) {
+      const bool is_act = w >= 4 && ((w - 4) % 9) >= 7;
+      if (!is_act) S[w * LDS] = ldg(inj + (long long)w * a.ld);
+    }
+  } else {
+#pragma unroll 1
+    for (int it = 0; it < P.substeps; ++it) substep_lane(S, P);
+  }
+  // 1d. post_physics_step: progress, rewards, dones (vss.py:189-193, 218-265)
+  progress += 1;
+  S[VSS_W_PROGRESS * LDS] = bitsf((uint32_t)progress);
+  float rew[VSS_REW_PER_FIELD];
+  rewards_lane(S, P, rew);
+  const bool done = is_goal(S[0], S[LDS], P) || progress >= P.max_len;
+  const bool tmo = done && progress >= P.max_len - 1;  // VecTask.step timeout_buf
+  a.reset_buf[env] = done ? 1 : 0;
+  if (VIEW == VIEW_FULL) {
+    float* rp = a.rew + env * VSS_REW_PER_FIELD;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) st4(rp + 4 * q, F4{rew[4 * q], rew[4 * q + 1], rew[4 * q + 2], rew[4 * q + 3]});
+    a.timeout[env] = tmo ? 1 : 0;
+    if (a.progress_f) a.progress_f[env] = (float)progress;
+  } else {
+#pragma unroll
+    for (int j = 0; j < AGENTS; ++j) {
+      const long long v = env * AGENTS + j;
+      float r4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (VIEW == VSS_VIEW_CMA) r4[c] = fdiv(fadd(fadd(rew[c], rew[4 + c]), rew[8 + c]), 3.0f);  // .mean(1)
+        else r4[c] = rew[4 * j + c];
+      }
+      st4(a.rew + 4 * v, F4{r4[0], r4[1], r4[2], r4[3]});
+      a.reward_v[v] = fadd(fadd(fadd(r4[0], r4[1]), r4[2]), r4[3]);
+      a.done_v[v] = done ? 1 : 0;
+      a.timeout[v] = tmo ? 1 : 0;
+      if (a.progress_f) a.progress_f[v] = (float)progress;
+      if (a.ep_ret) {  // RecordEpisodeStatisticsTorch.step, wrappers.py:68-75
+        const float keep = done ? 0.0f : 1.0f;
+        F4 er = ld4(a.ep_ret + 4 * v);
+        er = F4{fadd(er.x, r4[0]), fadd(er.y, r4[1]), fadd(er.z, r4[2]), fadd(er.w, r4[3])};
+        st4(a.ret_ret + 4 * v, er);
+        st4(a.ep_ret + 4 * v, F4{fmul(er.x, keep), fmul(er.y, keep), fmul(er.z, keep), fmul(er.w, keep)});
+        const int el = a.ep_len[v] + 1;
+        a.ret_len[v] = el;
+        a.ep_len[v] = done ? 0 : el;
+      }
+    }
+  }
+  return done;
+}
+
+// Phase 5: state out (+ zero the view's action buffer row of a done field, wrappers.py:105-107)
+template <int VIEW>
+VSS_HD void lane_phase5(const float* S, long long env, const StepArgs& a, bool done) {
+  store_state(S, a.state, a.ld, env);
+  if (VIEW != VIEW_FULL && done) {
+    float* ap = a.action_buf + env * VSS_ACT_PER_FIELD;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const F4 v = ld4(ap + 4 * q);  // `*= 0` keeps the sign of zero
+      st4(ap + 4 * q, F4{fmul(v.x, 0.0f), fmul(v.y, 0.0f), fmul(v.z, 0.0f), fmul(v.w, 0.0f)});
+    }
+  }
+}
+
+// Cooperative, coalesced observation write of one tile (all 32 lanes call it).
+//   per_field = float4 per field in this layout (78 full, 13 sa/cma, 39 dma)
+//   skip_mask = fields whose `ob` row is NOT written now (they are reset first)
+VSS_HD void write_obs_tile(const float* T, const uint32_t* tab, int lane, int valid, int per_field, float* tob,
+                           float* ob, uint32_t skip_mask) {
+  const int total = valid * per_field;
+#pragma unroll 4
+  for (int f = lane; f < total; f += 32) {
+    const int e = f / per_field, j = f - e * per_field;
+    const F4 v = obs_gather(T, tab[j], e);
+    if (tob) st4(tob + 4 * f, v);
+    if (!((skip_mask >> e) & 1u)) st4(ob + 4 * f, v);
+  }
+}
+
+VSS_HD void write_obs_fields(const float* T, const uint32_t* tab, int lane, int per_field, float* ob,
+                             uint32_t field_mask) {
+  while (field_mask) {
+    const int e = ffs32(field_mask) - 1;
+    field_mask &= field_mask - 1;
+    for (int j = lane; j < per_field; j += 32) st4(ob + 4 * (e * per_field + j), obs_gather(T, tab[j], e));
+  }
+}
+
+}  // namespace vss

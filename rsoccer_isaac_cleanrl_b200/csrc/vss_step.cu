@@ -1,0 +1,376 @@
+// vss_step.cu — the fused VSS env-step kernels for sm_100a and their C-ABI.
+//
+// One warp = one tile of 32 consecutive fields. Phase structure of a step:
+//   1. per lane : coalesced SoA load of the 60 state words into a shared-memory column,
+//                 actions / OU noise, physics substeps, rewards, dones, per-field outputs
+//   2. warp     : terminal observation (and the final observation of fields that are not
+//                 reset) written row-major with 128-bit fully coalesced stores, gathered
+//                 from the staged columns through a 78-entry permutation/sign table
+//   3. per lane : masked reset (Philox rejection sampling) of done fields
+//   4. warp     : observation rows of the fields that were reset
+//   5. per lane : coalesced SoA store of the state
+// HBM traffic per field-step (full VSS.step contract): 240 B state in + 240 B out, 48 B
+// actions, 8+8 B reset flags, 1248 B obs, 1248 B terminal obs, 96 B rewards, 5 B flags.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "vss_lane.cuh"
+
+namespace vss {
+
+__constant__ ObsTable c_obs_table = make_obs_table();
+
+constexpr int TAB_WORDS = 80;  // 78 table entries, padded
+template <int VIEW, bool INJECT>
+__global__ void __launch_bounds__(128)
+k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) {
+  extern __shared__ __align__(16) float smem[];
+  uint32_t* tab = reinterpret_cast<uint32_t*>(smem);
+  for (int i = threadIdx.x; i < F4_PER_FIELD; i += blockDim.x) tab[i] = c_obs_table.v[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long env0 = tile * 32;
+  if (env0 >= a.n) return;
+  float* T = smem + TAB_WORDS + warp * (SM_WORDS * LDS);
+  float* S = T + lane;
+  const long long env = env0 + lane;
+  const bool active = env < a.n;
+  const int valid = (int)min(32LL, a.n - env0);
+  constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
+  const RngKey key = make_key(a, env);
+  // 1. per lane: load, actions, physics, rewards, dones
+  bool done = false;
+  if (active) done = lane_phase1<VIEW, INJECT>(S, env, a, P, key);
+  __syncwarp();
+  // 2. terminal observation + observation of the fields that keep their state (vss.py:195-196)
+  const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
+  float* ob = a.obs + env0 * (PER_FIELD * 4);
+  float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
+  write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, done_mask);
+  __syncwarp();
+  // 3. masked reset (vss.py:202, 267-333)
+  if (done) reset_lane(S, P, key);
+  __syncwarp();
+  // 4. observation of the fields that were reset (vss.py:203)
+  write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask);
+  // 5. state out
+  if (active) lane_phase5<VIEW>(S, env, a, done);
+}
+
+// reset_dones() + compute_observations(): vss.py:72-73, 267-333, 205-216
+__global__ void __launch_bounds__(128)
+k_reset_dones(float* state, long long n, long long ld, unsigned long long goff, uint32_t seed_lo,
+              uint32_t seed_hi, const long long* reset_buf, float* obs, const __grid_constant__ DevParams P) {
+  extern __shared__ __align__(16) float smem[];
+  uint32_t* tab = reinterpret_cast<uint32_t*>(smem);
+  for (int i = threadIdx.x; i < F4_PER_FIELD; i += blockDim.x) tab[i] = c_obs_table.v[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long env0 = tile * 32;
+  if (env0 >= n) return;
+  float* T = smem + TAB_WORDS + warp * (SM_WORDS * LDS);
+  float* S = T + lane;
+  const long long env = env0 + lane;
+  const bool active = env < n;
+  const int valid = (int)min(32LL, n - env0);
+  bool flagged = false;
+  if (active) {
+    load_state(S, state, ld, env);
+    flagged = reset_buf[env] != 0;
+    if (flagged) {
+      const unsigned long long gid = goff + (unsigned long long)env;
+      reset_lane(S, P, RngKey{seed_lo, seed_hi, (uint32_t)gid, (uint32_t)(gid >> 32)});
+      store_state(S, state, ld, env);
+    }
+  }
+  __syncwarp();
+  if (obs) write_obs_tile(T, tab, lane, valid, F4_PER_FIELD, nullptr, obs + env0 * VSS_OBS_PER_FIELD, 0u);
+}
+
+// ----------------------------------------------------------------------------------------
+// GAE reverse scan: ppo_continuous_action_isaacgym.py:282-296. One thread per env column,
+// coalesced across envs, the T loop in registers, loads unrolled 8 deep ahead of the
+// (serial) recurrence. 28 B of HBM traffic per (t, env).
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_gae(const float* __restrict__ rewards, const float* __restrict__ values, const float* __restrict__ next_values,
+      const float* __restrict__ next_dones, const float* __restrict__ next_timeouts,
+      float* __restrict__ advantages, float* __restrict__ returns, int T, long long N, float gamma,
+      float gamma_lambda) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float last = 0.0f;
+  constexpr int U = 8;
+  int t = T - 1;
+  for (; t >= U - 1; t -= U) {
+    float r[U], v[U], nv[U], d[U], to[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long i = (long long)(t - k) * N + n;
+      r[k] = __ldg(rewards + i); v[k] = __ldg(values + i); nv[k] = __ldg(next_values + i);
+      d[k] = __ldg(next_dones + i); to[k] = __ldg(next_timeouts + i);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long i = (long long)(t - k) * N + n;
+      const float nnt = (d[k] != 0.0f && !(to[k] != 0.0f)) ? 0.0f : 1.0f;
+      const float delta = fsub(fadd(r[k], fmul(fmul(gamma, nv[k]), nnt)), v[k]);
+      last = fadd(delta, fmul(fmul(gamma_lambda, fsub(1.0f, d[k])), last));
+      advantages[i] = last;
+      returns[i] = fadd(last, v[k]);
+    }
+  }
+  for (; t >= 0; --t) {
+    const long long i = (long long)t * N + n;
+    const float d = next_dones[i], v = values[i];
+    const float nnt = (d != 0.0f && !(next_timeouts[i] != 0.0f)) ? 0.0f : 1.0f;
+    const float delta = fsub(fadd(rewards[i], fmul(fmul(gamma, next_values[i]), nnt)), v);
+    last = fadd(delta, fmul(fmul(gamma_lambda, fsub(1.0f, d)), last));
+    advantages[i] = last;
+    returns[i] = fadd(last, v);
+  }
+}
+
+}  // namespace vss
+
+// ========================================================================================
+// C-ABI
+// ========================================================================================
+using namespace vss;
+
+struct vss_engine {
+  int device;
+  int64_t n, ld, goff;
+  uint64_t seed;
+  uint64_t step_count;
+  vss_params params;
+  DevParams dp;
+  float* state;
+};
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  g_last_error = what;
+  if (e != cudaSuccess) { g_last_error += ": "; g_last_error += cudaGetErrorString(e); }
+  return code;
+}
+#define VSS_CUDA(call)                                        \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) return fail(VSS_E_CUDA, #call, e_); \
+  } while (0)
+
+static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* smem) {
+  const int64_t tiles = (n + 31) / 32;
+  int wpb = 4;
+  if (tiles < 148 * 2) wpb = 1;
+  else if (tiles < 148 * 8) wpb = 2;
+  *warps_per_block = wpb;
+  *grid = (unsigned)((tiles + wpb - 1) / wpb);
+  *smem = sizeof(float) * (TAB_WORDS + (size_t)wpb * SM_WORDS * LDS);
+  return 0;
+}
+
+static int use_device(vss_handle h) {
+  int cur = -1;
+  VSS_CUDA(cudaGetDevice(&cur));
+  if (cur != h->device) VSS_CUDA(cudaSetDevice(h->device));
+  return VSS_OK;
+}
+
+static StepArgs base_args(vss_handle h) {
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.state = h->state; a.n = h->n; a.ld = h->ld; a.goff = (unsigned long long)h->goff;
+  a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.step = (uint32_t)h->step_count;
+  return a;
+}
+
+template <int VIEW, bool INJECT>
+static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
+  int wpb; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem);
+  k_step<VIEW, INJECT><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
+  VSS_CUDA(cudaGetLastError());
+  h->step_count += 1;
+  return VSS_OK;
+}
+
+extern "C" {
+
+VSS_API const char* vss_last_error(void) { return g_last_error.c_str(); }
+VSS_API const char* vss_version(void) { return "vss_b200 0.1 (sm_100a)"; }
+
+VSS_API int vss_default_params(vss_params* p) {
+  if (!p) return fail(VSS_E_INVALID, "vss_default_params: null");
+  const double PI = 3.14159265358979323846;
+  p->dt = 0.05f; p->substeps = 4; p->max_episode_length = 400;
+  p->field_half_length = 0.75f; p->field_half_width = 0.65f; p->goal_half_width = 0.2f; p->goal_depth = 0.1f;
+  p->ball_radius = 0.02134f;
+  p->ball_mass = (float)(1130.0 * 4.0 / 3.0 * PI * 0.02134 * 0.02134 * 0.02134);
+  p->ball_drag = (float)(0.5 * 2.0 / 7.0);
+  p->robot_half_size = 0.035f; p->robot_mass = 0.44f;
+  p->robot_inertia = (float)(0.4 * (0.07 * 0.07 + 0.07 * 0.07) / 12.0 + 2.0 * 0.02 * 0.03375 * 0.03375);
+  p->wheel_radius = 0.024f; p->wheel_half_track = 0.03375f; p->wheel_coll_radius = 0.024f;
+  p->max_wheel_rad_s = 42.0f; p->drive_damping = 0.01f; p->drive_max_torque = 0.1f;
+  p->wheel_inertia = (float)(0.0002 + 0.4 * 0.02 * 0.024 * 0.024);
+  p->mu_traction = 0.7f; p->mu_lateral = 0.55f; p->gravity = 9.81f;
+  p->restitution = 0.0f; p->mu_ball_robot = 0.5f; p->mu_ball_wall = 1.0f; p->mu_robot_wall = 0.5f;
+  p->reset_scale_x = (float)(1.5 - 0.14); p->reset_scale_y = (float)(1.3 - 0.14);
+  p->min_placement_dist = 0.07f; p->ball_reset_speed = 1.0f;
+  p->w_goal = 10.0f; p->w_grad = 2.0f; p->w_move = 3.0f; p->w_energy = 0.0f;
+  p->ou_theta = 0.1f; p->ou_sigma = 0.15f;
+  return VSS_OK;
+}
+
+VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, int64_t global_env_offset,
+                       int device, uint64_t seed) {
+  if (!out || !p) return fail(VSS_E_INVALID, "vss_create: null argument");
+  if (num_envs <= 0) return fail(VSS_E_INVALID, "vss_create: num_envs must be > 0");
+  if (p->substeps < 0 || p->substeps > 64) return fail(VSS_E_INVALID, "vss_create: substeps out of range");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(VSS_E_NODEVICE, "vss_create: no CUDA device (this library has no CPU fallback)", e);
+  if (device < 0 || device >= count) return fail(VSS_E_INVALID, "vss_create: bad device index");
+  cudaDeviceProp prop;
+  VSS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(VSS_E_NODEVICE, "vss_create: kernels are built for sm_100a only (Blackwell B200)");
+  VSS_CUDA(cudaSetDevice(device));
+  vss_engine* h = new (std::nothrow) vss_engine();
+  if (!h) return fail(VSS_E_NOMEM, "vss_create: host allocation failed");
+  h->device = device; h->n = num_envs; h->ld = (num_envs + 31) / 32 * 32; h->goff = global_env_offset;
+  h->seed = seed; h->step_count = 0; h->params = *p; h->dp = derive_params(*p); h->state = nullptr;
+  const size_t bytes = sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld;
+  e = cudaMalloc(&h->state, bytes);
+  if (e != cudaSuccess) { delete h; return fail(VSS_E_NOMEM, "vss_create: cudaMalloc(state)", e); }
+  e = cudaMemset(h->state, 0, bytes);
+  if (e != cudaSuccess) { cudaFree(h->state); delete h; return fail(VSS_E_CUDA, "vss_create: cudaMemset", e); }
+  *out = h;
+  return VSS_OK;
+}
+
+VSS_API int vss_destroy(vss_handle h) {
+  if (!h) return VSS_OK;
+  cudaFree(h->state);
+  delete h;
+  return VSS_OK;
+}
+
+VSS_API int64_t vss_num_envs(vss_handle h) { return h ? h->n : 0; }
+VSS_API int64_t vss_state_ld(vss_handle h) { return h ? h->ld : 0; }
+VSS_API uint64_t vss_step_count(vss_handle h) { return h ? h->step_count : 0; }
+VSS_API int vss_set_step_count(vss_handle h, uint64_t n) {
+  if (!h) return fail(VSS_E_INVALID, "null handle");
+  h->step_count = n;
+  return VSS_OK;
+}
+
+VSS_API int vss_set_reward_weights(vss_handle h, const float w[4]) {
+  if (!h || !w) return fail(VSS_E_INVALID, "vss_set_reward_weights: null");
+  h->params.w_goal = w[0]; h->params.w_grad = w[1]; h->params.w_move = w[2]; h->params.w_energy = w[3];
+  h->dp.w_goal = w[0]; h->dp.w_grad = w[1]; h->dp.w_move = w[2]; h->dp.w_energy = w[3];
+  return VSS_OK;
+}
+
+VSS_API int vss_reset_dones(vss_handle h, const int64_t* reset_buf, float* obs, void* stream) {
+  if (!h || !reset_buf) return fail(VSS_E_INVALID, "vss_reset_dones: null argument");
+  if (int rc = use_device(h)) return rc;
+  int wpb; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem);
+  k_reset_dones<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(
+      h->state, h->n, h->ld, (unsigned long long)h->goff, (uint32_t)h->seed, (uint32_t)(h->seed >> 32),
+      reinterpret_cast<const long long*>(reset_buf), obs, h->dp);
+  VSS_CUDA(cudaGetLastError());
+  return VSS_OK;
+}
+
+VSS_API int vss_step(vss_handle h, const float* actions, int64_t* reset_buf, float* obs, float* term_obs,
+                     float* rew, uint8_t* timeout, float* progress_f, void* stream) {
+  if (!h || !actions || !reset_buf || !obs || !rew || !timeout)
+    return fail(VSS_E_INVALID, "vss_step: null argument");
+  if (int rc = use_device(h)) return rc;
+  StepArgs a = base_args(h);
+  a.actions = actions; a.reset_buf = reinterpret_cast<long long*>(reset_buf); a.obs = obs; a.term_obs = term_obs;
+  a.rew = rew; a.timeout = timeout; a.progress_f = progress_f;
+  return launch_step<VIEW_FULL, false>(h, a, stream);
+}
+
+VSS_API int vss_step_injected(vss_handle h, const float* actions, const float* post_state, int64_t* reset_buf,
+                              float* obs, float* term_obs, float* rew, uint8_t* timeout, float* progress_f,
+                              void* stream) {
+  if (!h || !actions || !post_state || !reset_buf || !obs || !rew || !timeout)
+    return fail(VSS_E_INVALID, "vss_step_injected: null argument");
+  if (int rc = use_device(h)) return rc;
+  StepArgs a = base_args(h);
+  a.actions = actions; a.inject = post_state; a.reset_buf = reinterpret_cast<long long*>(reset_buf); a.obs = obs;
+  a.term_obs = term_obs; a.rew = rew; a.timeout = timeout; a.progress_f = progress_f;
+  return launch_step<VIEW_FULL, true>(h, a, stream);
+}
+
+VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, float* action_buf,
+                          int64_t* reset_buf, float* obs_v, float* term_obs_v, float* rews_v, float* reward_v,
+                          int64_t* done_v, uint8_t* timeout_v, float* progress_v, float* ep_ret, int32_t* ep_len,
+                          float* ret_ret, int32_t* ret_len, void* stream) {
+  if (!h || !policy_action || !action_buf || !reset_buf || !obs_v || !rews_v || !reward_v || !done_v || !timeout_v)
+    return fail(VSS_E_INVALID, "vss_step_view: null argument");
+  if (ep_ret && (!ep_len || !ret_ret || !ret_len))
+    return fail(VSS_E_INVALID, "vss_step_view: episode statistics need all four buffers");
+  if (int rc = use_device(h)) return rc;
+  StepArgs a = base_args(h);
+  a.policy_action = policy_action; a.action_buf = action_buf; a.reset_buf = reinterpret_cast<long long*>(reset_buf);
+  a.obs = obs_v; a.term_obs = term_obs_v; a.rew = rews_v; a.reward_v = reward_v;
+  a.done_v = reinterpret_cast<long long*>(done_v); a.timeout = timeout_v; a.progress_f = progress_v;
+  a.ep_ret = ep_ret; a.ep_len = ep_len; a.ret_ret = ret_ret; a.ret_len = ret_len;
+  switch (view) {
+    case VSS_VIEW_SA: return launch_step<VSS_VIEW_SA, false>(h, a, stream);
+    case VSS_VIEW_CMA: return launch_step<VSS_VIEW_CMA, false>(h, a, stream);
+    case VSS_VIEW_DMA: return launch_step<VSS_VIEW_DMA, false>(h, a, stream);
+    default: return fail(VSS_E_INVALID, "vss_step_view: unknown view");
+  }
+}
+
+VSS_API int vss_get_state(vss_handle h, float* state_out, void* stream) {
+  if (!h || !state_out) return fail(VSS_E_INVALID, "vss_get_state: null argument");
+  if (int rc = use_device(h)) return rc;
+  VSS_CUDA(cudaMemcpyAsync(state_out, h->state, sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld,
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return VSS_OK;
+}
+
+VSS_API int vss_set_state(vss_handle h, const float* state_in, void* stream) {
+  if (!h || !state_in) return fail(VSS_E_INVALID, "vss_set_state: null argument");
+  if (int rc = use_device(h)) return rc;
+  VSS_CUDA(cudaMemcpyAsync(h->state, state_in, sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld,
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return VSS_OK;
+}
+
+VSS_API int vss_gae(const float* rewards, const float* values, const float* next_values, const float* next_dones,
+                    const float* next_timeouts, float* advantages, float* returns, int32_t T, int64_t N,
+                    double gamma, double gae_lambda, void* stream) {
+  if (!rewards || !values || !next_values || !next_dones || !next_timeouts || !advantages || !returns)
+    return fail(VSS_E_INVALID, "vss_gae: null argument");
+  if (T <= 0 || N <= 0) return fail(VSS_E_INVALID, "vss_gae: T and N must be > 0");
+  const unsigned grid = (unsigned)((N + 127) / 128);
+  k_gae<<<grid, 128, 0, (cudaStream_t)stream>>>(rewards, values, next_values, next_dones, next_timeouts,
+                                                advantages, returns, T, N, (float)gamma,
+                                                (float)(gamma * gae_lambda));
+  VSS_CUDA(cudaGetLastError());
+  return VSS_OK;
+}
+
+VSS_API void vss_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const U4 r = philox4x32_10(U4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+"""Thin torch-facing wrapper of the C-ABI: borrows torch CUDA buffers by pointer, launches on
+torch's current stream, owns nothing but the engine handle."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import VIEW_CMA, VIEW_DMA, VIEW_SA, check
+
+
+def _ptr(t, dtype, numel=None, name="tensor"):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    if numel is not None and t.numel() != numel:
+        raise ValueError(f"{name}: expected {numel} elements, got {t.numel()}")
+    return t.data_ptr()
+
+
+class Engine:
+    """One engine per device: SoA field state in HBM + the fused step kernels."""
+
+    def __init__(self, num_envs: int, device="cuda:0", seed: int = 0, global_env_offset: int = 0, params=None):
+        self.lib = _lib.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("rsoccer_isaac_cleanrl_b200 runs on a CUDA device only (no CPU fallback)")
+        self.params = params if params is not None else _lib.default_params()
+        self.num_envs = int(num_envs)
+        self._h = C.c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(self.lib.vss_create(C.byref(self._h), C.byref(self.params), self.num_envs, int(global_env_offset),
+                                  idx, int(seed) & 0xFFFFFFFFFFFFFFFF))
+        self.ld = int(self.lib.vss_state_ld(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.vss_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- parameters
+    def set_reward_weights(self, goal, grad, move, energy):
+        w = (C.c_float * 4)(float(goal), float(grad), float(move), float(energy))
+        check(self.lib.vss_set_reward_weights(self._h, w))
+
+    # ---- state access
+    def get_state(self):
+        out = torch.empty((_lib.STATE_WORDS, self.ld), dtype=torch.float32, device=self.device)
+        check(self.lib.vss_get_state(self._h, out.data_ptr(), self._stream()))
+        return out
+
+    def set_state(self, state):
+        check(self.lib.vss_set_state(self._h, _ptr(state, torch.float32, _lib.STATE_WORDS * self.ld, "state"),
+                                     self._stream()))
+
+    @property
+    def step_count(self):
+        return int(self.lib.vss_step_count(self._h))
+
+    @step_count.setter
+    def step_count(self, n):
+        check(self.lib.vss_set_step_count(self._h, int(n)))
+
+    # ---- hot path
+    def reset_dones(self, reset_buf, obs):
+        n = self.num_envs
+        check(self.lib.vss_reset_dones(self._h, _ptr(reset_buf, torch.int64, n, "reset_buf"),
+                                       _ptr(obs, torch.float32, n * 312, "obs"), self._stream()))
+
+    def step(self, actions, reset_buf, obs, term_obs, rew, timeout, progress_f, post_state=None):
+        n = self.num_envs
+        args = [_ptr(actions, torch.float32, n * 12, "actions")]
+        if post_state is not None:
+            args.append(_ptr(post_state, torch.float32, None, "post_state"))
+            if post_state.numel() < _lib.STATE_FLOATS * self.ld:
+                raise ValueError("post_state: expected at least 58 x ld floats")
+        args += [_ptr(reset_buf, torch.int64, n, "reset_buf"), _ptr(obs, torch.float32, n * 312, "obs"),
+                 _ptr(term_obs, torch.float32, n * 312, "term_obs"), _ptr(rew, torch.float32, n * 24, "rew"),
+                 _ptr(timeout, torch.uint8, n, "timeout"), _ptr(progress_f, torch.float32, n, "progress_f"),
+                 self._stream()]
+        fn = self.lib.vss_step if post_state is None else self.lib.vss_step_injected
+        check(fn(self._h, *args))
+
+    def step_view(self, view, policy_action, action_buf, reset_buf, obs_v, term_obs_v, rews_v, reward_v, done_v,
+                  timeout_v, progress_v, ep_ret=None, ep_len=None, ret_ret=None, ret_len=None):
+        n = self.num_envs
+        nv = n * 3 if view == VIEW_DMA else n
+        adim = 6 if view == VIEW_CMA else 2
+        check(self.lib.vss_step_view(
+            self._h, int(view), _ptr(policy_action, torch.float32, nv * adim, "policy_action"),
+            _ptr(action_buf, torch.float32, n * 12, "action_buf"), _ptr(reset_buf, torch.int64, n, "reset_buf"),
+            _ptr(obs_v, torch.float32, nv * 52, "obs_v"), _ptr(term_obs_v, torch.float32, nv * 52, "term_obs_v"),
+            _ptr(rews_v, torch.float32, nv * 4, "rews_v"), _ptr(reward_v, torch.float32, nv, "reward_v"),
+            _ptr(done_v, torch.int64, nv, "done_v"), _ptr(timeout_v, torch.uint8, nv, "timeout_v"),
+            _ptr(progress_v, torch.float32, nv, "progress_v"), _ptr(ep_ret, torch.float32, nv * 4, "ep_ret"),
+            _ptr(ep_len, torch.int32, nv, "ep_len"), _ptr(ret_ret, torch.float32, nv * 4, "ret_ret"),
+            _ptr(ret_len, torch.int32, nv, "ret_len"), self._stream()))
+
+
+def gae(rewards, values, next_values, next_dones, next_timeouts, gamma=0.99, gae_lambda=0.95, advantages=None,
+        returns=None):
+    """Reverse-scan GAE kernel (ppo_continuous_action_isaacgym.py:282-296). All (T,N) f32 CUDA."""
+    lib = _lib.load_library()
+    T, N = rewards.shape
+    if advantages is None:
+        advantages = torch.empty_like(rewards)
+    if returns is None:
+        returns = torch.empty_like(rewards)
+    k = T * N
+    check(lib.vss_gae(_ptr(rewards, torch.float32, k, "rewards"), _ptr(values, torch.float32, k, "values"),
+                      _ptr(next_values, torch.float32, k, "next_values"),
+                      _ptr(next_dones, torch.float32, k, "next_dones"),
+                      _ptr(next_timeouts, torch.float32, k, "next_timeouts"),
+                      _ptr(advantages, torch.float32, k, "advantages"), _ptr(returns, torch.float32, k, "returns"),
+                      int(T), int(N), float(gamma), float(gae_lambda),
+                      torch.cuda.current_stream(rewards.device).cuda_stream))
+    return advantages, returns

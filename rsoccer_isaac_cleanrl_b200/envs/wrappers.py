@@ -1,0 +1,225 @@
+"""Agent views — drop-ins for the reference's `envs/wrappers.py`.
+
+`SingleAgent`, `CMA`, `DMA`, `RecordEpisodeStatisticsTorch` and `make_env` keep the reference's
+names, constructor arguments and return conventions (envs/wrappers.py:21-180). Each view's
+`step()` is ONE kernel launch (`vss_step_view`): OU noise for the uncontrolled robots
+(wrappers.py:5-19), the policy-action overwrite, the env step, the view slicing / reward
+aggregation and the running episode statistics are fused; only the policy-visible 52-float rows
+are written to HBM (208 B per agent instead of 1248 B per field).
+"""
+import os
+
+import numpy as np
+import torch
+
+from .._lib import VIEW_CMA, VIEW_DMA, VIEW_SA
+from .spaces import Box, Wrapper
+
+
+def random_ou(prev):
+    """Ornstein-Uhlenbeck update of an action buffer (torch version, for callers such as team
+    policies that own their buffer; the views do this inside the step kernel)."""
+    ou_theta, ou_sigma = 0.1, 0.15
+    return torch.clamp(prev * (1.0 - ou_theta) + ou_sigma * torch.randn_like(prev), -1.0, 1.0)
+
+
+def make_env(args):
+    """(raw VSS task, agent view) for args.env_id in {'sa','cma','dma'} (wrappers.py:21-48).
+    `args.num_envs` counts AGENTS: for 'dma' it must be divisible by 3 and the task gets a third
+    as many fields. Under torchrun each rank builds its own shard of fields (global ids offset by
+    rank) on its own GPU."""
+    from .vss import VSS, load_cfg
+    cfg = load_cfg(getattr(args, "cfg_path", None))
+    assert args.cuda, "the VSS engine is CUDA-only"
+    cfg["env"]["numEnvs"] = args.num_envs
+    if args.env_id == "dma":
+        assert args.num_envs % 3 == 0
+        cfg["env"]["numEnvs"] = int(args.num_envs / 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = f"cuda:{local_rank}"
+    envs = VSS(cfg=cfg, rl_device=device, sim_device=device, graphics_device_id=0,
+               headless=not getattr(args, "capture_video", False),
+               virtual_screen_capture=getattr(args, "capture_video", False), force_render=False,
+               seed=getattr(args, "seed", 0), global_env_offset=rank * cfg["env"]["numEnvs"])
+    wrappers = {"sa": SingleAgent, "cma": CMA, "dma": DMA}
+    return envs, wrappers[args.env_id](envs)
+
+
+class _FusedView(Wrapper):
+    VIEW = None
+    AGENTS = 1   # view "envs" per field
+    ACT_DIM = 2
+
+    def __init__(self, env):
+        super().__init__(env)
+        task = env.unwrapped
+        self.task = task
+        n, dev = task.num_fields, task.device
+        nv = n * self.AGENTS
+        self.num_view_envs = nv
+        f32 = torch.float32
+        self._action_space = Box(-1.0, 1.0, (self.ACT_DIM,))
+        self._observation_space = Box(-np.inf, np.inf, (task.num_obs,))
+        self.action_buf = torch.zeros((n, 2, 3, 2), device=dev, dtype=f32)  # env.dof_velocity_buf.clone()
+        self._obs = torch.zeros((nv, task.num_obs), device=dev, dtype=f32)
+        self._term_obs = torch.zeros_like(self._obs)
+        self._rews = torch.zeros((nv, 4), device=dev, dtype=f32)
+        self._reward = torch.zeros(nv, device=dev, dtype=f32)
+        self._done = torch.zeros(nv, device=dev, dtype=torch.long)
+        self._timeout_u8 = torch.zeros(nv, device=dev, dtype=torch.uint8)
+        self._progress = torch.zeros(nv, device=dev, dtype=f32)
+        self.episode_returns = self.episode_lengths = None
+        self.returned_episode_returns = self.returned_episode_lengths = None
+        self._host = None
+
+    # ---- running episode statistics fused into the step epilogue (wrappers.py:50-87)
+    def enable_episode_stats(self):
+        nv, dev = self.num_view_envs, self.task.device
+        self.episode_returns = torch.zeros((nv, 4), dtype=torch.float32, device=dev)
+        self.episode_lengths = torch.zeros(nv, dtype=torch.int32, device=dev)
+        self.returned_episode_returns = torch.zeros((nv, 4), dtype=torch.float32, device=dev)
+        self.returned_episode_lengths = torch.zeros(nv, dtype=torch.int32, device=dev)
+
+    def _slice_obs(self, full):
+        raise NotImplementedError
+
+    def reset(self, **kwargs):
+        observations = self.env.reset(**kwargs)
+        return {"obs": self._slice_obs(observations["obs"])}
+
+    def step(self, action):
+        task = self.task
+        if action.device != task.device or action.dtype != torch.float32 or not action.is_contiguous():
+            action = action.to(task.device, torch.float32).contiguous()
+        task.engine.step_view(self.VIEW, action, self.action_buf, task.reset_buf, self._obs, self._term_obs,
+                              self._rews, self._reward, self._done, self._timeout_u8, self._progress,
+                              self.episode_returns, self.episode_lengths, self.returned_episode_returns,
+                              self.returned_episode_lengths)
+        task._obs_stale = True
+        infos = task.extras
+        infos["rews"] = self._rews
+        infos["terminal_observation"] = self._term_obs
+        infos["time_outs"] = self._timeout_u8.view(torch.bool)
+        infos["progress_buffer"] = self._progress
+        return {"obs": self._obs}, self._reward, self._done, infos
+
+    # ---- the same call with HOST buffers (pinned): action in, (obs, reward, done) out
+    def step_host(self, action_host):
+        if self._host is None:
+            nv = self.num_view_envs
+            self._host = dict(
+                act=torch.empty((nv, self.ACT_DIM), device=self.task.device, dtype=torch.float32),
+                obs=torch.empty((nv, self.task.num_obs), dtype=torch.float32).pin_memory(),
+                reward=torch.empty(nv, dtype=torch.float32).pin_memory(),
+                done=torch.empty(nv, dtype=torch.long).pin_memory())
+        h = self._host
+        h["act"].copy_(action_host.view(h["act"].shape), non_blocking=True)
+        obs, reward, done, _ = self.step(h["act"])
+        h["obs"].copy_(obs["obs"], non_blocking=True)
+        h["reward"].copy_(reward, non_blocking=True)
+        h["done"].copy_(done, non_blocking=True)
+        torch.cuda.current_stream(self.task.device).synchronize()
+        return h["obs"], h["reward"], h["done"]
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self.num_view_envs * self.ACT_DIM * 4
+
+    @property
+    def d2h_bytes_per_step(self):
+        return self.num_view_envs * (self.task.num_obs * 4 + 4 + 8)
+
+
+class SingleAgent(_FusedView):
+    """Controls blue robot 0; the other five follow OU noise (wrappers.py:89-115)."""
+    VIEW, AGENTS, ACT_DIM = VIEW_SA, 1, 2
+
+    @property
+    def act_view(self):
+        return self.action_buf[:, 0, 0, :]
+
+    def _slice_obs(self, full):
+        return full[:, 0, 0, :]
+
+
+class CMA(_FusedView):
+    """Centralised multi-agent: one 6-dim action drives blue robots 0-2, observing robot 0's view;
+    reward = mean over the three blue robots (wrappers.py:118-148)."""
+    VIEW, AGENTS, ACT_DIM = VIEW_CMA, 1, 6
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.num_envs = getattr(env, "num_envs", 1)
+        self.device = env.device
+
+    @property
+    def act_view(self):
+        return self.action_buf[:, 0, :, :].view(-1, 6)
+
+    def _slice_obs(self, full):
+        return full[:, 0, 0, :]
+
+
+class DMA(_FusedView):
+    """Decentralised multi-agent: blue robots 0-2 are three agents, field-major (wrappers.py:151-180)."""
+    VIEW, AGENTS, ACT_DIM = VIEW_DMA, 3, 2
+
+    def __init__(self, env):
+        super().__init__(env)
+        setattr(env.unwrapped, "num_environments", getattr(env, "num_envs", 1) * 3)
+
+    def _slice_obs(self, full):
+        return full[:, 0, :, :].reshape(-1, self.task.num_obs)
+
+
+def _find_fused(env):
+    e = env
+    while e is not None:
+        if isinstance(e, _FusedView):
+            return e
+        e = getattr(e, "env", None) if isinstance(e, Wrapper) else None
+    return None
+
+
+class RecordEpisodeStatisticsTorch(Wrapper):
+    """Per-env running sums of the 4 reward components and the episode length
+    (wrappers.py:50-87). Over a fused view the sums are maintained by the step kernel;
+    over any other env they are computed with torch ops."""
+
+    def __init__(self, env, device):
+        super().__init__(env)
+        self.num_envs = getattr(env, "num_envs", 1)
+        self.device = device
+        self._fused = _find_fused(env)
+        self.episode_returns = None
+        self.episode_lengths = None
+
+    def reset(self, **kwargs):
+        observations = super().reset(**kwargs)
+        if self._fused is not None:
+            v = self._fused
+            v.enable_episode_stats()
+            self.episode_returns, self.episode_lengths = v.episode_returns, v.episode_lengths
+            self.returned_episode_returns = v.returned_episode_returns
+            self.returned_episode_lengths = v.returned_episode_lengths
+            return observations
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=self.device)
+        self.episode_returns, self.episode_lengths = z((self.num_envs, 4), torch.float32), z(self.num_envs, torch.int32)
+        self.returned_episode_returns = z((self.num_envs, 4), torch.float32)
+        self.returned_episode_lengths = z(self.num_envs, torch.int32)
+        return observations
+
+    def step(self, action):
+        observations, rewards, dones, infos = super().step(action)
+        if self._fused is None:
+            self.episode_returns += infos["rews"]
+            self.episode_lengths += 1
+            self.returned_episode_returns[:] = self.episode_returns
+            self.returned_episode_lengths[:] = self.episode_lengths
+            self.episode_returns *= 1 - dones.unsqueeze(1)
+            self.episode_lengths *= 1 - dones
+        r = self.returned_episode_returns
+        infos["r"] = {"goal": r[:, 0], "grad": r[:, 1], "move": r[:, 2], "energy": r[:, 3], "return": r.sum(1)}
+        infos["l"] = self.returned_episode_lengths
+        return observations, rewards, dones, infos

@@ -1,0 +1,96 @@
+// vss_emu.cpp — TEST HARNESS: runs the product's per-lane step code (csrc/vss_lane.cuh,
+// the exact source the CUDA kernel compiles) on the host, one 32-field tile at a time, so the
+// step logic can be checked against the oracle in the GPU-less build container. The
+// orchestration below mirrors k_step / k_reset_dones in csrc/vss_step.cu (phases 1-5).
+// Not part of the product: libvss_b200.so has no host execution path.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../rsoccer_isaac_cleanrl_b200/csrc/vss_lane.cuh"
+
+using namespace vss;
+
+static const ObsTable g_tab = make_obs_table();
+
+template <int VIEW, bool INJECT>
+static void emu_step_t(const StepArgs& a, const DevParams& P) {
+  constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
+  const long long tiles = (a.n + 31) / 32;
+#pragma omp parallel for schedule(static)
+  for (long long tile = 0; tile < tiles; ++tile) {
+    std::vector<float> Tbuf(SM_WORDS * LDS, 0.0f);
+    float* T = Tbuf.data();
+    const long long env0 = tile * 32;
+    const int valid = (int)std::min(32LL, a.n - env0);
+    bool done[32] = {false};
+    uint32_t done_mask = 0;
+    for (int lane = 0; lane < valid; ++lane) {
+      done[lane] = lane_phase1<VIEW, INJECT>(T + lane, env0 + lane, a, P, make_key(a, env0 + lane));
+      if (done[lane]) done_mask |= 1u << lane;
+    }
+    float* ob = a.obs + env0 * (PER_FIELD * 4);
+    float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
+    for (int lane = 0; lane < 32; ++lane) write_obs_tile(T, g_tab.v, lane, valid, PER_FIELD, tob, ob, done_mask);
+    for (int lane = 0; lane < valid; ++lane)
+      if (done[lane]) reset_lane(T + lane, P, make_key(a, env0 + lane));
+    for (int lane = 0; lane < 32; ++lane) write_obs_fields(T, g_tab.v, lane, PER_FIELD, ob, done_mask);
+    for (int lane = 0; lane < valid; ++lane) lane_phase5<VIEW>(T + lane, env0 + lane, a, done[lane]);
+  }
+}
+
+extern "C" {
+
+__attribute__((visibility("default"))) int emu_step(
+    const vss_params* p, int view, float* state, long long n, long long ld, unsigned long long goff,
+    unsigned long long seed, unsigned int step, const float* actions, const float* inject, long long* reset_buf,
+    float* obs, float* term_obs, float* rew, uint8_t* timeout, float* progress_f, const float* policy_action,
+    float* action_buf, float* reward_v, long long* done_v, float* ep_ret, int* ep_len, float* ret_ret,
+    int* ret_len) {
+  const DevParams P = derive_params(*p);
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.state = state; a.n = n; a.ld = ld; a.goff = goff;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.step = step;
+  a.actions = actions; a.inject = inject; a.reset_buf = reset_buf; a.obs = obs; a.term_obs = term_obs;
+  a.rew = rew; a.timeout = timeout; a.progress_f = progress_f; a.policy_action = policy_action;
+  a.action_buf = action_buf; a.reward_v = reward_v; a.done_v = done_v; a.ep_ret = ep_ret; a.ep_len = ep_len;
+  a.ret_ret = ret_ret; a.ret_len = ret_len;
+  if (view == VIEW_FULL) { if (inject) emu_step_t<VIEW_FULL, true>(a, P); else emu_step_t<VIEW_FULL, false>(a, P); }
+  else if (view == VSS_VIEW_SA) emu_step_t<VSS_VIEW_SA, false>(a, P);
+  else if (view == VSS_VIEW_CMA) emu_step_t<VSS_VIEW_CMA, false>(a, P);
+  else if (view == VSS_VIEW_DMA) emu_step_t<VSS_VIEW_DMA, false>(a, P);
+  else return -1;
+  return 0;
+}
+
+__attribute__((visibility("default"))) int emu_reset_dones(const vss_params* p, float* state, long long n,
+                                                           long long ld, unsigned long long goff,
+                                                           unsigned long long seed, const long long* reset_buf,
+                                                           float* obs) {
+  const DevParams P = derive_params(*p);
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.goff = goff; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  const long long tiles = (n + 31) / 32;
+  for (long long tile = 0; tile < tiles; ++tile) {
+    std::vector<float> Tbuf(SM_WORDS * LDS, 0.0f);
+    float* T = Tbuf.data();
+    const long long env0 = tile * 32;
+    const int valid = (int)std::min(32LL, n - env0);
+    for (int lane = 0; lane < valid; ++lane) {
+      load_state(T + lane, state, ld, env0 + lane);
+      if (reset_buf[env0 + lane] != 0) {
+        reset_lane(T + lane, P, make_key(a, env0 + lane));
+        store_state(T + lane, state, ld, env0 + lane);
+      }
+    }
+    if (obs)
+      for (int lane = 0; lane < 32; ++lane)
+        write_obs_tile(T, g_tab.v, lane, valid, F4_PER_FIELD, nullptr, obs + env0 * VSS_OBS_PER_FIELD, 0u);
+  }
+  return 0;
+}
+
+}  // extern "C"

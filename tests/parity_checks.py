@@ -1,0 +1,314 @@
+"""Parity checks shared by the CPU (emu backend) and GPU (C-ABI backend) test files.
+
+Tolerances (stated once, used everywhere):
+  * integer / index / flag outputs (reset, timeout, progress, done, episode lengths): exact.
+  * observations: every slot is a signed copy of a state word -> compared as raw bits,
+    including the sign of zero; the cos/sin slots of freshly reset robots differ between
+    glibc and CUDA libm -> atol 1e-6 there.
+  * rewards: the CUDA side issues the same IEEE fp32 operation sequence as the oracle
+    (no FMA contraction) -> bit-exact given identical states.
+  * physics (float32 kernel vs float64 oracle of the same model): |a-b| <= 2e-5 + 1e-4|b|
+    per control step; a contact test that flips on a last-bit difference changes a velocity
+    discontinuously, so up to 0.5 % of the fields may exceed it ("branch flips").
+"""
+import numpy as np
+
+from oracle import vss_oracle as orc
+
+TRIG = np.zeros(52, bool)
+for _base in (4, 13, 22, 31, 38, 45):
+    TRIG[_base + 4:_base + 6] = True
+
+PHYS_ATOL, PHYS_RTOL, FLIP_FRACTION = 2e-5, 1e-4, 0.005
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_bits_equal(a, b, what):
+    a, b = bits(a), bits(b)
+    bad = np.argwhere(a != b)
+    assert bad.size == 0, f"{what}: {len(bad)} words differ, first at {bad[:5].tolist()}"
+
+
+def assert_obs_equal(a, b, what, trig_atol=0.0):
+    """(…,52) observations: non-trig slots bitwise; trig slots bitwise or within trig_atol."""
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert_bits_equal(a[..., ~TRIG], b[..., ~TRIG], what + " (copy slots)")
+    if trig_atol == 0.0:
+        assert_bits_equal(a[..., TRIG], b[..., TRIG], what + " (cos/sin slots)")
+    else:
+        np.testing.assert_allclose(a[..., TRIG], b[..., TRIG], rtol=0, atol=trig_atol, err_msg=what)
+
+
+def oracle_from_backend(be):
+    return orc.State.from_soa(be.get_state(), be.n)
+
+
+def make_backend_pair(Backend, n, seed, goff, **kw):
+    p = orc.default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    be = Backend(n, seed=seed, goff=goff, params=p)
+    return be, p
+
+
+# --------------------------------------------------------------------------- reset
+def check_reset(Backend, n=1000, seed=123, goff=5000):
+    be, p = make_backend_pair(Backend, n, seed, goff)
+    ones = np.ones(n, np.int64)
+    obs = be.reset_dones(ones)
+    st = orc.State(n)
+    orc.reset_dones(p, seed, goff, st, ones)
+    got = orc.State.from_soa(be.get_state(), n)
+    assert_bits_equal(got.ball_pos, st.ball_pos, "reset ball_pos")
+    assert_bits_equal(got.ball_vel, st.ball_vel, "reset ball_vel")
+    assert_bits_equal(got.r_pos, st.r_pos, "reset r_pos")
+    assert_bits_equal(got.r_vel, st.r_vel, "reset r_vel")
+    assert_bits_equal(got.r_w, st.r_w, "reset r_w")
+    assert_bits_equal(got.r_act, st.r_act, "reset r_act")
+    np.testing.assert_allclose(got.r_rot, st.r_rot, rtol=0, atol=1e-6)
+    assert np.array_equal(got.episode, st.episode) and np.all(got.episode == 1)
+    assert np.array_equal(got.progress, st.progress)
+    ref_obs = orc.compute_obs(st.ball_pos, st.ball_vel, st.r_pos, st.r_vel, st.r_rot, st.r_w, st.r_act)
+    assert_obs_equal(obs, ref_obs, "reset obs", trig_atol=1e-6)
+    # distribution facts of envs/vss.py:267-327
+    ent = np.concatenate([got.ball_pos[:, None, :], got.r_pos.reshape(n, 6, 2)], 1)
+    d = np.linalg.norm(ent[:, :, None, :] - ent[:, None, :, :], axis=-1) + np.eye(7) * 10
+    assert d.min() >= 0.07 - 1e-6
+    assert np.abs(ent[..., 0]).max() <= 1.36 / 2 and np.abs(ent[..., 1]).max() <= 1.16 / 2
+    assert np.abs(got.ball_vel).max() <= 0.5
+    np.testing.assert_allclose(np.linalg.norm(got.r_rot, axis=-1), 1.0, atol=1e-6)
+    # a second masked reset only touches flagged fields and advances their episode counter
+    mask = (np.arange(n) % 3 == 0).astype(np.int64)
+    before = be.get_state()
+    be.reset_dones(mask)
+    after = be.get_state()
+    keep = mask == 0
+    assert np.array_equal(before.view(np.uint32)[:, :n][:, keep], after.view(np.uint32)[:, :n][:, keep])
+    assert np.all(after.view(np.uint32)[59, :n][~keep] == 2)
+    orc.reset_dones(p, seed, goff, st, mask)
+    assert_bits_equal(orc.State.from_soa(after, n).r_pos, st.r_pos, "second reset r_pos")
+    return be, p
+
+
+# --------------------------------------------------------------------------- full step
+def stage_interesting_state(be, rng):
+    """After a reset, push some fields towards timeouts, goals and contacts."""
+    n = be.n
+    s = be.get_state()
+    prog = s.view(np.int32)[58]
+    prog[:n] = rng.integers(0, 390, n)
+    k = min(n, 48)
+    prog[:k] = 396 + (np.arange(k) % 4)                 # timeouts within a few steps
+    g = slice(k, min(n, 2 * k))
+    m = s[:, g].shape[1]
+    s[0, g] = np.where(np.arange(m) % 2 == 0, 0.72, -0.72)      # ball near a goal mouth, moving in
+    s[1, g] = rng.uniform(-0.15, 0.15, m)
+    s[2, g] = np.where(np.arange(m) % 2 == 0, 1.0, -1.0) * rng.uniform(0.3, 1.5, m)
+    s[3, g] = rng.uniform(-0.2, 0.2, m)
+    c = slice(min(n, 2 * k), min(n, 3 * k))                      # robots packed around the ball
+    m = s[:, c].shape[1]
+    for r in range(6):
+        s[4 + 9 * r, c] = s[0, c] + rng.uniform(-0.09, 0.09, m)
+        s[5 + 9 * r, c] = s[1, c] + rng.uniform(-0.09, 0.09, m)
+        s[6 + 9 * r, c] = rng.uniform(-1, 1, m)
+        s[7 + 9 * r, c] = rng.uniform(-1, 1, m)
+    w = slice(min(n, 3 * k), min(n, 4 * k))                      # robots and ball against the walls
+    m = s[:, w].shape[1]
+    s[0, w] = rng.uniform(-0.7, 0.7, m); s[1, w] = np.where(np.arange(m) % 2 == 0, 0.62, -0.62)
+    s[3, w] = np.where(np.arange(m) % 2 == 0, 1.0, -1.0)
+    for r in range(6):
+        s[4 + 9 * r, w] = np.where(np.arange(m) % 2 == 0, 0.72, -0.72) * rng.uniform(0.9, 1.0, m)
+        s[5 + 9 * r, w] = rng.uniform(-0.6, 0.6, m)
+        s[6 + 9 * r, w] = np.where(np.arange(m) % 2 == 0, 1.0, -1.0)
+    be.set_state(s)
+
+
+def compare_full_step(out, ref, rb, rb_ref, n, what, exact_physics):
+    """out/ref: dicts of a backend step and an oracle step from the SAME input state."""
+    if exact_physics:
+        assert np.array_equal(rb, rb_ref), what + " reset_buf"
+        assert np.array_equal(out["timeout"], ref["timeout"]), what + " timeout"
+        assert np.array_equal(out["progress_f"], ref["progress_f"]), what + " progress"
+        assert_bits_equal(out["rew"], ref["rew"], what + " rew")
+        assert_obs_equal(out["term_obs"], ref["term_obs"], what + " term_obs")
+        keep = rb == 0
+        assert_obs_equal(out["obs"][keep], ref["obs"][keep], what + " obs (kept)")
+        assert_obs_equal(out["obs"][~keep], ref["obs"][~keep], what + " obs (reset)", trig_atol=1e-6)
+        return 0
+    assert np.array_equal(out["progress_f"], ref["progress_f"]), what + " progress"
+    tol = lambda a, b: np.abs(a - b) <= PHYS_ATOL + PHYS_RTOL * np.abs(b)
+    ok_t = tol(out["term_obs"], ref["term_obs"]).reshape(n, -1).all(1)
+    # rewards are differences of positions: same tolerance scaled by the largest weight (10 for goal is
+    # integer-valued; grad/move weights 2 and 3)
+    ok_r = (np.abs(out["rew"] - ref["rew"]) <= 3 * (PHYS_ATOL + PHYS_RTOL * np.abs(ref["rew"]))).reshape(n, -1).all(1)
+    same_done = rb == rb_ref
+    good = ok_t & ok_r & same_done & (out["timeout"] == ref["timeout"])
+    # fields that agree on the reset decision and were reset must agree on the new state
+    both = good & (rb != 0)
+    if both.any():
+        assert_obs_equal(out["obs"][both], ref["obs"][both], what + " obs after reset", trig_atol=1e-6)
+    kept = good & (rb == 0)
+    assert np.array_equal(bits(out["obs"][kept]), bits(out["term_obs"][kept])), what + " obs == term_obs when kept"
+    return int((~good).sum())
+
+
+def check_rollout(Backend, n=777, steps=40, seed=7, goff=1 << 33, exact_after=False, **params):
+    """Random-action rollout; every step the oracle is re-seeded with the backend's state so
+    single-step errors do not compound (chaotic contacts), and outputs are compared."""
+    be, p = make_backend_pair(Backend, n, seed, goff, **params)
+    rng = np.random.default_rng(seed)
+    rb = np.ones(n, np.int64)
+    be.reset_dones(rb)
+    rb[:] = 0  # as if one step had passed: otherwise pre_physics_step zeroes every progress counter
+    stage_interesting_state(be, rng)
+    flips = dones = timeouts = goals = 0
+    for t in range(steps):
+        st = oracle_from_backend(be)
+        rb_ref = rb.copy()
+        actions = rng.uniform(-1.3, 1.3, (n, 2, 3, 2)).astype(np.float32)  # exercises the +-1 clamp
+        out = be.step(actions, rb)
+        ref = orc.step(p, seed, goff, st, actions, rb_ref)
+        flips += compare_full_step(out, ref, rb, rb_ref, n, f"step {t}", exact_physics=False)
+        dones += int(rb.sum()); timeouts += int(out["timeout"].sum())
+        goals += int((np.abs(out["rew"][:, 0, 0, 0]) > 0).sum())
+        # invariants: nothing leaves the field box, unit headings
+        got = oracle_from_backend(be)
+        assert np.abs(got.ball_pos[:, 0]).max() <= 0.85 + 1e-5 and np.abs(got.ball_pos[:, 1]).max() <= 0.65 + 1e-5
+        assert np.abs(got.r_pos[..., 0]).max() <= 0.86 and np.abs(got.r_pos[..., 1]).max() <= 0.66
+        np.testing.assert_allclose(np.linalg.norm(got.r_rot, axis=-1), 1.0, atol=2e-6)
+    assert dones > 0 and timeouts > 0 and goals > 0, (dones, timeouts, goals)
+    assert flips <= max(2, FLIP_FRACTION * n * steps), f"{flips} field-steps outside the physics tolerance"
+    return dict(flips=flips, dones=dones, timeouts=timeouts, goals=goals)
+
+
+def random_post_state(rng, n, ld):
+    s = np.zeros((58, ld), np.float32)
+    s[0, :n] = rng.uniform(-0.85, 0.85, n); s[1, :n] = rng.uniform(-0.65, 0.65, n)
+    s[2:4, :n] = rng.uniform(-1.5, 1.5, (2, n))
+    for r in range(6):
+        b = 4 + 9 * r
+        s[b, :n] = rng.uniform(-0.85, 0.85, n); s[b + 1, :n] = rng.uniform(-0.65, 0.65, n)
+        s[b + 2:b + 4, :n] = rng.uniform(-1.2, 1.2, (2, n))
+        yaw = rng.uniform(-np.pi, np.pi, n)
+        s[b + 4, :n] = np.cos(yaw); s[b + 5, :n] = np.sin(yaw)
+        s[b + 6, :n] = rng.uniform(-30, 30, n)
+    return s
+
+
+def check_injected(Backend, n=500, steps=6, seed=99, goff=12345, **params):
+    """Identical input states: physics replaced by an injected post-physics state on both sides.
+    Everything (rewards, dones, timeouts, progress, obs, terminal obs, masked reset) must agree."""
+    be, p = make_backend_pair(Backend, n, seed, goff, **params)
+    rng = np.random.default_rng(seed)
+    rb = np.ones(n, np.int64)
+    be.reset_dones(rb)
+    rb[:] = 0
+    rb[::7] = 1  # some fields still flagged from "the previous step": their progress restarts at 0
+    s = be.get_state()
+    s.view(np.int32)[58, :n] = rng.integers(380, 400, n)  # many timeouts
+    be.set_state(s)
+    ndone = 0
+    for t in range(steps):
+        st = oracle_from_backend(be)
+        rb_ref = rb.copy()
+        actions = rng.uniform(-1.3, 1.3, (n, 2, 3, 2)).astype(np.float32)
+        post = random_post_state(rng, n, be.ld)
+        post[0, :8] = [0.8, -0.8, 0.75, 0.76, -0.7500001, 0.0, 0.8, -0.76]   # goal edge cases
+        post[1, :8] = [0.05, -0.19, 0.0, 0.2, 0.1, 0.0, 0.3, 0.199]
+        out = be.step(actions, rb, post_state=post)
+        ref = orc.step(p, seed, goff, st, actions, rb_ref, post_state=post)
+        compare_full_step(out, ref, rb, rb_ref, n, f"injected step {t}", exact_physics=True)
+        got, want = oracle_from_backend(be), st
+        assert np.array_equal(got.progress, want.progress) and np.array_equal(got.episode, want.episode)
+        ndone += int(rb.sum())
+    assert ndone > 0
+    return ndone
+
+
+def check_views(Backend, view, n=333, steps=12, seed=5, goff=777):
+    be, p = make_backend_pair(Backend, n, seed, goff)
+    rng = np.random.default_rng(seed + view)
+    nv = n * 3 if view == orc.VIEW_DMA else n
+    adim = 6 if view == orc.VIEW_CMA else 2
+    rb = np.ones(n, np.int64)
+    be.reset_dones(rb)
+    rb[:] = 0
+    stage_interesting_state(be, rng)
+    abuf = np.zeros((n, 2, 3, 2), np.float32)
+    ep_ret, ep_len = np.zeros((nv, 4), np.float32), np.zeros((nv,), np.int32)
+    flips = 0
+    for t in range(steps):
+        st = oracle_from_backend(be)
+        rb_ref, abuf_ref, er_ref, el_ref = rb.copy(), abuf.copy(), ep_ret.copy(), ep_len.copy()
+        pa = rng.uniform(-1.2, 1.2, (nv, adim)).astype(np.float32)
+        step_index = be.step_count
+        out = be.step_view(view, pa, abuf, rb, ep_ret, ep_len)
+        ref = orc.step_view(p, seed, goff, step_index, st, view, pa, abuf_ref, rb_ref, er_ref, el_ref)
+        # the OU noise stream: same Philox counters, libm differences only
+        same = rb == rb_ref
+        np.testing.assert_allclose(abuf[same], abuf_ref[same], rtol=0, atol=2e-6, err_msg=f"action_buf step {t}")
+        assert np.array_equal(out["progress"], ref["progress"])
+        per = nv // n
+        same_v = np.repeat(same, per)
+        tol = lambda a, b: np.abs(a - b) <= 3 * (PHYS_ATOL + PHYS_RTOL * np.abs(b))
+        good = same_v & tol(out["term_obs"], ref["term_obs"]).all(1) & tol(out["rews"], ref["rews"]).all(1)
+        good &= tol(out["reward"], ref["reward"]) & (out["timeout"] == ref["timeout"]) & (out["done"] == ref["done"])
+        good &= tol(out["ret_ret"], ref["ret_ret"]).all(1) & (out["ret_len"] == ref["ret_len"])
+        flips += int((~good).sum())
+        # internal consistency of the view outputs (exact)
+        assert_bits_equal(out["reward"], ((out["rews"][:, 0] + out["rews"][:, 1]) + out["rews"][:, 2]) + out["rews"][:, 3],
+                          "reward = rews.sum(-1)")
+        assert np.array_equal(out["done"], np.repeat(rb, per))
+        assert np.all(abuf[rb != 0] == 0)
+        assert np.array_equal(ep_len, np.where(out["done"] != 0, 0, out["ret_len"]))
+        # keep the two statistics streams together (tolerance-level differences would otherwise add up)
+        ep_ret[...] = er_ref; ep_len[...] = el_ref; abuf[...] = abuf_ref
+        if not same.all():
+            break  # a flipped done decision: the states have diverged, stop comparing this run
+    assert flips <= max(2, FLIP_FRACTION * nv * steps), f"{flips} view rows outside tolerance"
+    return flips
+
+
+def check_golden_injected(Backend, golden_path):
+    """The engine's rewards/dones/obs against vectors produced by the REFERENCE's own jit functions
+    (tests/golden/jit_functions.npz): prev state -> engine state, cur state -> injected post state."""
+    g = np.load(golden_path)
+    n = g["ball_pos"].shape[0]
+    be, p = make_backend_pair(Backend, n, 1, 0)
+    prev = orc.State(n)
+    prev.ball_pos[...] = g["prev_ball_pos"]; prev.r_pos[...] = g["prev_r_pos"]
+    # progress such that progress+1 equals the golden progress_buf (flagged fields restart from 0)
+    prev.progress[...] = g["progress"] - 1
+    rb = np.zeros(n, np.int64)
+    restart = g["progress"] == 1
+    rb[restart] = 1
+    prev.progress[restart] = 123
+    neg = g["progress"] < 1
+    be.set_state(prev.to_soa(be.ld))
+    cur = orc.State(n)
+    cur.ball_pos[...] = g["ball_pos"]; cur.ball_vel[...] = g["ball_vel"]; cur.r_pos[...] = g["r_pos"]
+    cur.r_vel[...] = g["r_vel"]; cur.r_rot[...] = g["r_rot"]; cur.r_w[...] = g["r_w"][..., 0]
+    post = cur.to_soa(be.ld)[:58]
+    out = be.step(g["acts"], rb, post_state=post)
+    ok = ~neg  # progress 0 cannot be produced by a step (it is always >= 1 after the increment)
+    assert np.array_equal(rb[ok], g["dones"][ok])
+    assert np.array_equal(out["progress_f"][ok], g["progress"][ok].astype(np.float32))
+    # rewards with the yaml weights (10, 2, 3, 0): vss.py:225-255
+    np.testing.assert_array_equal(out["rew"][..., 0], g["goal_rew"].astype(np.float32) * 10.0)
+    np.testing.assert_allclose(out["rew"][..., 1], g["grad_rew"] * 2.0, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(out["rew"][..., 2], g["move_rew"] * 3.0, rtol=1e-5, atol=2e-6)
+    assert np.all(out["rew"][..., 3] == 0)
+    assert_obs_equal(out["term_obs"], g["obs"], "terminal obs vs reference compute_obs", trig_atol=1e-6)
+    keep = rb == 0
+    assert_obs_equal(out["obs"][keep], g["obs"][keep], "obs vs reference compute_obs", trig_atol=1e-6)
+    # energy reward switched on (w_energy > 0 path, vss.py:253-255)
+    be2, _ = make_backend_pair(Backend, n, 1, 0)
+    be2.set_reward_weights(10.0, 2.0, 3.0, 0.5)
+    be2.set_state(prev.to_soa(be2.ld))
+    rb2 = np.zeros(n, np.int64)
+    out2 = be2.step(g["acts"], rb2, post_state=post)
+    np.testing.assert_allclose(out2["rew"][..., 3], g["energy_rew"] * 0.5, rtol=1e-6, atol=1e-7)
+    return n

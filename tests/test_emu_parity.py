@@ -1,0 +1,35 @@
+"""CPU: the product's per-lane step code (host build, tests/emu) against the oracle."""
+import os
+
+import pytest
+
+import parity_checks as pc
+from backends import EmuBackend
+from conftest import GOLDEN
+from oracle import vss_oracle as orc
+
+
+def test_reset_matches_oracle():
+    pc.check_reset(EmuBackend)
+
+
+def test_injected_step_is_exact():
+    assert pc.check_injected(EmuBackend) > 0
+
+
+def test_injected_step_energy_weight():
+    pc.check_injected(EmuBackend, n=100, steps=2, w_energy=0.25, w_goal=1.0, w_grad=0.0)
+
+
+def test_golden_rewards_and_obs():
+    pc.check_golden_injected(EmuBackend, os.path.join(GOLDEN, "jit_functions.npz"))
+
+
+def test_rollout_tracks_oracle_physics():
+    r = pc.check_rollout(EmuBackend)
+    print(r)
+
+
+@pytest.mark.parametrize("view", [orc.VIEW_SA, orc.VIEW_CMA, orc.VIEW_DMA])
+def test_views(view):
+    pc.check_views(EmuBackend, view)
