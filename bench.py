@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-ppo", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also time N in {1K..1M} (config 5) into `sweep`")
+    ap.add_argument("--ppo-env-id", default="sa")
+    ap.add_argument("--ppo-envs", type=int, default=4096, help="agents per GPU of the PPO leg (configs[1])")
+    ap.add_argument("--ppo-updates", type=int, default=4)
     return ap.parse_args()
 
 
@@ -258,6 +261,28 @@ def run_native(args):
             launches += 220
             del e2, a2
 
+    # ---- PPO SPS (BASELINE configs[1]: ppo-sa, 4096 envs per GPU, OU-noise opponents as in training)
+    ppo_res = None
+    if not args.skip_ppo:
+        from rsoccer_isaac_cleanrl_b200 import ppo as ppo_mod
+        try:
+            del envs, acts
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        pa_ = ppo_mod.parse_args(["--env-id", args.ppo_env_id, "--num-envs", str(args.ppo_envs), "--quiet",
+                                  "--total-timesteps", str(args.ppo_envs * 128 * world * (args.ppo_updates + 1))])
+        st = ppo_mod.train(pa_)
+        sps_list = st["sps"]
+        # SPS exactly as ppo…:376 (global_step / wall since start), plus the steady-state rate of the
+        # updates after the first (which pays one-off allocation and cuBLAS/NCCL initialisation)
+        ppo_res = {"sps": st["final_sps"], "unit": "samples/s (global_step / wall, ppo…:257,376), all GPUs",
+                   "workload": f"ppo-{args.ppo_env_id}, {args.ppo_envs} agents per GPU x 128 steps, 4 minibatches x "
+                               f"8 epochs, {st['updates']} updates, defaults of ppo…:71-108",
+                   "rollout_s": st["rollout_s"], "update_s": st["update_s"], "wall_s": st["wall"],
+                   "mlp_backend": st.get("mlp_backend", "torch-fp32"), "n_gpus": world}
+        del st
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         cpu_baseline, _ = cpu_oracle_run(32768, seconds=args.cpu_seconds)
@@ -274,7 +299,7 @@ def run_native(args):
                                                "(> 126 MB L2 when envs_per_gpu >= 65536)",
                        "parallelism": f"fields sharded over {world} GPU(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks,
+            "clocks": clocks, "ppo": ppo_res,
         }
         if sweep:
             line["sweep"] = sweep

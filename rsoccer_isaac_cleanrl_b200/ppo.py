@@ -1,0 +1,324 @@
+"""PPO training loop — drop-in for the reference's `ppo_continuous_action_isaacgym.py`.
+
+Same CLI flags and defaults (reference ppo…:48-118), same `Agent` (attribute names and
+state_dict keys `critic.{0,2,4,6,8}.*`, `actor_mean.{0,2,4,6,8}.*`, `actor_logstd`, :121-164),
+same rollout / GAE / clipped-surrogate update (:231-365), with
+  * the env step, OU opponents, view slicing and episode statistics in ONE kernel per step
+    (`vss_step_view`),
+  * GAE as one reverse-scan kernel (`vss_gae`) instead of a 128-iteration python loop,
+  * no per-minibatch `.item()` host syncs (the reference syncs at :322; statistics are
+    accumulated on the device and read once per update),
+  * data-parallel over GPUs: each rank owns `--num-envs` agents on its own fields; the only
+    collective is one all-reduce of the flat gradient per minibatch (NCCL over NVLink).
+
+Run:  python -m rsoccer_isaac_cleanrl_b200.ppo --env-id sa --num-envs 4096 --total-timesteps 2000000
+      torchrun --nproc-per-node 8 -m rsoccer_isaac_cleanrl_b200.ppo --env-id dma --num-envs 196608
+"""
+import argparse
+import os
+import random
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .engine import gae as gae_kernel
+from .envs.spaces import ObservationWrapper
+
+
+def _strtobool(x):
+    x = str(x).lower()
+    if x in ("y", "yes", "t", "true", "on", "1"):
+        return True
+    if x in ("n", "no", "f", "false", "off", "0"):
+        return False
+    raise ValueError(f"invalid truth value {x!r}")
+
+
+def parse_args(argv=None):
+    b = lambda x: bool(_strtobool(x))
+    p = argparse.ArgumentParser()
+    p.add_argument("--exp-name", type=str, help="the name of this experiment")
+    p.add_argument("--seed", type=int, default=1)
+    p.add_argument("--torch-deterministic", type=b, default=True, nargs="?", const=True)
+    p.add_argument("--cuda", type=b, default=True, nargs="?", const=True)
+    p.add_argument("--track", type=b, default=False, nargs="?", const=True)
+    p.add_argument("--wandb-project-name", type=str, default="ppo-isaac-cleanrl")
+    p.add_argument("--wandb-entity", type=str, default=None)
+    p.add_argument("--capture-video", type=b, default=False, nargs="?", const=True)
+    # algorithm
+    p.add_argument("--env-id", type=str, default="sa")
+    p.add_argument("--total-timesteps", type=int, default=1000000000)
+    p.add_argument("--learning-rate", type=float, default=0.001)
+    p.add_argument("--num-envs", type=int, default=4095, help="parallel agents PER GPU")
+    p.add_argument("--num-steps", type=int, default=128)
+    p.add_argument("--anneal-lr", type=b, default=False, nargs="?", const=True)
+    p.add_argument("--adaptative-lr", type=b, default=False, nargs="?", const=True)
+    p.add_argument("--gamma", type=float, default=0.99)
+    p.add_argument("--gae-lambda", type=float, default=0.95)
+    p.add_argument("--num-minibatches", type=int, default=4)
+    p.add_argument("--update-epochs", type=int, default=8)
+    p.add_argument("--norm-adv", type=b, default=True, nargs="?", const=True)
+    p.add_argument("--clip-coef", type=float, default=0.2)
+    p.add_argument("--clip-vloss", type=b, default=False, nargs="?", const=True)
+    p.add_argument("--ent-coef", type=float, default=0.005)
+    p.add_argument("--vf-coef", type=float, default=4)
+    p.add_argument("--max-grad-norm", type=float, default=1.5)
+    p.add_argument("--target-kl", type=float, default=None)
+    p.add_argument("--threshold-kl", type=float, default=0.008)
+    p.add_argument("--reward-scaler", type=float, default=1000)  # parsed and unused, as in the reference
+    p.add_argument("--record-video-step-frequency", type=int, default=20000)
+    p.add_argument("--test", type=b, default=False, nargs="?", const=True)
+    # engine-specific additions
+    p.add_argument("--save-path", type=str, default="runs")
+    p.add_argument("--mlp-backend", type=str, default="auto", choices=["auto", "tc", "torch"],
+                   help="tc: hand-written tcgen05 GEMMs (bf16 in, fp32 accumulate); torch: fp32 library GEMMs")
+    p.add_argument("--quiet", type=b, default=False, nargs="?", const=True)
+    args = p.parse_args(argv)
+    args.batch_size = int(args.num_envs * args.num_steps)
+    args.minibatch_size = int(args.batch_size // args.num_minibatches)
+    return args
+
+
+def layer_init(layer, std=np.sqrt(2), bias_const=0.0):
+    torch.nn.init.orthogonal_(layer.weight, std)
+    torch.nn.init.constant_(layer.bias, bias_const)
+    return layer
+
+
+def _mlp(n_in, n_out, out_std):
+    return nn.Sequential(
+        layer_init(nn.Linear(n_in, 256)), nn.Tanh(),
+        layer_init(nn.Linear(256, 512)), nn.Tanh(),
+        layer_init(nn.Linear(512, 512)), nn.Tanh(),
+        layer_init(nn.Linear(512, 256)), nn.Tanh(),
+        layer_init(nn.Linear(256, n_out), std=out_std))
+
+
+class Agent(nn.Module):
+    """Two independent 52-256-512-512-256-{A,1} tanh MLPs + state-independent log-std."""
+
+    def __init__(self, envs):
+        super().__init__()
+        n_obs = int(np.array(envs.single_observation_space.shape).prod())
+        n_act = int(np.prod(envs.single_action_space.shape))
+        self.critic = _mlp(n_obs, 1, 1.0)
+        self.actor_mean = _mlp(n_obs, n_act, 0.01)
+        self.actor_logstd = nn.Parameter(torch.zeros(1, n_act))
+
+    def get_value(self, x):
+        return self.critic(x)
+
+    def get_action_and_value(self, x, action=None):
+        action_mean = self.actor_mean(x)
+        action_logstd = self.actor_logstd.expand_as(action_mean)
+        action_std = torch.exp(action_logstd)
+        if action is None:
+            action = action_mean + action_std * torch.randn_like(action_mean)  # Normal.sample()
+        # Normal(mean, std).log_prob(action).sum(1) and .entropy().sum(1)
+        var = action_std * action_std
+        logp = (-((action - action_mean) ** 2) / (2 * var) - action_logstd - 0.5 * np.log(2 * np.pi)).sum(1)
+        entropy = (0.5 + 0.5 * np.log(2 * np.pi) + action_logstd).sum(1)
+        return action, logp, entropy, self.critic(x)
+
+
+class ExtractObsWrapper(ObservationWrapper):
+    def observation(self, obs):
+        return obs["obs"]
+
+
+def flatten_parameters(module):
+    """Re-home every parameter (and its .grad) as a view of one flat buffer, so the gradient
+    all-reduce, the norm clip and Adam each touch ONE tensor."""
+    params = list(module.parameters())
+    total = sum(p.numel() for p in params)
+    flat = torch.zeros(total, device=params[0].device, dtype=params[0].dtype)
+    flat_grad = torch.zeros_like(flat)
+    off = 0
+    for p in params:
+        n = p.numel()
+        flat[off:off + n].copy_(p.data.view(-1))
+        p.data = flat[off:off + n].view_as(p.data)
+        p.grad = flat_grad[off:off + n].view_as(p.data)
+        off += n
+    return flat, flat_grad
+
+
+class FlatAdam:
+    """Adam (eps 1e-5, no weight decay; torch.optim.Adam semantics) over the flat buffer."""
+
+    def __init__(self, flat, flat_grad, lr, eps=1e-5, betas=(0.9, 0.999)):
+        self.flat, self.grad, self.lr, self.eps, self.b1, self.b2 = flat, flat_grad, lr, eps, betas[0], betas[1]
+        self.m, self.v, self.t = torch.zeros_like(flat), torch.zeros_like(flat), 0
+        self.param_groups = [{"lr": lr}]
+
+    def step(self):
+        self.t += 1
+        lr = self.param_groups[0]["lr"]
+        g = self.grad
+        self.m.mul_(self.b1).add_(g, alpha=1 - self.b1)
+        self.v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+        bc1, bc2 = 1 - self.b1 ** self.t, 1 - self.b2 ** self.t
+        denom = (self.v.sqrt() / (bc2 ** 0.5)).add_(self.eps)
+        self.flat.addcdiv_(self.m, denom, value=-lr / bc1)
+
+
+def train(args, log=print):
+    import torch.distributed as dist
+    from .envs import RecordEpisodeStatisticsTorch, make_env
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    random.seed(args.seed); np.random.seed(args.seed); torch.manual_seed(args.seed + rank)
+    torch.backends.cudnn.deterministic = args.torch_deterministic
+    device = torch.device("cuda", local)
+
+    unwrapped_env, envs = make_env(args)
+    envs = ExtractObsWrapper(envs)
+    envs = RecordEpisodeStatisticsTorch(envs, device)
+    envs.single_action_space = envs.action_space
+    envs.single_observation_space = envs.observation_space
+
+    torch.manual_seed(args.seed)  # identical initial weights on every rank
+    agent = Agent(envs).to(device)
+    torch.manual_seed(args.seed + 1000 * (rank + 1))
+    flat, flat_grad = flatten_parameters(agent)
+    if world > 1:
+        dist.broadcast(flat, 0)
+    optimizer = FlatAdam(flat, flat_grad, lr=args.learning_rate, eps=1e-5)
+
+    T, N = args.num_steps, args.num_envs
+    oshape, ashape = envs.single_observation_space.shape, envs.single_action_space.shape
+    z = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
+    obs, actions = z(T, N, *oshape), z(T, N, *ashape)
+    logprobs, rewards, next_dones, next_timeouts, values, next_values = (z(T, N) for _ in range(6))
+    advantages, returns = z(T, N), z(T, N)
+    term_obs_all = z(T, N, *oshape)
+
+    global_step = 0
+    start_time = time.time()
+    next_obs = envs.reset()
+    num_updates = args.total_timesteps // (args.batch_size * world)
+    stats = {"sps": [], "updates": 0}
+    t_roll = t_upd = 0.0
+    for update in range(1, num_updates + 1):
+        if args.anneal_lr:
+            optimizer.param_groups[0]["lr"] = (1.0 - (update - 1.0) / num_updates) * args.learning_rate
+        tr0 = time.time()
+        with torch.no_grad():
+            for step in range(T):
+                global_step += N * world
+                obs[step] = next_obs
+                action, logprob, _, value = agent.get_action_and_value(next_obs)
+                values[step] = value.flatten()
+                actions[step] = action
+                logprobs[step] = logprob
+                next_obs, rewards[step], next_done, info = envs.step(action)
+                next_dones[step] = next_done
+                next_timeouts[step] = info["time_outs"]
+                term_obs_all[step] = info["terminal_observation"]
+            # V(terminal_observation) for the whole rollout in one batched pass (ppo…:272 does it per step)
+            next_values.copy_(agent.get_value(term_obs_all.view(T * N, *oshape)).view(T, N))
+            gae_kernel(rewards, values, next_values, next_dones, next_timeouts, args.gamma, args.gae_lambda,
+                       advantages, returns)
+        torch.cuda.synchronize()
+        tu0 = time.time()
+        t_roll += tu0 - tr0
+
+        b_obs = obs.reshape((-1,) + oshape)
+        b_logprobs, b_actions = logprobs.reshape(-1), actions.reshape((-1,) + ashape)
+        b_advantages, b_returns, b_values = advantages.reshape(-1), returns.reshape(-1), values.reshape(-1)
+        clipfrac_sum = torch.zeros((), device=device)
+        n_mb = 0
+        stop = False
+        for epoch in range(args.update_epochs):
+            b_inds = torch.randperm(args.batch_size, device=device)
+            for start in range(0, args.batch_size, args.minibatch_size):
+                mb_inds = b_inds[start:start + args.minibatch_size]
+                _, newlogprob, entropy, newvalue = agent.get_action_and_value(b_obs[mb_inds], b_actions[mb_inds])
+                logratio = newlogprob - b_logprobs[mb_inds]
+                ratio = logratio.exp()
+                with torch.no_grad():
+                    old_approx_kl = (-logratio).mean()
+                    approx_kl = ((ratio - 1) - logratio).mean()
+                    clipfrac_sum += ((ratio - 1.0).abs() > args.clip_coef).float().mean()
+                    n_mb += 1
+                mb_advantages = b_advantages[mb_inds]
+                if args.norm_adv:
+                    mb_advantages = (mb_advantages - mb_advantages.mean()) / (mb_advantages.std() + 1e-8)
+                pg_loss = torch.max(-mb_advantages * ratio,
+                                    -mb_advantages * torch.clamp(ratio, 1 - args.clip_coef, 1 + args.clip_coef)).mean()
+                newvalue = newvalue.view(-1)
+                if args.clip_vloss:
+                    v_loss_unclipped = (newvalue - b_returns[mb_inds]) ** 2
+                    v_clipped = b_values[mb_inds] + torch.clamp(newvalue - b_values[mb_inds], -args.clip_coef,
+                                                                args.clip_coef)
+                    v_loss = 0.5 * torch.max(v_loss_unclipped, (v_clipped - b_returns[mb_inds]) ** 2).mean()
+                else:
+                    v_loss = 0.5 * ((newvalue - b_returns[mb_inds]) ** 2).mean()
+                entropy_loss = entropy.mean()
+                loss = pg_loss - args.ent_coef * entropy_loss + v_loss * args.vf_coef
+
+                flat_grad.zero_()
+                loss.backward()
+                if world > 1:  # the one collective of the path: mean gradient over ranks
+                    dist.all_reduce(flat_grad)
+                    flat_grad.div_(world)
+                # nn.utils.clip_grad_norm_(agent.parameters(), max_grad_norm) on the flat buffer
+                gnorm = torch.linalg.vector_norm(flat_grad)
+                flat_grad.mul_(torch.clamp(args.max_grad_norm / (gnorm + 1e-6), max=1.0))
+                optimizer.step()
+
+                if args.adaptative_lr or args.target_kl is not None:
+                    kl = approx_kl.detach().clone()
+                    if world > 1:
+                        dist.all_reduce(kl); kl /= world
+                    kl = float(kl)
+                    if args.adaptative_lr:
+                        cur = optimizer.param_groups[0]["lr"]
+                        if kl > 2.0 * args.threshold_kl:
+                            optimizer.param_groups[0]["lr"] = max(cur / 1.5, 1e-6)
+                        elif kl < 0.5 * args.threshold_kl:
+                            optimizer.param_groups[0]["lr"] = min(cur * 1.5, 1e-2)
+                    if args.target_kl is not None and kl > args.target_kl:
+                        stop = True
+            if stop:
+                break
+        torch.cuda.synchronize()
+        t_upd += time.time() - tu0
+        sps = int(global_step / (time.time() - start_time))
+        stats["sps"].append(sps)
+        stats["updates"] = update
+        if rank == 0 and not args.quiet:
+            r = info["r"]["return"]
+            log(f"update {update}/{num_updates} step {global_step} SPS {sps} lr {optimizer.param_groups[0]['lr']:.2e} "
+                f"v_loss {v_loss.item():.4f} pg_loss {pg_loss.item():.4f} ent {entropy_loss.item():.3f} "
+                f"kl {approx_kl.item():.5f} clipfrac {(clipfrac_sum / max(n_mb, 1)).item():.3f} "
+                f"ep_ret(last) {r.mean().item():.3f}")
+    stats.update(global_step=global_step, wall=time.time() - start_time, rollout_s=t_roll, update_s=t_upd,
+                 final_sps=(global_step / max(time.time() - start_time, 1e-9)))
+    stats["agent"] = agent
+    stats["env"] = unwrapped_env
+    return stats
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    if args.test:
+        args.total_timesteps = 1000000
+    run_name = f"{args.exp_name}_ppo-{args.env_id}_{args.seed}"
+    stats = train(args)
+    if int(os.environ.get("RANK", "0")) == 0:
+        os.makedirs(os.path.join(args.save_path, run_name), exist_ok=True)
+        path = os.path.join(args.save_path, run_name, f"{run_name}-agent.pt")
+        torch.save(stats["agent"].state_dict(), path)  # ppo…:379, same state_dict keys
+        print(f"saved {path}; SPS {stats['final_sps']:.0f} (rollout {stats['rollout_s']:.1f}s, "
+              f"update {stats['update_s']:.1f}s)")
+
+
+if __name__ == "__main__":
+    main()

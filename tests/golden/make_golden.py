@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference, which does not exist on the GPU
 box):   python tests/golden/make_golden.py
-Outputs (committed): tests/golden/jit_functions.npz, gae.npz, wrappers.npz, agent.npz
+Outputs (committed): tests/golden/jit_functions.npz, gae.npz, wrappers.npz, agent.npz, ppo_defaults.json
 
 Nothing from the reference is copied into the repo: the source ranges below are read from
 /root/reference at generation time and exec'd in a scratch namespace.
@@ -12,6 +12,7 @@ Nothing from the reference is copied into the repo: the source ranges below are 
                               stand-in restating its published formula.
   - ppo_continuous_action_isaacgym.py:282-296   the GAE loop, verbatim.
   - ppo_continuous_action_isaacgym.py:121-164   layer_init + Agent, verbatim.
+  - ppo_continuous_action_isaacgym.py:48-118    parse_args, verbatim (flag names and defaults).
   - envs/wrappers.py (whole file)  executed against a 20-line `gym` shim (gym 0.23.1 is
                               un-vendored) and a fake task that replays fixed VSS.step outputs.
 """
@@ -326,8 +327,37 @@ def gen_agent():
     print("agent.npz", len(out), "arrays")
 
 
+def gen_ppo_defaults():
+    """Defaults of every CLI flag: the reference's parse_args (ppo…:48-118) executed with no argv."""
+    import argparse
+    import json
+
+    def strtobool(x):  # distutils.util.strtobool (removed from python 3.12)
+        x = x.lower()
+        if x in ("y", "yes", "t", "true", "on", "1"):
+            return 1
+        if x in ("n", "no", "f", "false", "off", "0"):
+            return 0
+        raise ValueError(x)
+
+    ns = dict(argparse=argparse, strtobool=strtobool)
+    exec(_lines("ppo_continuous_action_isaacgym.py", 48, 118), ns)
+    old = sys.argv
+    sys.argv = ["ppo"]
+    try:
+        d = vars(ns["parse_args"]())
+        sys.argv = ["ppo", "--env-id", "dma", "--num-envs", "65535", "--num-steps", "64", "--anneal-lr", "--norm-adv", "false"]
+        d2 = vars(ns["parse_args"]())
+    finally:
+        sys.argv = old
+    with open(os.path.join(OUT, "ppo_defaults.json"), "w") as f:
+        json.dump({"defaults": d, "dma_case": d2}, f, indent=1, sort_keys=True)
+    print("ppo_defaults.json", len(d), "flags")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    gen_ppo_defaults()
     gen_jit(load_ref_jit())
     gen_gae()
     gen_wrappers()

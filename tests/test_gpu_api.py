@@ -1,0 +1,124 @@
+"""GPU: the reference-facing Python surface (VSS, views, make_env, PPO loop) over libvss_b200.so."""
+import types
+
+import numpy as np
+import pytest
+
+import parity_checks as pc
+from oracle import vss_oracle as orc
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _cfg(n):
+    from rsoccer_isaac_cleanrl_b200.envs import load_cfg
+    cfg = load_cfg()
+    cfg["env"]["numEnvs"] = n
+    return cfg
+
+
+def _oracle_state(envs):
+    return orc.State.from_soa(envs.engine.get_state().cpu().numpy(), envs.num_fields)
+
+
+def test_vss_task_contract_and_oracle_parity():
+    from rsoccer_isaac_cleanrl_b200.envs import VSS
+    n = 300
+    envs = VSS(_cfg(n), "cuda:0", "cuda:0", 0, True, False, False, seed=3, global_env_offset=40)
+    assert envs.num_envs == n and envs.num_obs == 52 and envs.num_actions == 2
+    assert envs.action_space.shape == (2, 3, 2) and envs.observation_space.shape == (2, 3, 52)
+    assert envs.reset_buf.dtype == torch.int64 and bool((envs.reset_buf == 1).all())
+    assert envs.dof_velocity_buf.shape == (n, 2, 3, 2)
+    o = envs.reset()
+    assert set(o) == {"obs"} and o["obs"].shape == (n, 2, 3, 52)
+    p = orc.default_params()
+    rng = np.random.default_rng(0)
+    for t in range(6):
+        st = _oracle_state(envs)
+        rb_ref = envs.reset_buf.cpu().numpy().copy()
+        a = torch.from_numpy(rng.uniform(-1.2, 1.2, (n, 2, 3, 2)).astype(np.float32)).cuda()
+        obs, rew, reset, extras = envs.step(a)
+        assert rew.shape == (n, 2, 3, 4) and reset.dtype == torch.int64 and reset.data_ptr() == envs.reset_buf.data_ptr()
+        assert extras["time_outs"].dtype == torch.bool and extras["progress_buffer"].dtype == torch.float32
+        assert extras["terminal_observation"].shape == (n, 2, 3, 52)
+        ref = orc.step(p, 3, 40, st, a.cpu().numpy(), rb_ref)
+        out = dict(obs=obs["obs"].cpu().numpy(), term_obs=extras["terminal_observation"].cpu().numpy(),
+                   rew=rew.cpu().numpy(), timeout=extras["time_outs"].cpu().numpy().astype(np.uint8),
+                   progress_f=extras["progress_buffer"].cpu().numpy())
+        assert pc.compare_full_step(out, ref, reset.cpu().numpy(), rb_ref, n, f"api step {t}", False) <= 1
+    # play.py:132-133 pattern: force a full reset through the public buffer
+    before = envs.ball_pos.clone()
+    envs.reset_buf[:] = 1
+    envs.reset_dones()
+    assert not torch.equal(before, envs.ball_pos)
+    assert bool((envs.dof_velocity_buf == 0).all())
+    # reward weights are live attributes (ppo…:389-392)
+    envs.w_goal, envs.w_grad, envs.w_move, envs.w_energy = 1.0, 0.0, 0.0, 0.0
+    _, rew, _, _ = envs.step(torch.zeros((n, 2, 3, 2), device="cuda"))
+    assert bool((rew[..., 1:] == 0).all())
+
+
+@pytest.mark.parametrize("env_id", ["sa", "cma", "dma"])
+def test_views_python_surface(env_id):
+    from rsoccer_isaac_cleanrl_b200.envs import RecordEpisodeStatisticsTorch, make_env
+    from rsoccer_isaac_cleanrl_b200.ppo import ExtractObsWrapper
+    n_agents = 192 * 3 if env_id == "dma" else 192
+    args = types.SimpleNamespace(cuda=True, num_envs=n_agents, env_id=env_id, capture_video=False, seed=9)
+    raw, view = make_env(args)
+    fields = 192
+    assert raw.num_fields == fields
+    envs = RecordEpisodeStatisticsTorch(ExtractObsWrapper(view), torch.device("cuda:0"))
+    adim = 6 if env_id == "cma" else 2
+    assert envs.action_space.shape == (adim,) and envs.observation_space.shape == (52,)
+    assert envs.num_envs == n_agents
+    obs = envs.reset()
+    assert obs.shape == (n_agents, 52)
+    p = orc.default_params()
+    vid = {"sa": orc.VIEW_SA, "cma": orc.VIEW_CMA, "dma": orc.VIEW_DMA}[env_id]
+    abuf = np.zeros((fields, 2, 3, 2), np.float32)
+    er, el = np.zeros((n_agents, 4), np.float32), np.zeros(n_agents, np.int32)
+    rng = np.random.default_rng(1)
+    for t in range(5):
+        st = _oracle_state(raw)
+        rb = raw.reset_buf.cpu().numpy().copy()
+        act = rng.uniform(-1, 1, (n_agents, adim)).astype(np.float32)
+        step_index = raw.engine.step_count
+        obs, reward, done, info = envs.step(torch.from_numpy(act).cuda())
+        ref = orc.step_view(p, 9, 0, step_index, st, vid, act, abuf, rb, er, el)
+        assert obs.shape == (n_agents, 52) and reward.shape == (n_agents,) and done.shape == (n_agents,)
+        assert info["terminal_observation"].shape == (n_agents, 52) and info["rews"].shape == (n_agents, 4)
+        assert info["time_outs"].shape == (n_agents,) and info["progress_buffer"].shape == (n_agents,)
+        same = np.repeat(raw.reset_buf.cpu().numpy() == rb, n_agents // fields)
+        tol = lambda a, b: np.abs(a - b) <= 3 * (pc.PHYS_ATOL + pc.PHYS_RTOL * np.abs(b))
+        good = same & tol(info["terminal_observation"].cpu().numpy(), ref["term_obs"]).all(1)
+        good &= tol(reward.cpu().numpy(), ref["reward"]) & (done.cpu().numpy() == ref["done"])
+        good &= tol(info["r"]["return"].cpu().numpy(), ref["ret_ret"].sum(1)) & (info["l"].cpu().numpy() == ref["ret_len"])
+        assert (~good).sum() <= 2, (t, int((~good).sum()))
+        np.testing.assert_allclose(view.action_buf.cpu().numpy()[same[::n_agents // fields]],
+                                   abuf[same[::n_agents // fields]], atol=2e-6)
+        # keep both sides on the engine's stream of states
+        abuf[...] = view.action_buf.cpu().numpy()
+        er[...] = view.episode_returns.cpu().numpy(); el[...] = view.episode_lengths.cpu().numpy()
+    # the raw task's reset() still returns a current observation after fused view steps
+    full = raw.reset()["obs"]
+    want = obs if env_id != "dma" else obs.view(fields, 3, 52)
+    got = full[:, 0, 0, :] if env_id != "dma" else full[:, 0, :, :]
+    assert torch.equal(got, want)
+
+
+def test_ppo_short_training_run(tmp_path):
+    from rsoccer_isaac_cleanrl_b200 import ppo
+    args = ppo.parse_args(["--env-id", "sa", "--num-envs", "256", "--num-steps", "16", "--total-timesteps",
+                           str(256 * 16 * 3), "--update-epochs", "2", "--quiet", "--seed", "2"])
+    stats = ppo.train(args)
+    assert stats["updates"] == 3 and stats["global_step"] == 256 * 16 * 3 and stats["final_sps"] > 0
+    sd = stats["agent"].state_dict()
+    assert "critic.0.weight" in sd and "actor_mean.8.bias" in sd and "actor_logstd" in sd
+    assert all(torch.isfinite(v).all() for v in sd.values())
