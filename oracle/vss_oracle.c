@@ -460,9 +460,9 @@ static void body_vs_walls(const phys_t* q, body_t* Q, double lx, double ly, doub
 }
 
 static void robot_walls(const phys_t* q, body_t* R) {
-  /* cheap reject: the box (half diagonal H*sqrt2) cannot reach any wall or post */
-  const double reach = q->H * 1.4142135623730951;
-  if (fabs(R->x) < q->HL - reach && fabs(R->y) < q->HW - reach) return;
+  /* reject: the box's axis-aligned extent H(|c|+|s|) cannot reach any wall or goal post */
+  const double ext = q->H * (fabs(R->c) + fabs(R->s));
+  if (fabs(R->x) + ext < q->HL && fabs(R->y) + ext < q->HW) return;
   for (int k = 0; k < 4; ++k) body_vs_walls(q, R, CORNER[k][0] * q->H, CORNER[k][1] * q->H, 0.0, q->mu_rw, 0.0);
   /* goal-post corners (+-HL, +-GH) poking into a box face */
   body_t wall = {0};

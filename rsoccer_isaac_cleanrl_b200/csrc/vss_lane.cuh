@@ -32,6 +32,8 @@ namespace vss {
 constexpr int LDS = 33;       // shared-memory column stride in words
 constexpr int W_PREV = 60;    // 14 words: ball xy, then robot xy x6, before physics
 constexpr int SM_WORDS = 74;  // words per field staged in shared memory
+constexpr int QUEUE_WORDS = 48; // per-warp (field, robot) wall-task queue: 32 x 6 bytes
+constexpr int TILE_WORDS = SM_WORDS * 33 + QUEUE_WORDS;  // shared-memory words per warp
 constexpr int F4_PER_FIELD = VSS_OBS_PER_FIELD / 4;  // 78 float4 per (2,3,52) observation
 constexpr int F4_PER_ROW = VSS_NUM_OBS / 4;          // 13
 constexpr int RESET_MAX_ATTEMPTS = 64;
@@ -267,6 +269,16 @@ VSS_HD void ball_robot(float* S, int r, const DevParams& P) {
 // 12 features in fixed order: corners of A in B, corners of B in A, wheels of A, wheels of B.
 VSS_HD void robot_robot(float* S, int i, int j, const DevParams& P) {
   Body A = load_robot(S, i, P), B = load_robot(S, j, P);
+  {  // exact reject (separating-axis bound on the four box axes): no feature of either robot can
+     // reach the other's box, so the 12-feature loop below would find nothing
+    const float dx = A.x - B.x, dy = A.y - B.y;
+    const float cd = fabsf(A.c * B.c + A.s * B.s), sd = fabsf(A.s * B.c - A.c * B.s);
+    const float hc = P.H * (cd + sd);
+    const float ex = fmaxf(hc, P.b * sd + P.rwc) + P.H + 1e-5f, ey = fmaxf(hc, P.b * cd + P.rwc) + P.H + 1e-5f;
+    const bool a_in_b = fabsf(dx * B.c + dy * B.s) < ex && fabsf(dy * B.c - dx * B.s) < ey;
+    const bool b_in_a = fabsf(dx * A.c + dy * A.s) < ex && fabsf(dy * A.c - dx * A.s) < ey;
+    if (!(a_in_b || b_in_a)) return;
+  }
   bool dirty = false;
 #pragma unroll 1
   for (int k = 0; k < 12; ++k) {
@@ -327,9 +339,16 @@ VSS_HD bool point_vs_walls(Body& Q, float lx, float ly, float rho, float mu, flo
   return any;
 }
 
-VSS_HD void robot_walls(float* S, int r, const DevParams& P) {
+// The box (axis-aligned extent H(|c|+|s|)) can reach a wall or a goal post.
+VSS_HD bool robot_near_walls(const float* S, int r, const DevParams& P) {
   const float* b = S + (4 + 9 * r) * LDS;
-  if (fabsf(b[0]) < P.wall_rej_x && fabsf(b[LDS]) < P.wall_rej_y) return;
+  const float ext = P.H * (fabsf(b[4 * LDS]) + fabsf(b[5 * LDS]));
+  return !(fabsf(b[0]) + ext < P.HL && fabsf(b[LDS]) + ext < P.HW);
+}
+
+// Wall contacts of robot r of the field whose column starts at S. Touches only that robot, so
+// tasks of different (field, robot) pairs are independent and can run on any lane.
+VSS_HD void robot_walls_task(float* S, int r, const DevParams& P) {
   Body R = load_robot(S, r, P);
   bool dirty = false;
 #pragma unroll 1
@@ -354,15 +373,30 @@ VSS_HD void robot_walls(float* S, int r, const DevParams& P) {
 
 // sin/cos of the small per-substep yaw increment
 VSS_HD void sincos_small(float a, float& sa, float& ca) {
+  if (fabsf(a) < 0.5f) {  // |w| < 40 rad/s at h = 12.5 ms: Taylor to a^9 / a^8, error < 1e-9
+    const float a2 = a * a;
+    sa = a * (1.0f + a2 * (-1.0f / 6 + a2 * (1.0f / 120 + a2 * (-1.0f / 5040 + a2 * (1.0f / 362880)))));
+    ca = 1.0f + a2 * (-0.5f + a2 * (1.0f / 24 + a2 * (-1.0f / 720 + a2 * (1.0f / 40320))));
+    return;
+  }
 #if defined(__CUDA_ARCH__)
   sincosf(a, &sa, &ca);
 #else
   sa = sinf(a); ca = cosf(a);
 #endif
 }
+VSS_HD float rsqrt_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
 
-VSS_HD void substep_lane(float* S, const DevParams& P) {
-  // A. wheel drive + integration (DESIGN.md §3.2)
+// Phases A-C of a substep for one field. Returns the 6-bit mask of robots that need the wall
+// phase D, which the caller runs as (field, robot) tasks spread over the lanes of the warp.
+VSS_HD uint32_t substep_pre_lane(float* S, const DevParams& P) {
+  // A. wheel drive + integration (DESIGN.md §3)
 #pragma unroll 2
   for (int r = 0; r < 6; ++r) {
     float* b = S + (4 + 9 * r) * LDS;
@@ -381,7 +415,7 @@ VSS_HD void substep_lane(float* S, const DevParams& P) {
     float sa, ca;
     sincos_small(w * P.h, sa, ca);
     const float c2 = c * ca - s * sa, s2 = s * ca + c * sa;
-    const float inv = 1.0f / sqrtf(c2 * c2 + s2 * s2);
+    const float inv = rsqrt_fast(c2 * c2 + s2 * s2);
     b[0] = x; b[LDS] = y; b[2 * LDS] = vx; b[3 * LDS] = vy; b[4 * LDS] = c2 * inv; b[5 * LDS] = s2 * inv;
     b[6 * LDS] = w;
   }
@@ -432,13 +466,19 @@ VSS_HD void substep_lane(float* S, const DevParams& P) {
                         (4ull << 36) | (5ull << 39) | (5ull << 42);
     robot_robot(S, (int)((PI >> (3 * p)) & 7), (int)((PJ >> (3 * p)) & 7), P);
   }
-  // D. robots vs walls, E. ball vs walls
-#pragma unroll 1
-  for (int r = 0; r < 6; ++r) robot_walls(S, r, P);
-  {
-    Body ball = load_ball(S, P);
-    if (point_vs_walls(ball, 0.0f, 0.0f, P.rb, P.mu_bw, 2.5f * P.inv_mb, P)) store_ball(S, ball);
-  }
+  // D. which robots can touch a wall
+  uint32_t walls = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) walls |= robot_near_walls(S, r, P) ? (1u << r) : 0u;
+  return walls;
+}
+
+// Phase E of a substep: ball vs walls.
+VSS_HD void substep_ball_walls_lane(float* S, const DevParams& P) {
+  const float bx = fabsf(S[0]), by = fabsf(S[LDS]);
+  if (bx + P.rb <= P.HL && by + P.rb <= P.HW) return;  // cannot touch any wall family
+  Body ball = load_ball(S, P);
+  if (point_vs_walls(ball, 0.0f, 0.0f, P.rb, P.mu_bw, 2.5f * P.inv_mb, P)) store_ball(S, ball);
 }
 
 // ---- rewards and dones: envs/vss.py:218-265, 578-655 -----------------------------------
@@ -602,14 +642,12 @@ VSS_HD void store_state(const float* S, float* state, long long ld, long long en
   for (int w = 0; w < VSS_STATE_WORDS; ++w) dst[(long long)w * ld] = S[w * LDS];
 }
 
-// Phase 1 of a step for one field: everything up to (not including) the observation write.
-// Returns the done flag of this step.
-template <int VIEW, bool INJECT>
-VSS_HD bool lane_phase1(float* S, long long env, const StepArgs& a, const DevParams& P, const RngKey& key) {
-  constexpr int AGENTS = ViewShape<VIEW>::AGENTS;
-  // 1a. state in: 60 coalesced loads in flight per lane
+// Phase 1a of a step for one field: state in, actions (+OU noise), progress restart, prev clones.
+template <int VIEW>
+VSS_HD void lane_phase1a(float* S, long long env, const StepArgs& a, const DevParams& P, const RngKey& key) {
+  // state in: 60 coalesced loads in flight per lane
   load_state(S, a.state, a.ld, env);
-  // 1b. actions (vss.py:180-187; wrappers.py:102-103)
+  // actions (vss.py:180-187; wrappers.py:102-103)
   float act[VSS_ACT_PER_FIELD];
   {
     const float* ap = (VIEW == VIEW_FULL ? a.actions : a.action_buf) + env * VSS_ACT_PER_FIELD;
@@ -632,8 +670,7 @@ VSS_HD bool lane_phase1(float* S, long long env, const StepArgs& a, const DevPar
 #pragma unroll
     for (int q = 0; q < 3; ++q) st4(ap + 4 * q, F4{act[4 * q], act[4 * q + 1], act[4 * q + 2], act[4 * q + 3]});
   }
-  int progress = (int)fbits(S[VSS_W_PROGRESS * LDS]);
-  if (a.reset_buf[env] != 0) progress = 0;  // flags of the previous step, vss.py:182-183
+  if (a.reset_buf[env] != 0) S[VSS_W_PROGRESS * LDS] = bitsf(0u);  // flags of the previous step, vss.py:182-183
 #pragma unroll
   for (int r = 0; r < 6; ++r) {  // dof_velocity_buf[:] = clamp(actions), vss.py:184 + VecTask clip
     S[(11 + 9 * r) * LDS] = clampf(act[2 * r], -1.0f, 1.0f);
@@ -646,20 +683,24 @@ VSS_HD bool lane_phase1(float* S, long long env, const StepArgs& a, const DevPar
     S[(W_PREV + 2 + 2 * r) * LDS] = S[(4 + 9 * r) * LDS];
     S[(W_PREV + 3 + 2 * r) * LDS] = S[(5 + 9 * r) * LDS];
   }
-  // 1c. physics (replaces gym.simulate)
-  if (INJECT) {
-    const float* inj = a.inject + env;
+}
+
+// Parity hook: take the post-physics state from `inject` instead of simulating.
+VSS_HD void lane_inject(float* S, long long env, const StepArgs& a) {
+  const float* inj = a.inject + env;
 #pragma unroll
-    for (int w = 0; w < VSS_STATE_FLOATS; ++w) {
-      const bool is_act = w >= 4 && ((w - 4) % 9) >= 7;
-      if (!is_act) S[w * LDS] = ldg(inj + (long long)w * a.ld);
-    }
-  } else {
-#pragma unroll 1
-    for (int it = 0; it < P.substeps; ++it) substep_lane(S, P);
+  for (int w = 0; w < VSS_STATE_FLOATS; ++w) {
+    const bool is_act = w >= 4 && ((w - 4) % 9) >= 7;
+    if (!is_act) S[w * LDS] = ldg(inj + (long long)w * a.ld);
   }
-  // 1d. post_physics_step: progress, rewards, dones (vss.py:189-193, 218-265)
-  progress += 1;
+}
+
+// Phase 1d: post_physics_step — progress, rewards, dones, per-field outputs (vss.py:189-193,
+// 218-265). Returns the done flag of this step.
+template <int VIEW>
+VSS_HD bool lane_phase1d(float* S, long long env, const StepArgs& a, const DevParams& P) {
+  constexpr int AGENTS = ViewShape<VIEW>::AGENTS;
+  const int progress = (int)fbits(S[VSS_W_PROGRESS * LDS]) + 1;
   S[VSS_W_PROGRESS * LDS] = bitsf((uint32_t)progress);
   float rew[VSS_REW_PER_FIELD];
   rewards_lane(S, P, rew);

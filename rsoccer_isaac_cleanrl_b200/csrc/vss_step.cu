@@ -25,6 +25,39 @@ namespace vss {
 __constant__ ObsTable c_obs_table = make_obs_table();
 
 constexpr int TAB_WORDS = 80;  // 78 table entries, padded
+// Physics of one tile (replaces gym.simulate): per substep, phases A-C per lane, then the robot-wall
+// contacts as (field, robot) tasks compacted over the warp — any lane can work on any field of the
+// tile because the state columns live in shared memory — then the ball-wall phase per lane.
+__device__ __forceinline__ void physics_tile(float* T, int lane, bool active, const DevParams& P) {
+  float* S = T + lane;
+  uint8_t* queue = reinterpret_cast<uint8_t*>(T + SM_WORDS * LDS);
+#pragma unroll 1
+  for (int it = 0; it < P.substeps; ++it) {
+    uint32_t m = active ? substep_pre_lane(S, P) : 0u;
+    const int cnt = __popc(m);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int pos = incl - cnt;
+    while (m) {
+      const int r = __ffs((int)m) - 1;
+      m &= m - 1;
+      queue[pos++] = (uint8_t)((lane << 3) | r);
+    }
+    __syncwarp();
+    for (int t = lane; t < total; t += 32) {
+      const int q = queue[t];
+      robot_walls_task(T + (q >> 3), q & 7, P);
+    }
+    __syncwarp();
+    if (active) substep_ball_walls_lane(S, P);
+  }
+}
+
 template <int VIEW, bool INJECT>
 __global__ void __launch_bounds__(128)
 k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) {
@@ -36,7 +69,7 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long env0 = tile * 32;
   if (env0 >= a.n) return;
-  float* T = smem + TAB_WORDS + warp * (SM_WORDS * LDS);
+  float* T = smem + TAB_WORDS + warp * TILE_WORDS;
   float* S = T + lane;
   const long long env = env0 + lane;
   const bool active = env < a.n;
@@ -44,8 +77,11 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
   const RngKey key = make_key(a, env);
   // 1. per lane: load, actions, physics, rewards, dones
+  if (active) lane_phase1a<VIEW>(S, env, a, P, key);
+  if (INJECT) { if (active) lane_inject(S, env, a); }
+  else physics_tile(T, lane, active, P);
   bool done = false;
-  if (active) done = lane_phase1<VIEW, INJECT>(S, env, a, P, key);
+  if (active) done = lane_phase1d<VIEW>(S, env, a, P);
   __syncwarp();
   // 2. terminal observation + observation of the fields that keep their state (vss.py:195-196)
   const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
@@ -74,7 +110,7 @@ k_reset_dones(float* state, long long n, long long ld, unsigned long long goff, 
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long env0 = tile * 32;
   if (env0 >= n) return;
-  float* T = smem + TAB_WORDS + warp * (SM_WORDS * LDS);
+  float* T = smem + TAB_WORDS + warp * TILE_WORDS;
   float* S = T + lane;
   const long long env = env0 + lane;
   const bool active = env < n;
@@ -174,7 +210,7 @@ static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* s
   else if (tiles < 148 * 8) wpb = 2;
   *warps_per_block = wpb;
   *grid = (unsigned)((tiles + wpb - 1) / wpb);
-  *smem = sizeof(float) * (TAB_WORDS + (size_t)wpb * SM_WORDS * LDS);
+  *smem = sizeof(float) * (TAB_WORDS + (size_t)wpb * TILE_WORDS);
   return 0;
 }
 

@@ -20,14 +20,28 @@ static void emu_step_t(const StepArgs& a, const DevParams& P) {
   const long long tiles = (a.n + 31) / 32;
 #pragma omp parallel for schedule(static)
   for (long long tile = 0; tile < tiles; ++tile) {
-    std::vector<float> Tbuf(SM_WORDS * LDS, 0.0f);
+    std::vector<float> Tbuf(TILE_WORDS, 0.0f);
     float* T = Tbuf.data();
     const long long env0 = tile * 32;
     const int valid = (int)std::min(32LL, a.n - env0);
     bool done[32] = {false};
     uint32_t done_mask = 0;
+    for (int lane = 0; lane < valid; ++lane) lane_phase1a<VIEW>(T + lane, env0 + lane, a, P, make_key(a, env0 + lane));
+    if (INJECT) {
+      for (int lane = 0; lane < valid; ++lane) lane_inject(T + lane, env0 + lane, a);
+    } else {  // physics_tile of vss_step.cu: wall tasks compacted over the warp
+      for (int it = 0; it < P.substeps; ++it) {
+        std::vector<int> queue;
+        for (int lane = 0; lane < valid; ++lane) {
+          uint32_t m = substep_pre_lane(T + lane, P);
+          for (int r = 0; r < 6; ++r) if (m & (1u << r)) queue.push_back((lane << 3) | r);
+        }
+        for (int q : queue) robot_walls_task(T + (q >> 3), q & 7, P);
+        for (int lane = 0; lane < valid; ++lane) substep_ball_walls_lane(T + lane, P);
+      }
+    }
     for (int lane = 0; lane < valid; ++lane) {
-      done[lane] = lane_phase1<VIEW, INJECT>(T + lane, env0 + lane, a, P, make_key(a, env0 + lane));
+      done[lane] = lane_phase1d<VIEW>(T + lane, env0 + lane, a, P);
       if (done[lane]) done_mask |= 1u << lane;
     }
     float* ob = a.obs + env0 * (PER_FIELD * 4);
@@ -75,7 +89,7 @@ __attribute__((visibility("default"))) int emu_reset_dones(const vss_params* p, 
   a.goff = goff; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
   const long long tiles = (n + 31) / 32;
   for (long long tile = 0; tile < tiles; ++tile) {
-    std::vector<float> Tbuf(SM_WORDS * LDS, 0.0f);
+    std::vector<float> Tbuf(TILE_WORDS, 0.0f);
     float* T = Tbuf.data();
     const long long env0 = tile * 32;
     const int valid = (int)std::min(32LL, n - env0);
