@@ -403,21 +403,28 @@ static int circle_vs_box(const body_t* B, double H, double px, double py, double
 
 static const double CORNER[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
 
-/* a feature point of A (box corner or wheel circle) against the box of B */
-static void feature_vs_box(const phys_t* q, body_t* A, body_t* B, double lx, double ly, double rho) {
-  const double px = A->x + lx * A->c - ly * A->s, py = A->y + lx * A->s + ly * A->c;
-  double nx, ny, depth, cpx, cpy;
-  if (circle_vs_box(B, q->H, px, py, rho, &nx, &ny, &depth, &cpx, &cpy))
-    resolve(B, A, nx, ny, depth, cpx, cpy, q->e, 0.0, 0.0);
-}
-
+/* Robot-robot contact, DESIGN.md §3 C: all 12 features are tested against the poses at entry
+ * (snapshot A0, B0); hits are resolved in feature order with the penetration reduced by the
+ * separation already gained along that normal. */
 static void robot_robot(const phys_t* q, body_t* A, body_t* B) {
-  for (int k = 0; k < 4; ++k) feature_vs_box(q, A, B, CORNER[k][0] * q->H, CORNER[k][1] * q->H, 0.0);
-  for (int k = 0; k < 4; ++k) feature_vs_box(q, B, A, CORNER[k][0] * q->H, CORNER[k][1] * q->H, 0.0);
-  feature_vs_box(q, A, B, 0.0, q->b, q->rwc);
-  feature_vs_box(q, A, B, 0.0, -q->b, q->rwc);
-  feature_vs_box(q, B, A, 0.0, q->b, q->rwc);
-  feature_vs_box(q, B, A, 0.0, -q->b, q->rwc);
+  const body_t A0 = *A, B0 = *B;
+  for (int k = 0; k < 12; ++k) {
+    /* order: corners of A in B (0-3), corners of B in A (4-7), wheels of A (8,9), wheels of B (10,11) */
+    const int a_owns = (k < 8) ? (k < 4) : (k < 10);
+    double lx, ly, rho;
+    if (k < 8) { lx = CORNER[k & 3][0] * q->H; ly = CORNER[k & 3][1] * q->H; rho = 0.0; }
+    else { lx = 0.0; ly = (k & 1) ? -q->b : q->b; rho = q->rwc; }
+    const body_t* F0 = a_owns ? &A0 : &B0;
+    const body_t* G0 = a_owns ? &B0 : &A0;
+    body_t* F = a_owns ? A : B;
+    body_t* G = a_owns ? B : A;
+    const double px = F0->x + lx * F0->c - ly * F0->s, py = F0->y + lx * F0->s + ly * F0->c;
+    double nx, ny, depth, cpx, cpy;
+    if (!circle_vs_box(G0, q->H, px, py, rho, &nx, &ny, &depth, &cpx, &cpy)) continue;
+    const double gained = ((F->x - F0->x) - (G->x - G0->x)) * nx + ((F->y - F0->y) - (G->y - G0->y)) * ny;
+    const double d = depth - gained;
+    resolve(G, F, nx, ny, d > 0.0 ? d : 0.0, cpx, cpy, q->e, 0.0, 0.0);
+  }
 }
 
 static void ball_robot(const phys_t* q, body_t* ball, body_t* R) {

@@ -266,37 +266,71 @@ VSS_HD void ball_robot(float* S, int r, const DevParams& P) {
   }
 }
 
-// 12 features in fixed order: corners of A in B, corners of B in A, wheels of A, wheels of B.
+// Detection of the 6 features of one robot (4 box corners, 2 wheel circles) against the box of
+// the other, done in the box's frame: (lx, ly) = owner centre, (cr, sr) = rotation of the owner
+// relative to the box. Returns bits 0-3 for corners, 4-5 for wheels.
+VSS_HD uint32_t features_in_box(float lx, float ly, float cr, float sr, const DevParams& P) {
+  const float H = P.H;
+  uint32_t hits = 0;
+  const float ch = cr * H, sh = sr * H;
+  // corner (cx, cy) in (+,+) (-,+) (-,-) (+,-): offset = R_rel * (cx H, cy H)
+  const float ox[4] = {ch - sh, -ch - sh, -ch + sh, ch + sh};
+  const float oy[4] = {sh + ch, -sh + ch, -sh - ch, sh - ch};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (fabsf(lx + ox[q]) < H && fabsf(ly + oy[q]) < H) hits |= 1u << q;
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {  // wheel centres at local (0, +-b)
+    const float wy = w ? -P.b : P.b;
+    const float px = lx - sr * wy, py = ly + cr * wy;
+    const float ex = px - clampf(px, -H, H), ey = py - clampf(py, -H, H);
+    if (ex * ex + ey * ey < P.rwc * P.rwc) hits |= 16u << w;  // (inside the box: ex = ey = 0)
+  }
+  return hits;
+}
+
+// Robot-robot contact. The 12 features — corners of A in B, corners of B in A,
+// wheels of A, wheels of B — are all tested against the poses at entry (one snapshot); the hits
+// are then resolved in that order, each penetration reduced by the separation already gained
+// along its normal.
 VSS_HD void robot_robot(float* S, int i, int j, const DevParams& P) {
   Body A = load_robot(S, i, P), B = load_robot(S, j, P);
-  {  // exact reject (separating-axis bound on the four box axes): no feature of either robot can
-     // reach the other's box, so the 12-feature loop below would find nothing
-    const float dx = A.x - B.x, dy = A.y - B.y;
-    const float cd = fabsf(A.c * B.c + A.s * B.s), sd = fabsf(A.s * B.c - A.c * B.s);
-    const float hc = P.H * (cd + sd);
-    const float ex = fmaxf(hc, P.b * sd + P.rwc) + P.H + 1e-5f, ey = fmaxf(hc, P.b * cd + P.rwc) + P.H + 1e-5f;
-    const bool a_in_b = fabsf(dx * B.c + dy * B.s) < ex && fabsf(dy * B.c - dx * B.s) < ey;
-    const bool b_in_a = fabsf(dx * A.c + dy * A.s) < ex && fabsf(dy * A.c - dx * A.s) < ey;
+  const float dx = A.x - B.x, dy = A.y - B.y;
+  const float cd = A.c * B.c + A.s * B.s, sd = A.s * B.c - A.c * B.s;  // rotation of A relative to B
+  const float lxb = dx * B.c + dy * B.s, lyb = dy * B.c - dx * B.s;    // A's centre in B's frame
+  const float lxa = -(dx * A.c + dy * A.s), lya = -(dy * A.c - dx * A.s);  // B's centre in A's frame
+  {  // exact reject (separating-axis bound on the four box axes): nothing can touch
+    const float acd = fabsf(cd), asd = fabsf(sd), hc = P.H * (acd + asd);
+    const float ex = fmaxf(hc, P.b * asd + P.rwc) + P.H + 1e-5f, ey = fmaxf(hc, P.b * acd + P.rwc) + P.H + 1e-5f;
+    const bool a_in_b = fabsf(lxb) < ex && fabsf(lyb) < ey;
+    const bool b_in_a = fabsf(lxa) < ex && fabsf(lya) < ey;
     if (!(a_in_b || b_in_a)) return;
   }
-  bool dirty = false;
-#pragma unroll 1
-  for (int k = 0; k < 12; ++k) {
+  const uint32_t ha = features_in_box(lxb, lyb, cd, sd, P);   // features of A against box B
+  const uint32_t hb = features_in_box(lxa, lya, cd, -sd, P);  // features of B against box A
+  // order: A corners (0-3), B corners (4-7), A wheels (8,9), B wheels (10,11)
+  uint32_t hits = (ha & 15u) | ((hb & 15u) << 4) | ((ha >> 4) << 8) | ((hb >> 4) << 10);
+  if (!hits) return;
+  const Body A0 = A, B0 = B;
+  while (hits) {
+    const int k = ffs32(hits) - 1;
+    hits &= hits - 1;
     const bool a_owns = (k < 8) ? (k < 4) : (k < 10);
     float lx, ly, rho;
     if (k < 8) { corner_xy(k & 3, P.H, lx, ly); rho = 0.0f; }
     else { lx = 0.0f; ly = (k & 1) ? -P.b : P.b; rho = P.rwc; }
-    Body F = a_owns ? A : B;  // feature owner
-    Body G = a_owns ? B : A;  // box
-    const float px = F.x + lx * F.c - ly * F.s, py = F.y + lx * F.s + ly * F.c;
-    const Hit h = circle_vs_box(G, P.H, px, py, rho);
+    const Body F0 = a_owns ? A0 : B0, G0 = a_owns ? B0 : A0;
+    const float px = F0.x + lx * F0.c - ly * F0.s, py = F0.y + lx * F0.s + ly * F0.c;
+    const Hit h = circle_vs_box(G0, P.H, px, py, rho);
     if (h.hit) {
-      resolve(G, F, h.nx, h.ny, h.depth, h.cpx, h.cpy, P.e1, 0.0f, 0.0f);
+      Body F = a_owns ? A : B, G = a_owns ? B : A;
+      const float gained = ((F.x - F0.x) - (G.x - G0.x)) * h.nx + ((F.y - F0.y) - (G.y - G0.y)) * h.ny;
+      resolve(G, F, h.nx, h.ny, fmaxf(h.depth - gained, 0.0f), h.cpx, h.cpy, P.e1, 0.0f, 0.0f);
       if (a_owns) { A = F; B = G; } else { B = F; A = G; }
-      dirty = true;
     }
   }
-  if (dirty) { store_robot(S, i, A); store_robot(S, j, B); }
+  store_robot(S, i, A);
+  store_robot(S, j, B);
 }
 
 // Point (rho = 0) or circle of body Q at local offset (lx,ly) against the static walls.
