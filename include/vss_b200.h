@@ -200,6 +200,21 @@ VSS_API int vss_gae(const float* rewards, const float* values, const float* next
                     float* returns, int32_t T, int64_t N, double gamma, double gae_lambda,
                     void* stream);
 
+/* Tensor-core GEMM of the PPO MLPs (tcgen05 / TMEM / TMA, csrc/tc_gemm.cu): replaces the cuBLAS
+ * GEMM + bias + tanh launches behind nn.Linear/nn.Tanh of the reference's Agent
+ * (ppo_continuous_action_isaacgym.py:127-164) and their autograd backward (:352).
+ *   C[M,N] = epilogue(op(A) * op(B)^T), bf16 operands, fp32 accumulation.
+ *   mn_major = 0: A [M,K], B [N,K] row-major (forward: A = activations, B = nn.Linear weight;
+ *                 dgrad: A = dZ, B = weight^T). mn_major = 1: A [K,M], B [K,N] row-major (wgrad:
+ *                 dW = dZ^T X with the batch as K; no transposed copies needed).
+ *   epilogue: 0 out_bf16 = tanh(acc + bias[n]); 1 out_bf16 = acc * (1 - aux[m,n]^2) (aux bf16);
+ *             2 out_f32 += acc (atomic, split-K; caller zeroes out); 3 out_f32 = acc + bias[n].
+ *   lda/ldb/ldo/ld_aux in elements; K multiple of 64 (K-major), N multiple of 64. */
+VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, void* out, int ldo, int M,
+                             int N, int K, int epilogue, const float* bias, const void* aux, int ld_aux,
+                             int splits, int mn_major, void* stream);
+VSS_API const char* vss_gemm_last_error(void);
+
 /* Philox4x32-10 known-answer hook (host side; same code as the device generator). */
 VSS_API void vss_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

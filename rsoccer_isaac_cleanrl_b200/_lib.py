@@ -60,6 +60,9 @@ _SYMBOLS = {
     "vss_step_count": (C.c_uint64, [_VP]),
     "vss_set_step_count": (C.c_int, [_VP, C.c_uint64]),
     "vss_gae": (C.c_int, [_VP] * 7 + [C.c_int32, C.c_int64, C.c_double, C.c_double, _VP]),
+    "vss_gemm_bf16_tn": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP,
+                                  _VP, C.c_int, C.c_int, C.c_int, _VP]),
+    "vss_gemm_last_error": (C.c_char_p, []),
     "vss_philox4x32_10": (None, [_VP, _VP, _VP]),
     "vss_last_error": (C.c_char_p, []),
     "vss_version": (C.c_char_p, []),
@@ -104,7 +107,8 @@ def load_library():
 
 def check(rc: int):
     if rc != 0:
-        msg = load_library().vss_last_error().decode()
+        lib = load_library()
+        msg = lib.vss_last_error().decode() or lib.vss_gemm_last_error().decode()
         raise RuntimeError(f"libvss_b200 error {rc}: {msg}")
 
 

@@ -1,0 +1,402 @@
+// tc_gemm.cu — hand-written tcgen05 GEMM for the PPO policy/value MLPs (sm_100a).
+//
+//   C[M,N] = epilogue( A[M,K] · B[N,K]^T ),  A and B bf16 row-major (K contiguous), fp32 accumulate in TMEM.
+//
+// Replaces the cuBLAS sgemm + bias + tanh launches behind `nn.Linear`/`nn.Tanh` of the reference's
+// `Agent` (ppo_continuous_action_isaacgym.py:127-164) and their autograd backward (:352).
+// One CTA = one 128 x BN output tile (optionally one K-split of it):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) into a 4-stage smem ring
+//   warp 1      TMEM allocator + MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16),
+//               tcgen05.commit releases smem stages / signals the accumulator
+//   warps 2-5   epilogue: tcgen05.ld 32 TMEM lanes x 32 columns per warp, fused bias+tanh /
+//               tanh-derivative / split-K fp32 atomics, vectorised global stores
+// Every mbarrier wait is bounded (trap instead of hanging the GPU).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "../../include/vss_b200.h"
+
+namespace tc {
+
+constexpr int BM = 128;       // CTA tile rows = UMMA M
+constexpr int BK = 64;        // k-block: 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;    // bf16
+constexpr int STAGES = 4;
+constexpr int THREADS = 192;
+
+enum Epilogue : int {
+  EPI_BIAS_TANH_BF16 = 0,  // out_bf16 = tanh(acc + bias[n])                       (forward hidden layer)
+  EPI_DTANH_BF16 = 1,      // out_bf16 = acc * (1 - aux[m,n]^2), aux bf16           (dgrad fused with tanh')
+  EPI_ATOMIC_F32 = 2,      // out_f32 += acc  (red.global.add.f32, split-K)         (wgrad)
+  EPI_BIAS_F32 = 3,        // out_f32 = acc + bias[n]                               (plain linear)
+};
+
+struct GemmArgs {
+  int M, N, K;             // problem; K multiple of 64, N multiple of BN
+  int k_blocks_per_split;  // k-blocks (of 64) handled by one blockIdx.z
+  void* out;               // bf16 or f32, row-major [M, ldo]
+  int ldo;
+  const float* bias;       // [N] or null
+  const __nv_bfloat16* aux;  // [M, ld_aux] for EPI_DTANH_BF16
+  int ld_aux;
+};
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 26); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  printf("tc_gemm: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+         threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 in [0,14), LBO (unused for swizzled K-major) in [16,30), SBO = 1024 B (8 rows
+// x 128 B) in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc_k128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D f32 [4,6)=1, A bf16 [7,10)=1, B bf16
+// [10,13)=1, both K-major (bits 15,16 = 0), N>>3 in [17,23), M>>4 in [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+// MN-major, 128-byte-swizzled operand (the GEMM's M or N index is the contiguous one in memory, as
+// for dW = dZ^T X where the batch is the reduction): the tile is stored as [k rows][64 mn elems]
+// boxes of 8 KB; LBO = 8192 B between 64-element MN atoms, SBO = 1024 B between 8-row K groups.
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+struct Smem {
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;   // 8 / 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI, bool MN>
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+          const __grid_constant__ GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Smem<BN>::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kb0 = blockIdx.z * g.k_blocks_per_split;
+  const int total_kb = g.K / BK;
+  const int nkb = min(g.k_blocks_per_split, total_kb - kb0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * Smem<BN>::STAGE_BYTES;
+        uint8_t* sb = sa + Smem<BN>::A_BYTES;
+        mbar_expect_tx(&full_bar[s], Smem<BN>::STAGE_BYTES);
+        if (!MN) {
+          tma_load_2d(sa, &map_a, &full_bar[s], (kb0 + kb) * BK, m0);
+          tma_load_2d(sb, &map_b, &full_bar[s], (kb0 + kb) * BK, n0);
+        } else {  // source tensors are [K, M] / [K, N]: 64 x 64 boxes, inner coordinate = m / n
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &map_a, &full_bar[s], m0 + 64 * i, (kb0 + kb) * BK);
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &map_b, &full_bar[s], n0 + 64 * i, (kb0 + kb) * BK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer
+      constexpr uint32_t idesc = make_idesc(BM, BN, MN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * Smem<BN>::STAGE_BYTES);
+        const uint64_t adesc = MN ? make_desc_mn128(sa) : make_desc_k128(sa);
+        const uint64_t bdesc = MN ? make_desc_mn128(sa + Smem<BN>::A_BYTES) : make_desc_k128(sa + Smem<BN>::A_BYTES);
+        // per K=16 step: K-major +32 B inside the swizzle row (>>4 = 2); MN-major +16 rows = 2048 B (>>4 = 128)
+        constexpr uint64_t kstep = MN ? 128 : 2;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_bf16(tmem_base, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
+        umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (nkb <= 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0;
+      }
+      if (row < g.M) {
+        const int col = n0 + c;
+        if (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16) {
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + col;
+          uint32_t packed[16];
+          if (EPI == EPI_BIAS_TANH_BF16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = tanh_fast(__uint_as_float(v[2 * i]) + __ldg(g.bias + col + 2 * i));
+              const float b = tanh_fast(__uint_as_float(v[2 * i + 1]) + __ldg(g.bias + col + 2 * i + 1));
+              __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+              packed[i] = *reinterpret_cast<uint32_t*>(&p);
+            }
+          } else {
+            const uint4* arow = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 y4 = __ldg(arow + j);
+              const uint32_t yy[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yy[i]);
+                const float ya = __bfloat162float(y2.x), yb = __bfloat162float(y2.y);
+                const float a = __uint_as_float(v[8 * j + 2 * i]) * (1.0f - ya * ya);
+                const float b = __uint_as_float(v[8 * j + 2 * i + 1]) * (1.0f - yb * yb);
+                __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+                packed[4 * j + i] = *reinterpret_cast<uint32_t*>(&p);
+              }
+            }
+          }
+          uint4* o4 = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        } else if (EPI == EPI_ATOMIC_F32) {
+          float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(orow + i, __uint_as_float(v[i]));
+        } else {
+          float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o;
+            o.x = __uint_as_float(v[4 * j]) + (g.bias ? __ldg(g.bias + col + 4 * j) : 0.0f);
+            o.y = __uint_as_float(v[4 * j + 1]) + (g.bias ? __ldg(g.bias + col + 4 * j + 1) : 0.0f);
+            o.z = __uint_as_float(v[4 * j + 2]) + (g.bias ? __ldg(g.bias + col + 4 * j + 2) : 0.0f);
+            o.w = __uint_as_float(v[4 * j + 3]) + (g.bias ? __ldg(g.bias + col + 4 * j + 3) : 0.0f);
+            reinterpret_cast<float4*>(orow)[j] = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (ld elements between rows), box = 64 cols x box_rows, 128B swizzle.
+// Out-of-bounds box elements read as zero.
+static bool make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int EPI, bool MN>
+static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tn<BN, EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Smem<BN>::TOTAL);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((g.M + BM - 1) / BM, g.N / BN, splits);
+  k_gemm_tn<BN, EPI, MN><<<grid, THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+
+extern thread_local std::string g_tc_error;
+thread_local std::string g_tc_error;
+
+extern "C" {
+
+VSS_API const char* vss_gemm_last_error(void) { return g_tc_error.c_str(); }
+
+// C[M,N] = epi(op(A) * op(B)^T), bf16 operands, fp32 accumulation on the tensor cores.
+//   mn_major = 0: A is [M,K], B is [N,K] row-major (K contiguous) — forward and dgrad.
+//   mn_major = 1: A is [K,M], B is [K,N] row-major (the reduction index is the row) — wgrad
+//                 dW[N_out,K_in] = sum_batch dZ[batch,N_out] * X[batch,K_in], no transposes needed.
+// lda/ldb in elements (multiples of 8). K: multiple of 64, or ragged with mn_major (TMA zero-fills
+// rows past K). N multiple of 64. epilogue: see tc::Epilogue. splits > 1 only with EPI_ATOMIC_F32
+// (the caller zeroes `out`). Returns 0 or a negative VSS_E_* code (message: vss_gemm_last_error).
+VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, void* out, int ldo, int M, int N, int K,
+                             int epilogue, const float* bias, const void* aux, int ld_aux, int splits, int mn_major,
+                             void* stream) {
+  using namespace tc;
+  if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) { g_tc_error = "vss_gemm_bf16_tn: bad argument"; return VSS_E_INVALID; }
+  if ((!mn_major && K % BK != 0) || N % 64 != 0 || lda % 8 != 0 || ldb % 8 != 0 || (mn_major && M % 128 != 0)) {
+    g_tc_error = "vss_gemm_bf16_tn: K must be a multiple of 64 (K-major), N of 64, lda/ldb of 8, M of 128 (MN-major)";
+    return VSS_E_INVALID;
+  }
+  if (splits < 1) splits = 1;
+  if (splits > 1 && epilogue != EPI_ATOMIC_F32) { g_tc_error = "vss_gemm_bf16_tn: split-K needs the atomic epilogue"; return VSS_E_INVALID; }
+  if ((epilogue == EPI_BIAS_TANH_BF16 && !bias) || (epilogue == EPI_DTANH_BF16 && !aux)) {
+    g_tc_error = "vss_gemm_bf16_tn: missing bias/aux"; return VSS_E_INVALID;
+  }
+  const int bn = (N % 128 == 0) ? 128 : 64;
+  CUtensorMap ma, mb;
+  const bool ok = mn_major ? (make_map(&ma, A, K, M, lda, BK) && make_map(&mb, B, K, N, ldb, BK))
+                           : (make_map(&ma, A, M, K, lda, BM) && make_map(&mb, B, N, K, ldb, bn));
+  if (!ok) {
+    g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA;
+  }
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.K = (K + BK - 1) / BK * BK;  // ragged K (MN-major only): the TMA zero-fills the tail rows
+  const int total_kb = g.K / BK;
+  g.k_blocks_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + g.k_blocks_per_split - 1) / g.k_blocks_per_split;
+  g.out = out; g.ldo = ldo; g.bias = bias; g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ld_aux = ld_aux;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+#define TC_CASE(BNV, EPIV, MNV) \
+  if (bn == BNV && epilogue == EPIV && (mn_major != 0) == MNV) e = launch<BNV, EPIV, MNV>(ma, mb, g, splits, st); else
+  TC_CASE(128, EPI_BIAS_TANH_BF16, false) TC_CASE(64, EPI_BIAS_TANH_BF16, false)
+  TC_CASE(128, EPI_DTANH_BF16, false) TC_CASE(64, EPI_DTANH_BF16, false)
+  TC_CASE(128, EPI_ATOMIC_F32, false) TC_CASE(64, EPI_ATOMIC_F32, false)
+  TC_CASE(128, EPI_BIAS_F32, false) TC_CASE(64, EPI_BIAS_F32, false)
+  TC_CASE(128, EPI_ATOMIC_F32, true) TC_CASE(64, EPI_ATOMIC_F32, true)
+  { g_tc_error = "vss_gemm_bf16_tn: unsupported epilogue / layout combination"; return VSS_E_INVALID; }
+#undef TC_CASE
+  if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
+  return VSS_OK;
+}
+
+}  // extern "C"

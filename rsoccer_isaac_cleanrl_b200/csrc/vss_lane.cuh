@@ -30,8 +30,8 @@
 namespace vss {
 
 constexpr int LDS = 33;       // shared-memory column stride in words
-constexpr int W_PREV = 60;    // 14 words: ball xy, then robot xy x6, before physics
-constexpr int SM_WORDS = 74;  // words per field staged in shared memory
+constexpr int W_PREV = 60;    // 7 words of pre-physics reward terms: ball potential, 6 robot-ball distances
+constexpr int SM_WORDS = 67;  // words per field staged in shared memory
 constexpr int QUEUE_WORDS = 48; // per-warp (field, robot) wall-task queue: 32 x 6 bytes
 constexpr int TILE_WORDS = SM_WORDS * 33 + QUEUE_WORDS;  // shared-memory words per warp
 constexpr int F4_PER_FIELD = VSS_OBS_PER_FIELD / 4;  // 78 float4 per (2,3,52) observation
@@ -522,9 +522,10 @@ VSS_HD float ball_potential(float bx, float by, float gx) {
 }
 VSS_HD bool is_goal(float bx, float by, const DevParams& P) { return fabsf(bx) > P.HL && fabsf(by) < P.GH; }
 
-// rew[r*4 + c] for r = team*3 + idx. Uses the pre-physics positions staged at W_PREV.
+// rew[r*4 + c] for r = team*3 + idx. The "prev" halves of the grad and move terms (functions
+// of the pre-physics positions only, vss.py:219-220) were staged at W_PREV before the physics.
 VSS_HD void rewards_lane(const float* S, const DevParams& P, float rew[VSS_REW_PER_FIELD]) {
-  const float bx = S[0], by = S[LDS], pbx = S[W_PREV * LDS], pby = S[(W_PREV + 1) * LDS];
+  const float bx = S[0], by = S[LDS];
 #pragma unroll
   for (int k = 0; k < VSS_REW_PER_FIELD; ++k) rew[k] = 0.0f;
   if (P.w_goal > 0.0f) {
@@ -537,16 +538,15 @@ VSS_HD void rewards_lane(const float* S, const DevParams& P, float rew[VSS_REW_P
     for (int r = 0; r < 6; ++r) rew[4 * r + 0] = fmul(r < 3 ? gv : gy, P.w_goal);
   }
   if (P.w_grad > 0.0f) {
-    const float grad = fsub(ball_potential(bx, by, P.HL), ball_potential(pbx, pby, P.HL));
+    const float grad = fsub(ball_potential(bx, by, P.HL), S[W_PREV * LDS]);
 #pragma unroll
     for (int r = 0; r < 6; ++r) rew[4 * r + 1] = fmul(r < 3 ? grad : -grad, P.w_grad);
   }
   if (P.w_move > 0.0f) {
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      const float px = S[(W_PREV + 2 + 2 * r) * LDS], py = S[(W_PREV + 3 + 2 * r) * LDS];
       const float x = S[(4 + 9 * r) * LDS], y = S[(5 + 9 * r) * LDS];
-      const float p_dist = norm2(fsub(px, pbx), fsub(py, pby));
+      const float p_dist = S[(W_PREV + 1 + r) * LDS];
       const float dist = norm2(fsub(x, bx), fsub(y, by));
       rew[4 * r + 2] = fmul(fsub(p_dist, dist), P.w_move);
     }
@@ -711,11 +711,12 @@ VSS_HD void lane_phase1a(float* S, long long env, const StepArgs& a, const DevPa
     S[(12 + 9 * r) * LDS] = clampf(act[2 * r + 1], -1.0f, 1.0f);
   }
   // prev_* clones, vss.py:219-220
-  S[W_PREV * LDS] = S[0]; S[(W_PREV + 1) * LDS] = S[LDS];
+  {
+    const float pbx = S[0], pby = S[LDS];
+    S[W_PREV * LDS] = ball_potential(pbx, pby, P.HL);
 #pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    S[(W_PREV + 2 + 2 * r) * LDS] = S[(4 + 9 * r) * LDS];
-    S[(W_PREV + 3 + 2 * r) * LDS] = S[(5 + 9 * r) * LDS];
+    for (int r = 0; r < 6; ++r)
+      S[(W_PREV + 1 + r) * LDS] = norm2(fsub(S[(4 + 9 * r) * LDS], pbx), fsub(S[(5 + 9 * r) * LDS], pby));
   }
 }
 

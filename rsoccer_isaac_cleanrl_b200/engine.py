@@ -129,3 +129,36 @@ def gae(rewards, values, next_values, next_dones, next_timeouts, gamma=0.99, gae
                       int(T), int(N), float(gamma), float(gae_lambda),
                       torch.cuda.current_stream(rewards.device).cuda_stream))
     return advantages, returns
+
+
+EPI_BIAS_TANH_BF16, EPI_DTANH_BF16, EPI_ATOMIC_F32, EPI_BIAS_F32 = 0, 1, 2, 3
+
+
+def gemm_bf16(a, b, out, epilogue, bias=None, aux=None, splits=1, mn_major=False):
+    """tcgen05 GEMM (csrc/tc_gemm.cu). K-major: a [M,K], b [N,K]; MN-major: a [K,M], b [K,N]; bf16, last
+    dimension contiguous. out [M,N] bf16 (epilogues 0,1) or f32 (2,3)."""
+    lib = _lib.load_library()
+    if mn_major:
+        K, M = a.shape
+        N = b.shape[1]
+        assert b.shape[0] == K
+    else:
+        M, K = a.shape
+        N = b.shape[0]
+        assert b.shape[1] == K
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    assert out.shape == (M, N) and out.stride(1) == 1
+    assert out.dtype == (torch.bfloat16 if epilogue in (EPI_BIAS_TANH_BF16, EPI_DTANH_BF16) else torch.float32)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    ld_aux = 0
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16 and aux.shape == (M, N) and aux.stride(1) == 1
+        ld_aux = aux.stride(0)
+    rc = lib.vss_gemm_bf16_tn(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
+                              M, N, K, int(epilogue), None if bias is None else bias.data_ptr(),
+                              None if aux is None else aux.data_ptr(), ld_aux, int(splits), int(bool(mn_major)),
+                              torch.cuda.current_stream(a.device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"vss_gemm_bf16_tn failed ({rc}): {lib.vss_gemm_last_error().decode()}")
+    return out

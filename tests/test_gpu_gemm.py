@@ -1,0 +1,78 @@
+"""GPU: the hand-written tcgen05 GEMM (csrc/tc_gemm.cu) against a plain PyTorch fp32 reference of the
+same op on the same bf16-rounded operands. Tolerance: fp32 accumulation of bf16 products ->
+|err| <= 2e-3 * sqrt(K) * scale for f32 outputs; bf16 outputs add one bf16 rounding (2^-8 relative)
+and the tanh.approx error (2^-11)."""
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 64), (4096, 512, 256), (300, 256, 512), (131072, 512, 512),
+                                   (1000, 64, 256)])
+def test_forward_bias_tanh(M, N, K):
+    from rsoccer_isaac_cleanrl_b200.engine import EPI_BIAS_TANH_BF16, gemm_bf16
+    a, w = _rand((M, K), 1), _rand((N, K), 2, K ** -0.5)
+    bias = torch.randn(N, device="cuda") * 0.1
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    gemm_bf16(a, w, out, EPI_BIAS_TANH_BF16, bias=bias)
+    ref = torch.tanh(a.float() @ w.float().t() + bias)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 1.2e-2, err
+
+
+def test_bias_f32_and_padded_input():
+    from rsoccer_isaac_cleanrl_b200.engine import EPI_BIAS_F32, gemm_bf16
+    M, N = 1024, 256
+    x = torch.zeros((M, 64), device="cuda", dtype=torch.bfloat16)   # 52 observation columns padded to 64
+    x[:, :52] = _rand((M, 52), 3)
+    w = torch.zeros((N, 64), device="cuda", dtype=torch.bfloat16)
+    w[:, :52] = _rand((N, 52), 4, 52 ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    out = torch.empty((M, N), device="cuda")
+    gemm_bf16(x, w, out, EPI_BIAS_F32, bias=bias)
+    ref = x[:, :52].float() @ w[:, :52].float().t() + bias
+    assert (out - ref).abs().max().item() < 2e-3
+
+
+def test_dgrad_fused_tanh_derivative():
+    from rsoccer_isaac_cleanrl_b200.engine import EPI_DTANH_BF16, gemm_bf16
+    M, N_out, K_in = 2048, 512, 256
+    dz, wt = _rand((M, N_out), 5), _rand((K_in, N_out), 6, N_out ** -0.5)   # wt = W^T, [K_in, N_out]
+    y = torch.tanh(_rand((M, K_in), 7).float()).to(torch.bfloat16)          # activations feeding this layer
+    out = torch.empty((M, K_in), device="cuda", dtype=torch.bfloat16)
+    gemm_bf16(dz, wt, out, EPI_DTANH_BF16, aux=y)
+    ref = (dz.float() @ wt.float().t()) * (1 - y.float() ** 2)
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("batch,N_out,K_in,splits", [(4096, 256, 64, 8), (8192, 512, 256, 16), (4000, 512, 512, 7),
+                                                     (131072, 256, 512, 32)])
+def test_wgrad_mn_major_split_k(batch, N_out, K_in, splits):
+    from rsoccer_isaac_cleanrl_b200.engine import EPI_ATOMIC_F32, gemm_bf16
+    dz, x = _rand((batch, N_out), 8, 0.1), _rand((batch, K_in), 9)
+    dw = torch.zeros((N_out, K_in), device="cuda")
+    gemm_bf16(dz, x, dw, EPI_ATOMIC_F32, splits=splits, mn_major=True)
+    ref = dz.float().t() @ x.float()
+    scale = ref.abs().max().item()
+    assert (dw - ref).abs().max().item() < 2e-3 * scale + 1e-3, ((dw - ref).abs().max().item(), scale)
+
+
+def test_split_k_k_major_atomic():
+    from rsoccer_isaac_cleanrl_b200.engine import EPI_ATOMIC_F32, gemm_bf16
+    a, b = _rand((256, 1024), 10), _rand((128, 1024), 11, 1 / 32)
+    out = torch.zeros((256, 128), device="cuda")
+    gemm_bf16(a, b, out, EPI_ATOMIC_F32, splits=4)
+    ref = a.float() @ b.float().t()
+    assert (out - ref).abs().max().item() < 5e-3
