@@ -99,19 +99,26 @@ def _mlp(n_in, n_out, out_std):
 class Agent(nn.Module):
     """Two independent 52-256-512-512-256-{A,1} tanh MLPs + state-independent log-std."""
 
-    def __init__(self, envs):
+    def __init__(self, envs, mlp_backend="torch"):
         super().__init__()
+        self.mlp_backend = mlp_backend  # "tc": tcgen05 GEMMs (bf16 in, fp32 accumulate); "torch": fp32 library
         n_obs = int(np.array(envs.single_observation_space.shape).prod())
         n_act = int(np.prod(envs.single_action_space.shape))
         self.critic = _mlp(n_obs, 1, 1.0)
         self.actor_mean = _mlp(n_obs, n_act, 0.01)
         self.actor_logstd = nn.Parameter(torch.zeros(1, n_act))
 
+    def _mlp(self, seq, x):
+        if self.mlp_backend == "tc" and x.is_cuda:
+            from .tc_mlp import mlp_forward
+            return mlp_forward(seq, x.contiguous())
+        return seq(x)
+
     def get_value(self, x):
-        return self.critic(x)
+        return self._mlp(self.critic, x)
 
     def get_action_and_value(self, x, action=None):
-        action_mean = self.actor_mean(x)
+        action_mean = self._mlp(self.actor_mean, x)
         action_logstd = self.actor_logstd.expand_as(action_mean)
         action_std = torch.exp(action_logstd)
         if action is None:
@@ -120,7 +127,7 @@ class Agent(nn.Module):
         var = action_std * action_std
         logp = (-((action - action_mean) ** 2) / (2 * var) - action_logstd - 0.5 * np.log(2 * np.pi)).sum(1)
         entropy = (0.5 + 0.5 * np.log(2 * np.pi) + action_logstd).sum(1)
-        return action, logp, entropy, self.critic(x)
+        return action, logp, entropy, self._mlp(self.critic, x)
 
 
 class ExtractObsWrapper(ObservationWrapper):
@@ -184,7 +191,8 @@ def train(args, log=print):
     envs.single_observation_space = envs.observation_space
 
     torch.manual_seed(args.seed)  # identical initial weights on every rank
-    agent = Agent(envs).to(device)
+    backend = "tc" if args.mlp_backend in ("auto", "tc") else "torch"
+    agent = Agent(envs, mlp_backend=backend).to(device)
     torch.manual_seed(args.seed + 1000 * (rank + 1))
     flat, flat_grad = flatten_parameters(agent)
     if world > 1:
@@ -301,6 +309,7 @@ def train(args, log=print):
                 f"ep_ret(last) {r.mean().item():.3f}")
     stats.update(global_step=global_step, wall=time.time() - start_time, rollout_s=t_roll, update_s=t_upd,
                  final_sps=(global_step / max(time.time() - start_time, 1e-9)))
+    stats["mlp_backend"] = "tcgen05-bf16" if backend == "tc" else "torch-fp32"
     stats["agent"] = agent
     stats["env"] = unwrapped_env
     return stats

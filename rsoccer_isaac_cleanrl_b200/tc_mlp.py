@@ -1,0 +1,82 @@
+"""The Agent's tanh MLPs on the hand-written tcgen05 GEMM (csrc/tc_gemm.cu).
+
+`TCMlp.apply(x, W0, b0, ..., W4, b4)` computes the reference's
+`Linear-Tanh-Linear-Tanh-Linear-Tanh-Linear-Tanh-Linear` stack
+(ppo_continuous_action_isaacgym.py:130-152) and its backward pass with:
+  forward  4 x  h = tanh(h W^T + b)            one GEMM each, bias+tanh fused in the TMEM epilogue
+  dgrad    3 x  dZ_prev = (dZ W) * (1 - h^2)    one GEMM each, tanh' fused in the epilogue
+  wgrad    4 x  dW = dZ^T h                     one split-K GEMM each on MN-major operands (no transposes)
+Operands are bf16 (activations and a per-call bf16 copy of the fp32 master weights), accumulation
+is fp32 in TMEM. The 256 -> {1,2,6} head and the bias gradients (column sums) stay on CUDA cores.
+"""
+import torch
+
+from .engine import EPI_ATOMIC_F32, EPI_BIAS_TANH_BF16, EPI_DTANH_BF16, gemm_bf16
+
+_SM_TARGET = 296  # ~2 CTAs' worth of split-K work per SM for the wgrad grids
+
+
+def _splits(n_out, k_in, batch):
+    tiles = (n_out // 128) * max(1, k_in // (128 if k_in % 128 == 0 else 64))
+    return max(1, min((batch + 63) // 64, -(-_SM_TARGET // tiles)))
+
+
+class TCMlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, *params):
+        assert len(params) == 10 and x.is_cuda and x.dtype == torch.float32
+        ws, bs = params[0::2], params[1::2]
+        M, n_in = x.shape
+        k0 = (n_in + 63) // 64 * 64
+        x16 = torch.zeros((M, k0), device=x.device, dtype=torch.bfloat16)
+        x16[:, :n_in] = x
+        w0 = torch.zeros((ws[0].shape[0], k0), device=x.device, dtype=torch.bfloat16)
+        w0[:, :n_in] = ws[0]
+        w16 = [w0] + [w.to(torch.bfloat16) for w in ws[1:4]]
+        hs = [x16]
+        for l in range(4):
+            h = torch.empty((M, w16[l].shape[0]), device=x.device, dtype=torch.bfloat16)
+            gemm_bf16(hs[-1], w16[l], h, EPI_BIAS_TANH_BF16, bias=bs[l].contiguous())
+            hs.append(h)
+        out = torch.addmm(bs[4], hs[4].float(), ws[4].t())
+        ctx.save_for_backward(*hs, *ws)
+        ctx.n_in = n_in
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved = ctx.saved_tensors
+        hs, ws = saved[:5], saved[5:]
+        M = dout.shape[0]
+        dev = dout.device
+        grads = [None] * 10
+        dout = dout.contiguous()
+        h4f = hs[4].float()
+        grads[8] = dout.t() @ h4f                       # dW4
+        grads[9] = dout.sum(0)                          # db4
+        dz = ((dout @ ws[4]) * (1.0 - h4f * h4f)).to(torch.bfloat16)   # dZ of hidden layer 3
+        del h4f
+        for l in (3, 2, 1, 0):
+            n_out, k_in = dz.shape[1], hs[l].shape[1]
+            dw = torch.zeros((n_out, k_in), device=dev, dtype=torch.float32)
+            gemm_bf16(dz, hs[l], dw, EPI_ATOMIC_F32, splits=_splits(n_out, k_in, M), mn_major=True)
+            grads[2 * l] = dw[:, :ctx.n_in] if l == 0 else dw
+            grads[2 * l + 1] = dz.sum(0, dtype=torch.float32)
+            if l > 0:
+                wt = ws[l].t().contiguous().to(torch.bfloat16)          # [k_in, n_out]
+                dz_prev = torch.empty((M, k_in), device=dev, dtype=torch.bfloat16)
+                gemm_bf16(dz, wt, dz_prev, EPI_DTANH_BF16, aux=hs[l])
+                dz = dz_prev
+        return (None, *grads)
+
+
+def mlp_params(seq):
+    """(W0, b0, ..., W4, b4) of an nn.Sequential(Linear, Tanh, ..., Linear)."""
+    out = []
+    for i in (0, 2, 4, 6, 8):
+        out += [seq[i].weight, seq[i].bias]
+    return out
+
+
+def mlp_forward(seq, x):
+    return TCMlp.apply(x, *mlp_params(seq))

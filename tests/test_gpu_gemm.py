@@ -76,3 +76,37 @@ def test_split_k_k_major_atomic():
     gemm_bf16(a, b, out, EPI_ATOMIC_F32, splits=4)
     ref = a.float() @ b.float().t()
     assert (out - ref).abs().max().item() < 5e-3
+
+
+def test_tc_mlp_matches_fp32_agent_forward_and_backward():
+    """The tcgen05 MLP against the reference-shaped fp32 torch Agent (bf16 tolerance)."""
+    import types
+    from rsoccer_isaac_cleanrl_b200 import ppo
+    envs = types.SimpleNamespace(single_observation_space=types.SimpleNamespace(shape=(52,)),
+                                 single_action_space=types.SimpleNamespace(shape=(2,)))
+    torch.manual_seed(0)
+    ref = ppo.Agent(envs, "torch").cuda()
+    tc = ppo.Agent(envs, "tc").cuda()
+    tc.load_state_dict(ref.state_dict())
+    with torch.no_grad():  # make the heads non-trivial (actor head is initialised with std 0.01)
+        for a in (ref, tc):
+            a.actor_mean[8].weight.mul_(30.0)
+    tc.load_state_dict(ref.state_dict())
+    M = 4096 + 77
+    x = torch.randn(M, 52, device="cuda")
+    act = torch.randn(M, 2, device="cuda")
+    adv = torch.randn(M, device="cuda")
+    outs = []
+    for a in (ref, tc):
+        a.zero_grad()
+        _, logp, ent, v = a.get_action_and_value(x, act)
+        loss = (-(adv * logp).mean()) + 0.5 * (v.view(-1) ** 2).mean() - 0.01 * ent.mean()
+        loss.backward()
+        outs.append((logp.detach(), v.detach(), {k: p.grad.clone() for k, p in a.named_parameters()}))
+    (lp0, v0, g0), (lp1, v1, g1) = outs
+    assert (v0 - v1).abs().max().item() < 0.05 * v0.abs().max().item() + 0.02
+    assert (lp0 - lp1).abs().max().item() < 0.05 * lp0.abs().max().item() + 0.05
+    for k in g0:
+        num = (g0[k] - g1[k]).norm().item()
+        den = g0[k].norm().item() + 1e-12
+        assert num / den < 0.06, (k, num / den)
