@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--sweep", action="store_true", help="also time N in {1K..1M} (config 5) into `sweep`")
     ap.add_argument("--ppo-env-id", default="sa")
     ap.add_argument("--ppo-envs", type=int, default=4096, help="agents per GPU of the PPO leg (configs[1])")
-    ap.add_argument("--ppo-updates", type=int, default=4)
+    ap.add_argument("--ppo-updates", type=int, default=6)
     return ap.parse_args()
 
 
@@ -276,7 +276,13 @@ def run_native(args):
         sps_list = st["sps"]
         # SPS exactly as ppo…:376 (global_step / wall since start), plus the steady-state rate of the
         # updates after the first (which pays one-off allocation and cuBLAS/NCCL initialisation)
+        # steady state: updates after the eager first one and the graph-capturing second one
+        tail_r, tail_u = st["rollout_wall"][2:] or st["rollout_wall"], st["update_wall"][2:] or st["update_wall"]
+        per_update = sorted(a + b for a, b in zip(tail_r, tail_u))[len(tail_r) // 2]
         ppo_res = {"sps": st["final_sps"], "unit": "samples/s (global_step / wall, ppo…:257,376), all GPUs",
+                   "sps_steady": args.ppo_envs * 128 * world / per_update,
+                   "steady_note": "median over updates >= 3 (update 1 runs eagerly, update 2 records the CUDA graphs)",
+                   "rollout_s_steady": sorted(tail_r)[len(tail_r) // 2], "update_s_steady": sorted(tail_u)[len(tail_u) // 2],
                    "workload": f"ppo-{args.ppo_env_id}, {args.ppo_envs} agents per GPU x 128 steps, 4 minibatches x "
                                f"8 epochs, {st['updates']} updates, defaults of ppo…:71-108",
                    "rollout_s": st["rollout_s"], "update_s": st["update_s"], "wall_s": st["wall"],

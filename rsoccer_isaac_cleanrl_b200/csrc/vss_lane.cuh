@@ -640,7 +640,9 @@ constexpr int VIEW_FULL = -1;
 
 struct StepArgs {
   float* state; long long n, ld; unsigned long long goff;
-  uint32_t seed_lo, seed_hi, step;
+  uint32_t seed_lo, seed_hi;
+  const uint32_t* step_ptr;    // device-resident step index (keys the OU stream); bumped after every step so
+                               // that a CUDA graph replaying the launch still advances it
   const float* actions;        // full: (N,2,3,2)
   const float* inject;         // injected post-physics state (58 x ld) or null
   long long* reset_buf;        // (N) io
@@ -692,7 +694,7 @@ VSS_HD void lane_phase1a(float* S, long long env, const StepArgs& a, const DevPa
     }
   }
   if (VIEW != VIEW_FULL) {
-    ou_lane(act, P, key, a.step);  // action_buf = random_ou(action_buf)
+    ou_lane(act, P, key, *a.step_ptr);  // action_buf = random_ou(action_buf)
     if (VIEW == VSS_VIEW_SA) {     // act_view[:] = action
       act[0] = a.policy_action[2 * env]; act[1] = a.policy_action[2 * env + 1];
     } else {  // cma (N,6) and dma (3N,2): the same 6 contiguous floats per field

@@ -98,6 +98,9 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   if (active) lane_phase5<VIEW>(S, env, a, done);
 }
 
+// Advances the device-resident step index after a step (stream-ordered, so graph replays see it).
+__global__ void k_bump(uint32_t* ctr) { *ctr += 1u; }
+
 // reset_dones() + compute_observations(): vss.py:72-73, 267-333, 205-216
 __global__ void __launch_bounds__(128)
 k_reset_dones(float* state, long long n, long long ld, unsigned long long goff, uint32_t seed_lo,
@@ -184,7 +187,7 @@ struct vss_engine {
   int device;
   int64_t n, ld, goff;
   uint64_t seed;
-  uint64_t step_count;
+  uint32_t* d_step;  // device-resident step index
   vss_params params;
   DevParams dp;
   float* state;
@@ -225,7 +228,7 @@ static StepArgs base_args(vss_handle h) {
   StepArgs a;
   memset(&a, 0, sizeof(a));
   a.state = h->state; a.n = h->n; a.ld = h->ld; a.goff = (unsigned long long)h->goff;
-  a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.step = (uint32_t)h->step_count;
+  a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.step_ptr = h->d_step;
   return a;
 }
 
@@ -235,7 +238,8 @@ static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
   launch_cfg(h->n, &wpb, &grid, &smem);
   k_step<VIEW, INJECT><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
   VSS_CUDA(cudaGetLastError());
-  h->step_count += 1;
+  k_bump<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_step);
+  VSS_CUDA(cudaGetLastError());
   return VSS_OK;
 }
 
@@ -284,12 +288,14 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
   vss_engine* h = new (std::nothrow) vss_engine();
   if (!h) return fail(VSS_E_NOMEM, "vss_create: host allocation failed");
   h->device = device; h->n = num_envs; h->ld = (num_envs + 31) / 32 * 32; h->goff = global_env_offset;
-  h->seed = seed; h->step_count = 0; h->params = *p; h->dp = derive_params(*p); h->state = nullptr;
+  h->seed = seed; h->d_step = nullptr; h->params = *p; h->dp = derive_params(*p); h->state = nullptr;
   const size_t bytes = sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld;
   e = cudaMalloc(&h->state, bytes);
   if (e != cudaSuccess) { delete h; return fail(VSS_E_NOMEM, "vss_create: cudaMalloc(state)", e); }
   e = cudaMemset(h->state, 0, bytes);
-  if (e != cudaSuccess) { cudaFree(h->state); delete h; return fail(VSS_E_CUDA, "vss_create: cudaMemset", e); }
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_step, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->d_step, 0, sizeof(uint32_t));
+  if (e != cudaSuccess) { cudaFree(h->state); cudaFree(h->d_step); delete h; return fail(VSS_E_CUDA, "vss_create: cudaMemset", e); }
   *out = h;
   return VSS_OK;
 }
@@ -297,16 +303,26 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
 VSS_API int vss_destroy(vss_handle h) {
   if (!h) return VSS_OK;
   cudaFree(h->state);
+  cudaFree(h->d_step);
   delete h;
   return VSS_OK;
 }
 
 VSS_API int64_t vss_num_envs(vss_handle h) { return h ? h->n : 0; }
 VSS_API int64_t vss_state_ld(vss_handle h) { return h ? h->ld : 0; }
-VSS_API uint64_t vss_step_count(vss_handle h) { return h ? h->step_count : 0; }
+// The counter lives on the device; these two synchronise (tests / checkpointing only).
+VSS_API uint64_t vss_step_count(vss_handle h) {
+  if (!h) return 0;
+  uint32_t v = 0;
+  if (use_device(h) != VSS_OK) return 0;
+  if (cudaMemcpy(&v, h->d_step, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return v;
+}
 VSS_API int vss_set_step_count(vss_handle h, uint64_t n) {
   if (!h) return fail(VSS_E_INVALID, "null handle");
-  h->step_count = n;
+  if (int rc = use_device(h)) return rc;
+  const uint32_t v = (uint32_t)n;
+  VSS_CUDA(cudaMemcpy(h->d_step, &v, sizeof(v), cudaMemcpyHostToDevice));
   return VSS_OK;
 }
 

@@ -74,6 +74,8 @@ def parse_args(argv=None):
     p.add_argument("--save-path", type=str, default="runs")
     p.add_argument("--mlp-backend", type=str, default="auto", choices=["auto", "tc", "torch"],
                    help="tc: hand-written tcgen05 GEMMs (bf16 in, fp32 accumulate); torch: fp32 library GEMMs")
+    p.add_argument("--cuda-graph", type=b, default=True, nargs="?", const=True,
+                   help="capture the whole T-step rollout (+ critic on terminal obs + GAE) in one CUDA graph")
     p.add_argument("--quiet", type=b, default=False, nargs="?", const=True)
     args = p.parse_args(argv)
     args.batch_size = int(args.num_envs * args.num_steps)
@@ -153,22 +155,33 @@ def flatten_parameters(module):
 
 
 class FlatAdam:
-    """Adam (eps 1e-5, no weight decay; torch.optim.Adam semantics) over the flat buffer."""
+    """Adam (eps 1e-5, no weight decay; torch.optim.Adam semantics) over the flat buffer. The step
+    count and the learning rate live in device tensors so that step() can sit inside a CUDA graph."""
 
     def __init__(self, flat, flat_grad, lr, eps=1e-5, betas=(0.9, 0.999)):
-        self.flat, self.grad, self.lr, self.eps, self.b1, self.b2 = flat, flat_grad, lr, eps, betas[0], betas[1]
-        self.m, self.v, self.t = torch.zeros_like(flat), torch.zeros_like(flat), 0
+        self.flat, self.grad, self.eps, self.b1, self.b2 = flat, flat_grad, eps, betas[0], betas[1]
+        self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+        self.t = torch.zeros((), device=flat.device, dtype=torch.float32)
+        self.lr_t = torch.full((), lr, device=flat.device, dtype=torch.float32)
         self.param_groups = [{"lr": lr}]
+        self._lr_host = lr
+
+    def sync_lr(self):
+        """Push param_groups[0]['lr'] (annealing / adaptive schedule) to the device scalar."""
+        lr = self.param_groups[0]["lr"]
+        if lr != self._lr_host:
+            self.lr_t.fill_(lr)
+            self._lr_host = lr
 
     def step(self):
-        self.t += 1
-        lr = self.param_groups[0]["lr"]
         g = self.grad
+        self.t += 1
         self.m.mul_(self.b1).add_(g, alpha=1 - self.b1)
         self.v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
-        bc1, bc2 = 1 - self.b1 ** self.t, 1 - self.b2 ** self.t
-        denom = (self.v.sqrt() / (bc2 ** 0.5)).add_(self.eps)
-        self.flat.addcdiv_(self.m, denom, value=-lr / bc1)
+        bc1 = 1 - torch.pow(self.b1, self.t)
+        bc2 = 1 - torch.pow(self.b2, self.t)
+        denom = (self.v.sqrt() / bc2.sqrt()).add_(self.eps)
+        self.flat.sub_((self.m / denom) * (self.lr_t / bc1))
 
 
 def train(args, log=print):
@@ -207,25 +220,18 @@ def train(args, log=print):
     advantages, returns = z(T, N), z(T, N)
     term_obs_all = z(T, N, *oshape)
 
-    global_step = 0
-    start_time = time.time()
-    next_obs = envs.reset()
-    num_updates = args.total_timesteps // (args.batch_size * world)
-    stats = {"sps": [], "updates": 0}
-    t_roll = t_upd = 0.0
-    for update in range(1, num_updates + 1):
-        if args.anneal_lr:
-            optimizer.param_groups[0]["lr"] = (1.0 - (update - 1.0) / num_updates) * args.learning_rate
-        tr0 = time.time()
+    def rollout(first_obs):
+        """T env steps + V(terminal obs) + GAE (ppo…:256-296). No host sync anywhere, so the whole
+        thing can be captured in a CUDA graph."""
+        cur = first_obs
         with torch.no_grad():
             for step in range(T):
-                global_step += N * world
-                obs[step] = next_obs
-                action, logprob, _, value = agent.get_action_and_value(next_obs)
+                obs[step] = cur
+                action, logprob, _, value = agent.get_action_and_value(cur)
                 values[step] = value.flatten()
                 actions[step] = action
                 logprobs[step] = logprob
-                next_obs, rewards[step], next_done, info = envs.step(action)
+                cur, rewards[step], next_done, info = envs.step(action)
                 next_dones[step] = next_done
                 next_timeouts[step] = info["time_outs"]
                 term_obs_all[step] = info["terminal_observation"]
@@ -233,56 +239,117 @@ def train(args, log=print):
             next_values.copy_(agent.get_value(term_obs_all.view(T * N, *oshape)).view(T, N))
             gae_kernel(rewards, values, next_values, next_dones, next_timeouts, args.gamma, args.gae_lambda,
                        advantages, returns)
+        return cur
+
+    b_obs = obs.reshape((-1,) + oshape)
+    b_logprobs, b_actions = logprobs.reshape(-1), actions.reshape((-1,) + ashape)
+    b_advantages, b_returns, b_values = advantages.reshape(-1), returns.reshape(-1), values.reshape(-1)
+    mb_inds = torch.zeros(args.minibatch_size, dtype=torch.long, device=device)
+    clipfrac_sum = torch.zeros((), device=device)
+    mb_stats = {k: torch.zeros((), device=device) for k in
+                ("v_loss", "pg_loss", "entropy", "old_approx_kl", "approx_kl")}
+
+    def forward_backward():
+        """One minibatch: clipped-surrogate loss and its gradient into flat_grad (ppo…:314-352).
+        Reads the static index buffer mb_inds; no host sync (the reference's `.item()` at :322 is
+        replaced by device-side accumulation), so it can be replayed as a CUDA graph."""
+        _, newlogprob, entropy, newvalue = agent.get_action_and_value(b_obs[mb_inds], b_actions[mb_inds])
+        logratio = newlogprob - b_logprobs[mb_inds]
+        ratio = logratio.exp()
+        with torch.no_grad():
+            mb_stats["old_approx_kl"].copy_((-logratio).mean())
+            mb_stats["approx_kl"].copy_(((ratio - 1) - logratio).mean())
+            clipfrac_sum.add_(((ratio - 1.0).abs() > args.clip_coef).float().mean())
+        mb_advantages = b_advantages[mb_inds]
+        if args.norm_adv:
+            mb_advantages = (mb_advantages - mb_advantages.mean()) / (mb_advantages.std() + 1e-8)
+        pg_loss = torch.max(-mb_advantages * ratio,
+                            -mb_advantages * torch.clamp(ratio, 1 - args.clip_coef, 1 + args.clip_coef)).mean()
+        newvalue = newvalue.view(-1)
+        if args.clip_vloss:
+            v_loss_unclipped = (newvalue - b_returns[mb_inds]) ** 2
+            v_clipped = b_values[mb_inds] + torch.clamp(newvalue - b_values[mb_inds], -args.clip_coef, args.clip_coef)
+            v_loss = 0.5 * torch.max(v_loss_unclipped, (v_clipped - b_returns[mb_inds]) ** 2).mean()
+        else:
+            v_loss = 0.5 * ((newvalue - b_returns[mb_inds]) ** 2).mean()
+        entropy_loss = entropy.mean()
+        loss = pg_loss - args.ent_coef * entropy_loss + v_loss * args.vf_coef
+        with torch.no_grad():
+            mb_stats["v_loss"].copy_(v_loss); mb_stats["pg_loss"].copy_(pg_loss); mb_stats["entropy"].copy_(entropy_loss)
+        flat_grad.zero_()
+        loss.backward()
+
+    def clip_and_step():
+        """nn.utils.clip_grad_norm_ + Adam on the flat buffer (ppo…:353-354); flat_grad holds the SUM
+        over ranks at this point."""
+        if world > 1:
+            flat_grad.div_(world)
+        gnorm = torch.linalg.vector_norm(flat_grad)
+        flat_grad.mul_(torch.clamp(args.max_grad_norm / (gnorm + 1e-6), max=1.0))
+        optimizer.step()
+
+    rollout_graph = fb_graph = opt_graph = None
+    global_step = 0
+    start_time = time.time()
+    next_obs = envs.reset()
+    num_updates = args.total_timesteps // (args.batch_size * world)
+    stats = {"sps": [], "updates": 0, "update_wall": [], "rollout_wall": []}
+    t_roll = t_upd = 0.0
+    for update in range(1, num_updates + 1):
+        if args.anneal_lr:
+            optimizer.param_groups[0]["lr"] = (1.0 - (update - 1.0) / num_updates) * args.learning_rate
+        tr0 = time.time()
+        global_step += T * N * world
+        if rollout_graph is not None:
+            rollout_graph.replay()
+        elif args.cuda_graph and update >= 2:
+            # every buffer the rollout touches is static by now (next_obs is the view's own output
+            # buffer): record the T steps once, replay them for all later updates
+            torch.cuda.synchronize()
+            rollout_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(rollout_graph):
+                rollout(next_obs)
+            rollout_graph.replay()
+        else:
+            next_obs = rollout(next_obs)
         torch.cuda.synchronize()
         tu0 = time.time()
         t_roll += tu0 - tr0
 
-        b_obs = obs.reshape((-1,) + oshape)
-        b_logprobs, b_actions = logprobs.reshape(-1), actions.reshape((-1,) + ashape)
-        b_advantages, b_returns, b_values = advantages.reshape(-1), returns.reshape(-1), values.reshape(-1)
-        clipfrac_sum = torch.zeros((), device=device)
+        clipfrac_sum.zero_()
         n_mb = 0
         stop = False
         for epoch in range(args.update_epochs):
             b_inds = torch.randperm(args.batch_size, device=device)
             for start in range(0, args.batch_size, args.minibatch_size):
-                mb_inds = b_inds[start:start + args.minibatch_size]
-                _, newlogprob, entropy, newvalue = agent.get_action_and_value(b_obs[mb_inds], b_actions[mb_inds])
-                logratio = newlogprob - b_logprobs[mb_inds]
-                ratio = logratio.exp()
-                with torch.no_grad():
-                    old_approx_kl = (-logratio).mean()
-                    approx_kl = ((ratio - 1) - logratio).mean()
-                    clipfrac_sum += ((ratio - 1.0).abs() > args.clip_coef).float().mean()
-                    n_mb += 1
-                mb_advantages = b_advantages[mb_inds]
-                if args.norm_adv:
-                    mb_advantages = (mb_advantages - mb_advantages.mean()) / (mb_advantages.std() + 1e-8)
-                pg_loss = torch.max(-mb_advantages * ratio,
-                                    -mb_advantages * torch.clamp(ratio, 1 - args.clip_coef, 1 + args.clip_coef)).mean()
-                newvalue = newvalue.view(-1)
-                if args.clip_vloss:
-                    v_loss_unclipped = (newvalue - b_returns[mb_inds]) ** 2
-                    v_clipped = b_values[mb_inds] + torch.clamp(newvalue - b_values[mb_inds], -args.clip_coef,
-                                                                args.clip_coef)
-                    v_loss = 0.5 * torch.max(v_loss_unclipped, (v_clipped - b_returns[mb_inds]) ** 2).mean()
+                mb_inds.copy_(b_inds[start:start + args.minibatch_size])
+                optimizer.sync_lr()
+                if fb_graph is not None:
+                    fb_graph.replay()
+                elif args.cuda_graph and update >= 2:
+                    torch.cuda.synchronize()
+                    fb_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(fb_graph):
+                        forward_backward()
+                    fb_graph.replay()
                 else:
-                    v_loss = 0.5 * ((newvalue - b_returns[mb_inds]) ** 2).mean()
-                entropy_loss = entropy.mean()
-                loss = pg_loss - args.ent_coef * entropy_loss + v_loss * args.vf_coef
-
-                flat_grad.zero_()
-                loss.backward()
+                    forward_backward()
                 if world > 1:  # the one collective of the path: mean gradient over ranks
                     dist.all_reduce(flat_grad)
-                    flat_grad.div_(world)
-                # nn.utils.clip_grad_norm_(agent.parameters(), max_grad_norm) on the flat buffer
-                gnorm = torch.linalg.vector_norm(flat_grad)
-                flat_grad.mul_(torch.clamp(args.max_grad_norm / (gnorm + 1e-6), max=1.0))
-                optimizer.step()
+                if opt_graph is not None:
+                    opt_graph.replay()
+                elif args.cuda_graph and update >= 2:
+                    torch.cuda.synchronize()
+                    opt_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(opt_graph):
+                        clip_and_step()
+                    opt_graph.replay()
+                else:
+                    clip_and_step()
+                n_mb += 1
 
                 if args.adaptative_lr or args.target_kl is not None:
-                    kl = approx_kl.detach().clone()
+                    kl = mb_stats["approx_kl"].detach().clone()
                     if world > 1:
                         dist.all_reduce(kl); kl /= world
                     kl = float(kl)
@@ -298,15 +365,17 @@ def train(args, log=print):
                 break
         torch.cuda.synchronize()
         t_upd += time.time() - tu0
+        stats["rollout_wall"].append(tu0 - tr0)
+        stats["update_wall"].append(time.time() - tu0)
         sps = int(global_step / (time.time() - start_time))
         stats["sps"].append(sps)
         stats["updates"] = update
         if rank == 0 and not args.quiet:
-            r = info["r"]["return"]
+            r = envs.returned_episode_returns.sum(1)
             log(f"update {update}/{num_updates} step {global_step} SPS {sps} lr {optimizer.param_groups[0]['lr']:.2e} "
-                f"v_loss {v_loss.item():.4f} pg_loss {pg_loss.item():.4f} ent {entropy_loss.item():.3f} "
-                f"kl {approx_kl.item():.5f} clipfrac {(clipfrac_sum / max(n_mb, 1)).item():.3f} "
-                f"ep_ret(last) {r.mean().item():.3f}")
+                f"v_loss {mb_stats['v_loss'].item():.4f} pg_loss {mb_stats['pg_loss'].item():.4f} "
+                f"ent {mb_stats['entropy'].item():.3f} kl {mb_stats['approx_kl'].item():.5f} "
+                f"clipfrac {(clipfrac_sum / max(n_mb, 1)).item():.3f} ep_ret(last) {r.mean().item():.3f}")
     stats.update(global_step=global_step, wall=time.time() - start_time, rollout_s=t_roll, update_s=t_upd,
                  final_sps=(global_step / max(time.time() - start_time, 1e-9)))
     stats["mlp_backend"] = "tcgen05-bf16" if backend == "tc" else "torch-fp32"
