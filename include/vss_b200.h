@@ -216,6 +216,20 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
                              int N, int K, int epilogue, const float* bias, const void* aux, int ld_aux,
                              int splits, int mn_major, void* stream);
 VSS_API const char* vss_gemm_last_error(void);
+/* out[N] (f32) += column sums of the bf16 matrix x [M,N] (row stride ld): bias gradients. */
+VSS_API int vss_colsum_bf16(const void* x, int ld, int M, int N, float* out, void* stream);
+/* dst [M,ncol_pad] bf16 = zero-padded src[idx[m] (or m if idx is NULL), :ncol] f32: the minibatch
+ * gather b_obs[mb_inds] (ppo...:314) fused with the bf16 conversion and K padding. */
+VSS_API int vss_gather_pad_bf16(const float* src, const int64_t* idx, int M, int ncol, int ncol_pad, void* dst,
+                                void* stream);
+
+/* Output head of the Agent MLPs (Linear 256 -> n_out in {1,2,6}, ppo...:138,151) and its backward
+ * fused with tanh' of the last hidden layer: dz = (dout W) * (1 - h^2) (bf16), dW += dout^T h,
+ * db += sum dout. h [M,256] bf16, W [n_out,256] f32, out/dout [M,n_out] f32. */
+VSS_API int vss_head_forward(const void* h, int ldh, const float* W, const float* b, float* out, int M, int n_out,
+                             void* stream);
+VSS_API int vss_head_backward(const float* dout, const void* h, int ldh, const float* W, void* dz, int ldz,
+                              float* dW, float* db, int M, int n_out, void* stream);
 
 /* Philox4x32-10 known-answer hook (host side; same code as the device generator). */
 VSS_API void vss_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -63,6 +63,10 @@ _SYMBOLS = {
     "vss_gemm_bf16_tn": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP,
                                   _VP, C.c_int, C.c_int, C.c_int, _VP]),
     "vss_gemm_last_error": (C.c_char_p, []),
+    "vss_head_forward": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
+    "vss_head_backward": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP, C.c_int, C.c_int, _VP]),
+    "vss_colsum_bf16": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
+    "vss_gather_pad_bf16": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_philox4x32_10": (None, [_VP, _VP, _VP]),
     "vss_last_error": (C.c_char_p, []),
     "vss_version": (C.c_char_p, []),

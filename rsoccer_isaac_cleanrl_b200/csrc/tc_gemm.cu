@@ -5,7 +5,7 @@
 // Replaces the cuBLAS sgemm + bias + tanh launches behind `nn.Linear`/`nn.Tanh` of the reference's
 // `Agent` (ppo_continuous_action_isaacgym.py:127-164) and their autograd backward (:352).
 // One CTA = one 128 x BN output tile (optionally one K-split of it):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) into a 4-stage smem ring
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) into a 3-stage smem ring
 //   warp 1      TMEM allocator + MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16),
 //               tcgen05.commit releases smem stages / signals the accumulator
 //   warps 2-5   epilogue: tcgen05.ld 32 TMEM lanes x 32 columns per warp, fused bias+tanh /
@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <algorithm>
 #include <cstdio>
 #include <mutex>
 #include <string>
@@ -27,7 +28,7 @@ namespace tc {
 constexpr int BM = 128;       // CTA tile rows = UMMA M
 constexpr int BK = 64;        // k-block: 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;    // bf16
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;    // 3 x 32 KB: two CTAs per SM, so one CTA's epilogue overlaps the other's MMAs
 constexpr int THREADS = 192;
 
 enum Epilogue : int {
@@ -155,7 +156,7 @@ struct Smem {
 };
 
 template <int BN, int EPI, bool MN>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)
 k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -342,6 +343,138 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Ge
 
 }  // namespace tc
 
+namespace tc {
+
+// Column sums of a bf16 [M, N] matrix into fp32 out[N] (+=): the bias gradients db = sum_m dZ[m, :].
+// Each warp streams 128-byte row segments (64 columns), 8 warps per block take interleaved rows.
+__global__ void __launch_bounds__(256)
+k_colsum_bf16(const __nv_bfloat16* __restrict__ x, int ld, int M, int N, float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 64 + 2 * lane;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float a0 = 0.f, a1 = 0.f;
+  if (c0 < N) {
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + (size_t)r * ld + c0);
+      a0 += __bfloat162float(v.x); a1 += __bfloat162float(v.y);
+    }
+  }
+  red[w][2 * lane] = a0; red[w][2 * lane + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    atomicAdd(out + blockIdx.x * 64 + threadIdx.x, s);
+  }
+}
+
+// dst[m, 0:ncol_pad] (bf16) = [ src[idx ? idx[m] : m, 0:ncol] (f32), zeros ]: the minibatch gather
+// (ppo…:314 `b_obs[mb_inds]`) fused with the bf16 conversion and the 52 -> 64 column padding.
+__global__ void __launch_bounds__(256)
+k_gather_pad_bf16(const float* __restrict__ src, const long long* __restrict__ idx, int M, int ncol, int ncol_pad,
+                  __nv_bfloat16* __restrict__ dst) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = ncol_pad / 2;
+  if (t >= (long long)M * per_row) return;
+  const int m = (int)(t / per_row), c = 2 * (int)(t % per_row);
+  const long long r = idx ? idx[m] : m;
+  const float a = c < ncol ? __ldg(src + r * ncol + c) : 0.f;
+  const float b = c + 1 < ncol ? __ldg(src + r * ncol + c + 1) : 0.f;
+  *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)m * ncol_pad + c) = __floats2bfloat162_rn(a, b);
+}
+
+// ---- the 256 -> {1,2,6} output head (Linear without activation, ppo…:138,151) on CUDA cores -------
+// One warp per row, lane l owns columns 8l..8l+7 of the 256-wide hidden vector (one 16-byte load).
+template <int NO>
+__global__ void __launch_bounds__(256)
+k_head_fwd(const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict__ W, const float* __restrict__ b,
+           float* __restrict__ out, int M) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  float w[NO][8];
+#pragma unroll
+  for (int j = 0; j < NO; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[j][c] = __ldg(W + j * 256 + 8 * lane + c);
+  for (int m = warp; m < M; m += nwarps) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(h + (size_t)m * ldh + 8 * lane);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float x[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { x[2 * c] = __bfloat162float(h2[c].x); x[2 * c + 1] = __bfloat162float(h2[c].y); }
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc = fmaf(x[c], w[j][c], acc);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+      if (lane == 0) out[(size_t)m * NO + j] = acc + __ldg(b + j);
+    }
+  }
+}
+
+// Backward of the head fused with the tanh' of the last hidden layer:
+//   dZ[m,c] = (sum_j dout[m,j] W[j,c]) * (1 - h[m,c]^2)   (bf16 out)
+//   dW[j,c] += sum_m dout[m,j] h[m,c];   db[j] += sum_m dout[m,j]
+template <int NO>
+__global__ void __launch_bounds__(256)
+k_head_bwd(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict__ W,
+           __nv_bfloat16* __restrict__ dz, int ldz, float* __restrict__ dW, float* __restrict__ db, int M) {
+  __shared__ float red[8][NO][256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  float w[NO][8], gw[NO][8], gb[NO];
+#pragma unroll
+  for (int j = 0; j < NO; ++j) {
+    gb[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { w[j][c] = __ldg(W + j * 256 + 8 * lane + c); gw[j][c] = 0.f; }
+  }
+  for (int m = warp; m < M; m += nwarps) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(h + (size_t)m * ldh + 8 * lane);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float x[8], g[8], d[NO];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { x[2 * c] = __bfloat162float(h2[c].x); x[2 * c + 1] = __bfloat162float(h2[c].y); }
+#pragma unroll
+    for (int j = 0; j < NO; ++j) { d[j] = __ldg(dout + (size_t)m * NO + j); gb[j] += d[j]; }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < NO; ++j) { acc = fmaf(d[j], w[j][c], acc); gw[j][c] = fmaf(d[j], x[c], gw[j][c]); }
+      g[c] = acc * (1.0f - x[c] * x[c]);
+    }
+    uint4 o;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(g[0], g[1]), p1 = __floats2bfloat162_rn(g[2], g[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(g[4], g[5]), p3 = __floats2bfloat162_rn(g[6], g[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(dz + (size_t)m * ldz + 8 * lane) = o;
+  }
+#pragma unroll
+  for (int j = 0; j < NO; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) red[wib][j][8 * lane + c] = gw[j][c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < NO * 256; i += blockDim.x) {
+    const int j = i / 256, c = i % 256;
+    float sacc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sacc += red[k][j][c];
+    atomicAdd(dW + j * 256 + c, sacc);
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < NO; ++j) atomicAdd(db + j, gb[j]);
+}
+
+}  // namespace tc
+
 extern thread_local std::string g_tc_error;
 thread_local std::string g_tc_error;
 
@@ -396,6 +529,69 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
   { g_tc_error = "vss_gemm_bf16_tn: unsupported epilogue / layout combination"; return VSS_E_INVALID; }
 #undef TC_CASE
   if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
+  return VSS_OK;
+}
+
+// out[N] (f32) += column sums of x [M,N] bf16 (row stride ld elements). N even.
+VSS_API int vss_colsum_bf16(const void* x, int ld, int M, int N, float* out, void* stream) {
+  if (!x || !out || M <= 0 || N <= 0 || (N & 1)) { g_tc_error = "vss_colsum_bf16: bad argument"; return VSS_E_INVALID; }
+  const int col_blocks = (N + 63) / 64;
+  int row_blocks = (148 * 8 + col_blocks - 1) / col_blocks;
+  int rows_per_block = (M + row_blocks - 1) / row_blocks;
+  rows_per_block = (rows_per_block + 7) / 8 * 8;
+  row_blocks = (M + rows_per_block - 1) / rows_per_block;
+  tc::k_colsum_bf16<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ld, M, N, out, rows_per_block);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_tc_error = std::string("vss_colsum_bf16: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
+  return VSS_OK;
+}
+
+// dst [M, ncol_pad] bf16 = pad(src[idx[m] or m, :ncol] f32). idx int64 device array or NULL. ncol_pad even.
+VSS_API int vss_gather_pad_bf16(const float* src, const int64_t* idx, int M, int ncol, int ncol_pad, void* dst,
+                                void* stream) {
+  if (!src || !dst || M <= 0 || ncol <= 0 || ncol_pad < ncol || (ncol_pad & 1)) {
+    g_tc_error = "vss_gather_pad_bf16: bad argument"; return VSS_E_INVALID;
+  }
+  const long long total = (long long)M * (ncol_pad / 2);
+  tc::k_gather_pad_bf16<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      src, reinterpret_cast<const long long*>(idx), M, ncol, ncol_pad, reinterpret_cast<__nv_bfloat16*>(dst));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_tc_error = std::string("vss_gather_pad_bf16: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
+  return VSS_OK;
+}
+
+// Output head of the MLP: out [M,n_out] f32 = h [M,256] bf16 * W[n_out,256]^T + b. n_out in {1,2,6}.
+VSS_API int vss_head_forward(const void* h, int ldh, const float* W, const float* b, float* out, int M, int n_out,
+                             void* stream) {
+  if (!h || !W || !b || !out || M <= 0) { g_tc_error = "vss_head_forward: bad argument"; return VSS_E_INVALID; }
+  const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h);
+  const int blocks = std::min((M + 7) / 8, 148 * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_out == 1) tc::k_head_fwd<1><<<blocks, 256, 0, st>>>(hp, ldh, W, b, out, M);
+  else if (n_out == 2) tc::k_head_fwd<2><<<blocks, 256, 0, st>>>(hp, ldh, W, b, out, M);
+  else if (n_out == 6) tc::k_head_fwd<6><<<blocks, 256, 0, st>>>(hp, ldh, W, b, out, M);
+  else { g_tc_error = "vss_head_forward: n_out must be 1, 2 or 6"; return VSS_E_INVALID; }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_tc_error = std::string("vss_head_forward: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
+  return VSS_OK;
+}
+
+// Backward of the head fused with tanh' of the last hidden layer (see k_head_bwd). dW [n_out,256] and
+// db [n_out] are accumulated (+=): the caller zeroes them. dz [M,256] bf16.
+VSS_API int vss_head_backward(const float* dout, const void* h, int ldh, const float* W, void* dz, int ldz, float* dW,
+                              float* db, int M, int n_out, void* stream) {
+  if (!dout || !h || !W || !dz || !dW || !db || M <= 0) { g_tc_error = "vss_head_backward: bad argument"; return VSS_E_INVALID; }
+  const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h);
+  __nv_bfloat16* zp = reinterpret_cast<__nv_bfloat16*>(dz);
+  const int blocks = std::min((M + 7) / 8, 148 * 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_out == 1) tc::k_head_bwd<1><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, M);
+  else if (n_out == 2) tc::k_head_bwd<2><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, M);
+  else if (n_out == 6) tc::k_head_bwd<6><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, M);
+  else { g_tc_error = "vss_head_backward: n_out must be 1, 2 or 6"; return VSS_E_INVALID; }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_tc_error = std::string("vss_head_backward: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
   return VSS_OK;
 }
 

@@ -162,3 +162,58 @@ def gemm_bf16(a, b, out, epilogue, bias=None, aux=None, splits=1, mn_major=False
     if rc != 0:
         raise RuntimeError(f"vss_gemm_bf16_tn failed ({rc}): {lib.vss_gemm_last_error().decode()}")
     return out
+
+
+def colsum_bf16(x, out=None):
+    """out[N] (f32) += column sums of x [M,N] bf16."""
+    lib = _lib.load_library()
+    M, N = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1
+    if out is None:
+        out = torch.zeros(N, device=x.device, dtype=torch.float32)
+    rc = lib.vss_colsum_bf16(x.data_ptr(), x.stride(0), M, N, out.data_ptr(),
+                             torch.cuda.current_stream(x.device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(lib.vss_gemm_last_error().decode())
+    return out
+
+
+def gather_pad_bf16(src, idx, ncol_pad):
+    """[M, ncol_pad] bf16 = zero-padded src[idx] (src [R, ncol] f32 contiguous; idx int64 or None)."""
+    lib = _lib.load_library()
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 2
+    M = src.shape[0] if idx is None else idx.numel()
+    dst = torch.empty((M, ncol_pad), device=src.device, dtype=torch.bfloat16)
+    rc = lib.vss_gather_pad_bf16(src.data_ptr(), None if idx is None else idx.data_ptr(), M, src.shape[1], ncol_pad,
+                                 dst.data_ptr(), torch.cuda.current_stream(src.device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(lib.vss_gemm_last_error().decode())
+    return dst
+
+
+def head_forward(h, W, b):
+    """out [M,n_out] f32 = h [M,256] bf16 @ W[n_out,256].T + b (CUDA-core kernel, one warp per row)."""
+    lib = _lib.load_library()
+    M, n_out = h.shape[0], W.shape[0]
+    assert h.dtype == torch.bfloat16 and h.shape[1] == 256 and h.stride(1) == 1 and W.shape[1] == 256
+    out = torch.empty((M, n_out), device=h.device, dtype=torch.float32)
+    rc = lib.vss_head_forward(h.data_ptr(), h.stride(0), W.contiguous().data_ptr(), b.contiguous().data_ptr(),
+                              out.data_ptr(), M, n_out, torch.cuda.current_stream(h.device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(lib.vss_gemm_last_error().decode())
+    return out
+
+
+def head_backward(dout, h, W):
+    """(dz [M,256] bf16, dW [n_out,256] f32, db [n_out] f32) of the head, tanh' of h fused into dz."""
+    lib = _lib.load_library()
+    M, n_out = dout.shape
+    dout = dout.contiguous()
+    dz = torch.empty((M, 256), device=h.device, dtype=torch.bfloat16)
+    dW = torch.zeros((n_out, 256), device=h.device, dtype=torch.float32)
+    db = torch.zeros(n_out, device=h.device, dtype=torch.float32)
+    rc = lib.vss_head_backward(dout.data_ptr(), h.data_ptr(), h.stride(0), W.contiguous().data_ptr(), dz.data_ptr(), 256,
+                               dW.data_ptr(), db.data_ptr(), M, n_out, torch.cuda.current_stream(h.device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(lib.vss_gemm_last_error().decode())
+    return dz, dW, db

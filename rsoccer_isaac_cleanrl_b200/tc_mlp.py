@@ -7,11 +7,13 @@
   dgrad    3 x  dZ_prev = (dZ W) * (1 - h^2)    one GEMM each, tanh' fused in the epilogue
   wgrad    4 x  dW = dZ^T h                     one split-K GEMM each on MN-major operands (no transposes)
 Operands are bf16 (activations and a per-call bf16 copy of the fp32 master weights), accumulation
-is fp32 in TMEM. The 256 -> {1,2,6} head and the bias gradients (column sums) stay on CUDA cores.
+is fp32 in TMEM. The 256 -> {1,2,6} head (forward, and backward fused with tanh'), the bias
+gradients (column sums) and the pad/convert of the observations are small CUDA-core kernels.
 """
 import torch
 
-from .engine import EPI_ATOMIC_F32, EPI_BIAS_TANH_BF16, EPI_DTANH_BF16, gemm_bf16
+from .engine import (EPI_ATOMIC_F32, EPI_BIAS_TANH_BF16, EPI_DTANH_BF16, colsum_bf16, gather_pad_bf16, gemm_bf16,
+                     head_backward, head_forward)
 
 _SM_TARGET = 296  # ~2 CTAs' worth of split-K work per SM for the wgrad grids
 
@@ -28,8 +30,7 @@ class TCMlp(torch.autograd.Function):
         ws, bs = params[0::2], params[1::2]
         M, n_in = x.shape
         k0 = (n_in + 63) // 64 * 64
-        x16 = torch.zeros((M, k0), device=x.device, dtype=torch.bfloat16)
-        x16[:, :n_in] = x
+        x16 = gather_pad_bf16(x, None, k0)
         w0 = torch.zeros((ws[0].shape[0], k0), device=x.device, dtype=torch.bfloat16)
         w0[:, :n_in] = ws[0]
         w16 = [w0] + [w.to(torch.bfloat16) for w in ws[1:4]]
@@ -38,7 +39,7 @@ class TCMlp(torch.autograd.Function):
             h = torch.empty((M, w16[l].shape[0]), device=x.device, dtype=torch.bfloat16)
             gemm_bf16(hs[-1], w16[l], h, EPI_BIAS_TANH_BF16, bias=bs[l].contiguous())
             hs.append(h)
-        out = torch.addmm(bs[4], hs[4].float(), ws[4].t())
+        out = head_forward(hs[4], ws[4], bs[4])
         ctx.save_for_backward(*hs, *ws)
         ctx.n_in = n_in
         return out
@@ -50,18 +51,13 @@ class TCMlp(torch.autograd.Function):
         M = dout.shape[0]
         dev = dout.device
         grads = [None] * 10
-        dout = dout.contiguous()
-        h4f = hs[4].float()
-        grads[8] = dout.t() @ h4f                       # dW4
-        grads[9] = dout.sum(0)                          # db4
-        dz = ((dout @ ws[4]) * (1.0 - h4f * h4f)).to(torch.bfloat16)   # dZ of hidden layer 3
-        del h4f
+        dz, grads[8], grads[9] = head_backward(dout, hs[4], ws[4])   # dZ of hidden layer 3, dW4, db4
         for l in (3, 2, 1, 0):
             n_out, k_in = dz.shape[1], hs[l].shape[1]
             dw = torch.zeros((n_out, k_in), device=dev, dtype=torch.float32)
             gemm_bf16(dz, hs[l], dw, EPI_ATOMIC_F32, splits=_splits(n_out, k_in, M), mn_major=True)
             grads[2 * l] = dw[:, :ctx.n_in] if l == 0 else dw
-            grads[2 * l + 1] = dz.sum(0, dtype=torch.float32)
+            grads[2 * l + 1] = colsum_bf16(dz)
             if l > 0:
                 wt = ws[l].t().contiguous().to(torch.bfloat16)          # [k_in, n_out]
                 dz_prev = torch.empty((M, k_in), device=dev, dtype=torch.bfloat16)
