@@ -70,8 +70,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t i = 0; i < (1u << 26); ++i)
     if (mbar_try_wait(bar, parity)) return;
-  printf("tc_gemm: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-         threadIdx.x);
+  printf("tc_gemm: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.z, threadIdx.x);
   __trap();
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
@@ -167,7 +166,10 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // n-tile fastest: the CTAs that share one 128-row A tile are adjacent in launch order, so A is
+  // fetched from HBM once and re-used out of L2 by the other N/BN - 1 column tiles
+  const int n_tiles = g.N / BN;
+  const int m0 = (blockIdx.x / n_tiles) * BM, n0 = (blockIdx.x % n_tiles) * BN;
   const int kb0 = blockIdx.z * g.k_blocks_per_split;
   const int total_kb = g.K / BK;
   const int nkb = min(g.k_blocks_per_split, total_kb - kb0);
@@ -336,7 +338,7 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Ge
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((g.M + BM - 1) / BM, g.N / BN, splits);
+  dim3 grid(((g.M + BM - 1) / BM) * (g.N / BN), 1, splits);
   k_gemm_tn<BN, EPI, MN><<<grid, THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
   return cudaGetLastError();
 }

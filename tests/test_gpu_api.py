@@ -122,3 +122,25 @@ def test_ppo_short_training_run(tmp_path):
     sd = stats["agent"].state_dict()
     assert "critic.0.weight" in sd and "actor_mean.8.bias" in sd and "actor_logstd" in sd
     assert all(torch.isfinite(v).all() for v in sd.values())
+
+
+def test_play_matches_with_team_policies(tmp_path):
+    """play.py surface: teams fill the (N,2,3,2) buffer, the yellow side sees mirrored observations,
+    a checkpoint saved by the PPO loop loads through TeamSA / TeamDMA."""
+    from rsoccer_isaac_cleanrl_b200 import play, ppo
+    from rsoccer_isaac_cleanrl_b200.envs import VSS
+    envs = VSS(_cfg(1065), "cuda:0", "cuda:0", 0, True, seed=4)
+    envs.w_goal, envs.w_grad, envs.w_move, envs.w_energy = 1.0, 0.0, 0.0, 0.0   # ppo…:389-392
+    score, length = play.play_matches(envs, play.get_team("ou"), play.get_team("zero"), 300)
+    assert -1.0 <= score <= 1.0 and 1.0 <= length <= 400.0
+    # a (barely trained) checkpoint in the reference's state_dict format
+    args = ppo.parse_args(["--env-id", "sa", "--num-envs", "128", "--num-steps", "8", "--total-timesteps",
+                           str(128 * 8), "--quiet"])
+    st = ppo.train(args)
+    path = str(tmp_path / "agent.pt")
+    torch.save(st["agent"].state_dict(), path)
+    blue = play.get_team("ppo-sa", path)
+    yellow = play.get_team("ppo-sa-x3", path)
+    score, length = play.play_matches(envs, blue, yellow, 200)
+    assert -1.0 <= score <= 1.0 and 1.0 <= length <= 400.0
+    assert set(play.baseline_teams(str(tmp_path))) == {"zero", "ou"}   # no base_nets checkpoints present
