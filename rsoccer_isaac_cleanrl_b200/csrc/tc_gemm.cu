@@ -4,10 +4,11 @@
 //
 // Replaces the cuBLAS sgemm + bias + tanh launches behind `nn.Linear`/`nn.Tanh` of the reference's
 // `Agent` (ppo_continuous_action_isaacgym.py:127-164) and their autograd backward (:352).
-// One CTA = one 128 x BN output tile (optionally one K-split of it):
+// Persistent CTAs (two per SM) walk the 128 x BN output tiles (times K-splits):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) into a 3-stage smem ring
-//   warp 1      TMEM allocator + MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16),
-//               tcgen05.commit releases smem stages / signals the accumulator
+//   warp 1      TMEM allocator + MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16)
+//               into one of two TMEM accumulator buffers; tcgen05.commit releases smem stages and
+//               signals the accumulator
 //   warps 2-5   epilogue: tcgen05.ld 32 TMEM lanes x 32 columns per warp, fused bias+tanh /
 //               tanh-derivative / split-K fp32 atomics, vectorised global stores
 // Every mbarrier wait is bounded (trap instead of hanging the GPU).
@@ -40,7 +41,8 @@ enum Epilogue : int {
 
 struct GemmArgs {
   int M, N, K;             // problem; K multiple of 64, N multiple of BN
-  int k_blocks_per_split;  // k-blocks (of 64) handled by one blockIdx.z
+  int k_blocks_per_split;  // k-blocks (of 64) handled by one K-split
+  int splits;              // number of K-splits (tiles = m_tiles * n_tiles * splits)
   void* out;               // bf16 or f32, row-major [M, ldo]
   int ldo;
   const float* bias;       // [N] or null
@@ -70,7 +72,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t i = 0; i < (1u << 26); ++i)
     if (mbar_try_wait(bar, parity)) return;
-  printf("tc_gemm: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.z, threadIdx.x);
+  printf("tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
   __trap();
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
@@ -154,6 +156,14 @@ struct Smem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so
+// CTAs working at the same time share A rows through L2). The accumulator is double-buffered in TMEM
+// (2 x BN columns): the MMA warp fills buffer (i+1)&1 while the epilogue warps drain buffer i&1, and the
+// TMA producer runs ahead across tile boundaries through the smem ring.
 template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(THREADS, 2)
 k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -162,24 +172,22 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Smem<BN>::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // n-tile fastest: the CTAs that share one 128-row A tile are adjacent in launch order, so A is
-  // fetched from HBM once and re-used out of L2 by the other N/BN - 1 column tiles
-  const int n_tiles = g.N / BN;
-  const int m0 = (blockIdx.x / n_tiles) * BM, n0 = (blockIdx.x % n_tiles) * BN;
-  const int kb0 = blockIdx.z * g.k_blocks_per_split;
+  const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
+  const int tiles_per_split = n_tiles * m_tiles;
+  const int total_tiles = tiles_per_split * g.splits;
   const int total_kb = g.K / BK;
-  const int nkb = min(g.k_blocks_per_split, total_kb - kb0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -187,113 +195,136 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * Smem<BN>::STAGE_BYTES;
-        uint8_t* sb = sa + Smem<BN>::A_BYTES;
-        mbar_expect_tx(&full_bar[s], Smem<BN>::STAGE_BYTES);
-        if (!MN) {
-          tma_load_2d(sa, &map_a, &full_bar[s], (kb0 + kb) * BK, m0);
-          tma_load_2d(sb, &map_b, &full_bar[s], (kb0 + kb) * BK, n0);
-        } else {  // source tensors are [K, M] / [K, N]: 64 x 64 boxes, inner coordinate = m / n
+      uint32_t it = 0;  // k-blocks issued so far (ring position, continues across tiles)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_per_split, r = t % tiles_per_split;
+        const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
+        const int kb0 = split * g.k_blocks_per_split;
+        const int nkb = min(g.k_blocks_per_split, total_kb - kb0);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * Smem<BN>::STAGE_BYTES;
+          uint8_t* sb = sa + Smem<BN>::A_BYTES;
+          mbar_expect_tx(&full_bar[s], Smem<BN>::STAGE_BYTES);
+          if (!MN) {
+            tma_load_2d(sa, &map_a, &full_bar[s], (kb0 + kb) * BK, m0);
+            tma_load_2d(sb, &map_b, &full_bar[s], (kb0 + kb) * BK, n0);
+          } else {  // source tensors are [K, M] / [K, N]: 64 x 64 boxes, inner coordinate = m / n
 #pragma unroll
-          for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &map_a, &full_bar[s], m0 + 64 * i, (kb0 + kb) * BK);
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &map_a, &full_bar[s], m0 + 64 * i, (kb0 + kb) * BK);
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &map_b, &full_bar[s], n0 + 64 * i, (kb0 + kb) * BK);
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &map_b, &full_bar[s], n0 + 64 * i, (kb0 + kb) * BK);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(BM, BN, MN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const int split = t / tiles_per_split;
+        const int kb0 = split * g.k_blocks_per_split;
+        const int nkb = min(g.k_blocks_per_split, total_kb - kb0);
+        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], bph ^ 1);  // the epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Smem<BN>::STAGE_BYTES);
-        const uint64_t adesc = MN ? make_desc_mn128(sa) : make_desc_k128(sa);
-        const uint64_t bdesc = MN ? make_desc_mn128(sa + Smem<BN>::A_BYTES) : make_desc_k128(sa + Smem<BN>::A_BYTES);
-        // per K=16 step: K-major +32 B inside the swizzle row (>>4 = 2); MN-major +16 rows = 2048 B (>>4 = 128)
-        constexpr uint64_t kstep = MN ? 128 : 2;
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Smem<BN>::STAGE_BYTES);
+          const uint64_t adesc = MN ? make_desc_mn128(sa) : make_desc_k128(sa);
+          const uint64_t bdesc = MN ? make_desc_mn128(sa + Smem<BN>::A_BYTES) : make_desc_k128(sa + Smem<BN>::A_BYTES);
+          // per K=16 step: K-major +32 B inside the swizzle row (>>4 = 2); MN-major +16 rows = 2048 B (>>4 = 128)
+          constexpr uint64_t kstep = MN ? 128 : 2;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)
-          umma_bf16(tmem_base, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
-        umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+        }
+        umma_commit(&tfull_bar[buf]);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const int r = t % tiles_per_split;
+      const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
+      const int row = m0 + q * 32 + lane;
+      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+      mbar_wait(&tfull_bar[buf], bph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (nkb <= 0) {
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
+        if (row < g.M) {
+          const int col = n0 + c;
+          if (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16) {
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + col;
+            uint32_t packed[16];
+            if (EPI == EPI_BIAS_TANH_BF16) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0;
-      }
-      if (row < g.M) {
-        const int col = n0 + c;
-        if (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16) {
-          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + col;
-          uint32_t packed[16];
-          if (EPI == EPI_BIAS_TANH_BF16) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a = tanh_fast(__uint_as_float(v[2 * i]) + __ldg(g.bias + col + 2 * i));
-              const float b = tanh_fast(__uint_as_float(v[2 * i + 1]) + __ldg(g.bias + col + 2 * i + 1));
-              __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-              packed[i] = *reinterpret_cast<uint32_t*>(&p);
-            }
-          } else {
-            const uint4* arow = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 y4 = __ldg(arow + j);
-              const uint32_t yy[4] = {y4.x, y4.y, y4.z, y4.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yy[i]);
-                const float ya = __bfloat162float(y2.x), yb = __bfloat162float(y2.y);
-                const float a = __uint_as_float(v[8 * j + 2 * i]) * (1.0f - ya * ya);
-                const float b = __uint_as_float(v[8 * j + 2 * i + 1]) * (1.0f - yb * yb);
+              for (int i = 0; i < 16; ++i) {
+                const float a = tanh_fast(__uint_as_float(v[2 * i]) + __ldg(g.bias + col + 2 * i));
+                const float b = tanh_fast(__uint_as_float(v[2 * i + 1]) + __ldg(g.bias + col + 2 * i + 1));
                 __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-                packed[4 * j + i] = *reinterpret_cast<uint32_t*>(&p);
+                packed[i] = *reinterpret_cast<uint32_t*>(&p);
+              }
+            } else {
+              const uint4* arow = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + col);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 y4 = __ldg(arow + j);
+                const uint32_t yy[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yy[i]);
+                  const float ya = __bfloat162float(y2.x), yb = __bfloat162float(y2.y);
+                  const float a = __uint_as_float(v[8 * j + 2 * i]) * (1.0f - ya * ya);
+                  const float b = __uint_as_float(v[8 * j + 2 * i + 1]) * (1.0f - yb * yb);
+                  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+                  packed[4 * j + i] = *reinterpret_cast<uint32_t*>(&p);
+                }
               }
             }
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(orow);
+            uint4* o4 = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        } else if (EPI == EPI_ATOMIC_F32) {
-          float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          } else if (EPI == EPI_ATOMIC_F32) {
+            float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(orow + i, __uint_as_float(v[i]));
-        } else {
-          float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+            for (int i = 0; i < 32; ++i) atomicAdd(orow + i, __uint_as_float(v[i]));
+          } else {
+            float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o;
-            o.x = __uint_as_float(v[4 * j]) + (g.bias ? __ldg(g.bias + col + 4 * j) : 0.0f);
-            o.y = __uint_as_float(v[4 * j + 1]) + (g.bias ? __ldg(g.bias + col + 4 * j + 1) : 0.0f);
-            o.z = __uint_as_float(v[4 * j + 2]) + (g.bias ? __ldg(g.bias + col + 4 * j + 2) : 0.0f);
-            o.w = __uint_as_float(v[4 * j + 3]) + (g.bias ? __ldg(g.bias + col + 4 * j + 3) : 0.0f);
-            reinterpret_cast<float4*>(orow)[j] = o;
+            for (int j = 0; j < 8; ++j) {
+              float4 o;
+              o.x = __uint_as_float(v[4 * j]) + (g.bias ? __ldg(g.bias + col + 4 * j) : 0.0f);
+              o.y = __uint_as_float(v[4 * j + 1]) + (g.bias ? __ldg(g.bias + col + 4 * j + 1) : 0.0f);
+              o.z = __uint_as_float(v[4 * j + 2]) + (g.bias ? __ldg(g.bias + col + 4 * j + 2) : 0.0f);
+              o.w = __uint_as_float(v[4 * j + 3]) + (g.bias ? __ldg(g.bias + col + 4 * j + 3) : 0.0f);
+              reinterpret_cast<float4*>(orow)[j] = o;
+            }
           }
         }
       }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld): hand the buffer back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -338,7 +369,15 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Ge
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid(((g.M + BM - 1) / BM) * (g.N / BN), 1, splits);
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    max_ctas = 2 * sms;  // two resident CTAs per SM (smem and TMEM both allow exactly two)
+  }
+  const long long tiles = (long long)((g.M + BM - 1) / BM) * (g.N / BN) * splits;
+  const unsigned grid = (unsigned)std::min<long long>(tiles, max_ctas);
   k_gemm_tn<BN, EPI, MN><<<grid, THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
   return cudaGetLastError();
 }
@@ -518,6 +557,7 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
   const int total_kb = g.K / BK;
   g.k_blocks_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + g.k_blocks_per_split - 1) / g.k_blocks_per_split;
+  g.splits = splits;
   g.out = out; g.ldo = ldo; g.bias = bias; g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ld_aux = ld_aux;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
