@@ -153,7 +153,7 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;   // 8 / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -175,6 +175,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + STAGES * Smem<BN>::STAGE_BYTES + 256);  // [<= 512]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
@@ -188,6 +189,9 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  const bool bias_in_smem = (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_BIAS_F32) && g.bias != nullptr && g.N <= 512;
+  if (bias_in_smem)  // the whole bias vector once per CTA: the epilogue reads it as broadcast float4s
+    for (int i = threadIdx.x; i < g.N; i += THREADS) bias_s[i] = __ldg(g.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -270,11 +274,16 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             uint32_t packed[16];
             if (EPI == EPI_BIAS_TANH_BF16) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float a = tanh_fast(__uint_as_float(v[2 * i]) + __ldg(g.bias + col + 2 * i));
-                const float b = tanh_fast(__uint_as_float(v[2 * i + 1]) + __ldg(g.bias + col + 2 * i + 1));
-                __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-                packed[i] = *reinterpret_cast<uint32_t*>(&p);
+              for (int j = 0; j < 8; ++j) {
+                const float4 bv = bias_in_smem ? *reinterpret_cast<const float4*>(bias_s + col + 4 * j)
+                                               : __ldg(reinterpret_cast<const float4*>(g.bias + col + 4 * j));
+                const float a = tanh_fast(__uint_as_float(v[4 * j]) + bv.x);
+                const float b = tanh_fast(__uint_as_float(v[4 * j + 1]) + bv.y);
+                const float c2 = tanh_fast(__uint_as_float(v[4 * j + 2]) + bv.z);
+                const float d = tanh_fast(__uint_as_float(v[4 * j + 3]) + bv.w);
+                __nv_bfloat162 p = __floats2bfloat162_rn(a, b), q2 = __floats2bfloat162_rn(c2, d);
+                packed[2 * j] = *reinterpret_cast<uint32_t*>(&p);
+                packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&q2);
               }
             } else {
               const uint4* arow = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + col);
