@@ -23,8 +23,10 @@
 
 #if defined(__CUDACC__)
 #define VSS_HD __host__ __device__ __forceinline__
+#define VSS_HD_COLD __host__ __device__ __noinline__  // rare paths kept out of the hot instruction stream
 #else
 #define VSS_HD inline
+#define VSS_HD_COLD inline
 #endif
 
 namespace vss {
@@ -414,7 +416,7 @@ VSS_HD void sincos_small(float a, float& sa, float& ca) {
     return;
   }
 #if defined(__CUDA_ARCH__)
-  sincosf(a, &sa, &ca);
+  __sincosf(a, &sa, &ca);  // |a| = |w| h stays below a few radians: the fast intrinsic is accurate to ~1e-6 there
 #else
   sa = sinf(a); ca = cosf(a);
 #endif
@@ -561,7 +563,7 @@ VSS_HD void rewards_lane(const float* S, const DevParams& P, float rew[VSS_REW_P
 }
 
 // ---- masked reset of one field: envs/vss.py:267-333 ---------------------------------------
-VSS_HD void reset_lane(float* S, const DevParams& P, const RngKey& key) {
+VSS_HD_COLD void reset_lane(float* S, const DevParams& P, const RngKey& key) {
   const uint32_t ep = fbits(S[VSS_W_EPISODE * LDS]);
   float px[7], py[7];
 #pragma unroll 1
