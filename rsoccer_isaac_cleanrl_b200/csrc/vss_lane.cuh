@@ -656,6 +656,7 @@ struct StepArgs {
   // view mode only
   const float* policy_action; float* action_buf; float* reward_v; long long* done_v;
   float* ep_ret; int* ep_len; float* ret_ret; int* ret_len;
+  int sync_level;              // 0: warps run free; >= 1: CTA-wide barriers keep them in the same code region
 };
 
 template <int VIEW>

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -28,11 +29,16 @@ constexpr int TAB_WORDS = 80;  // 78 table entries, padded
 // Physics of one tile (replaces gym.simulate): per substep, phases A-C per lane, then the robot-wall
 // contacts as (field, robot) tasks compacted over the warp — any lane can work on any field of the
 // tile because the state columns live in shared memory — then the ball-wall phase per lane.
-__device__ __forceinline__ void physics_tile(float* T, int lane, bool active, const DevParams& P) {
+template <bool SYNC>
+__device__ __forceinline__ void physics_tile(float* T, int lane, bool active, const DevParams& P, int sync_level) {
   float* S = T + lane;
   uint8_t* queue = reinterpret_cast<uint8_t*>(T + SM_WORDS * LDS);
 #pragma unroll 1
   for (int it = 0; it < P.substeps; ++it) {
+    // keep the warps of a CTA in the same code region: the kernel is instruction-fetch bound
+    // (85 KB of SASS, "no instruction" stalls), and warps that run the same 128-byte lines at the
+    // same time share them in the instruction caches
+    if (SYNC) __syncthreads();
     uint32_t m = active ? substep_pre_lane(S, P) : 0u;
     const int cnt = __popc(m);
     int incl = cnt;
@@ -48,18 +54,18 @@ __device__ __forceinline__ void physics_tile(float* T, int lane, bool active, co
       m &= m - 1;
       queue[pos++] = (uint8_t)((lane << 3) | r);
     }
-    __syncwarp();
+    if (SYNC && sync_level >= 3) __syncthreads(); else __syncwarp();
     for (int t = lane; t < total; t += 32) {
       const int q = queue[t];
       robot_walls_task(T + (q >> 3), q & 7, P);
     }
-    __syncwarp();
+    if (SYNC && sync_level >= 3) __syncthreads(); else __syncwarp();
     if (active) substep_ball_walls_lane(S, P);
   }
 }
 
-template <int VIEW, bool INJECT>
-__global__ void __launch_bounds__(128)
+template <int VIEW, bool INJECT, bool SYNC>
+__global__ void __launch_bounds__(384)
 k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) {
   extern __shared__ __align__(16) float smem[];
   uint32_t* tab = reinterpret_cast<uint32_t*>(smem);
@@ -68,21 +74,23 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long env0 = tile * 32;
-  if (env0 >= a.n) return;
+  if (!SYNC && env0 >= a.n) return;  // (with block-level syncs every warp must stay until the end)
   float* T = smem + TAB_WORDS + warp * TILE_WORDS;
   float* S = T + lane;
   const long long env = env0 + lane;
   const bool active = env < a.n;
-  const int valid = (int)min(32LL, a.n - env0);
+  const int valid = (int)max(0LL, min(32LL, a.n - env0));
   constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
   const RngKey key = make_key(a, env);
   // 1. per lane: load, actions, physics, rewards, dones
   if (active) lane_phase1a<VIEW>(S, env, a, P, key);
   if (INJECT) { if (active) lane_inject(S, env, a); }
-  else physics_tile(T, lane, active, P);
+  else physics_tile<SYNC>(T, lane, active, P, a.sync_level);
+  if (SYNC) __syncthreads();
   bool done = false;
   if (active) done = lane_phase1d<VIEW>(S, env, a, P);
   __syncwarp();
+  if (SYNC && a.sync_level >= 2) __syncthreads();
   // 2. terminal observation + observation of the fields that keep their state (vss.py:195-196)
   const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
   float* ob = a.obs + env0 * (PER_FIELD * 4);
@@ -95,6 +103,7 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   // 4. observation of the fields that were reset (vss.py:203)
   write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask);
   // 5. state out
+  if (SYNC && a.sync_level >= 2) __syncthreads();
   if (active) lane_phase5<VIEW>(S, env, a, done);
 }
 
@@ -102,7 +111,7 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
 __global__ void k_bump(uint32_t* ctr) { *ctr += 1u; }
 
 // reset_dones() + compute_observations(): vss.py:72-73, 267-333, 205-216
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(384)
 k_reset_dones(float* state, long long n, long long ld, unsigned long long goff, uint32_t seed_lo,
               uint32_t seed_hi, const long long* reset_buf, float* obs, const __grid_constant__ DevParams P) {
   extern __shared__ __align__(16) float smem[];
@@ -206,14 +215,30 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e_ != cudaSuccess) return fail(VSS_E_CUDA, #call, e_); \
   } while (0)
 
-static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* smem) {
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// Launch shape. Large batches: 8 warps per CTA with CTA-wide barriers at phase boundaries — the step
+// kernel is instruction-fetch bound (profiles/r01_b_*.md), and warps that execute the same code
+// region at the same time share its lines in the instruction caches (+25 % measured). Small
+// batches: 1-2 warps per CTA so that at least 148 CTAs exist; no barriers (latency matters there).
+// VSS_WPB / VSS_SYNC environment variables override (tuning).
+static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* smem, int* sync_level = nullptr) {
   const int64_t tiles = (n + 31) / 32;
-  int wpb = 4;
-  if (tiles < 148 * 2) wpb = 1;
-  else if (tiles < 148 * 8) wpb = 2;
+  int wpb = 8, sync = 2;
+  if (tiles < 148 * 2) { wpb = 1; sync = 0; }
+  else if (tiles < 148 * 8) { wpb = 2; sync = 0; }
+  else if (tiles < 148 * 24) { wpb = 4; sync = 2; }
+  static const int forced_wpb = env_int("VSS_WPB", 0), forced_sync = env_int("VSS_SYNC", -1);
+  if (forced_wpb >= 1 && forced_wpb <= 12) wpb = forced_wpb;
+  if (forced_sync >= 0) sync = forced_sync;
+  if (wpb == 1) sync = 0;
   *warps_per_block = wpb;
   *grid = (unsigned)((tiles + wpb - 1) / wpb);
   *smem = sizeof(float) * (TAB_WORDS + (size_t)wpb * TILE_WORDS);
+  if (sync_level) *sync_level = sync;
   return 0;
 }
 
@@ -234,9 +259,17 @@ static StepArgs base_args(vss_handle h) {
 
 template <int VIEW, bool INJECT>
 static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
-  int wpb; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem);
-  k_step<VIEW, INJECT><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
+  int wpb, sync_phases; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem, &sync_phases);
+  const_cast<StepArgs&>(a).sync_level = sync_phases;
+  static bool big_smem_ok = false;
+  if (smem > 48 * 1024 && !big_smem_ok) {
+    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    big_smem_ok = true;
+  }
+  if (sync_phases && wpb > 1) k_step<VIEW, INJECT, true><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
+  else k_step<VIEW, INJECT, false><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
   VSS_CUDA(cudaGetLastError());
   k_bump<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_step);
   VSS_CUDA(cudaGetLastError());
@@ -338,6 +371,11 @@ VSS_API int vss_reset_dones(vss_handle h, const int64_t* reset_buf, float* obs, 
   if (int rc = use_device(h)) return rc;
   int wpb; unsigned grid; size_t smem;
   launch_cfg(h->n, &wpb, &grid, &smem);
+  static bool big_smem_ok = false;
+  if (smem > 48 * 1024 && !big_smem_ok) {
+    VSS_CUDA(cudaFuncSetAttribute(k_reset_dones, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    big_smem_ok = true;
+  }
   k_reset_dones<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(
       h->state, h->n, h->ld, (unsigned long long)h->goff, (uint32_t)h->seed, (uint32_t)(h->seed >> 32),
       reinterpret_cast<const long long*>(reset_buf), obs, h->dp);
