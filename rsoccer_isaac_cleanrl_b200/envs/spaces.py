@@ -71,8 +71,8 @@ class ObservationWrapper(Wrapper):
     def reset(self, **kwargs):
         return self.observation(self.env.reset(**kwargs))
 
-    def step(self, action):
-        observation, reward, done, info = self.env.step(action)
+    def step(self, action, **kwargs):
+        observation, reward, done, info = self.env.step(action, **kwargs)
         return self.observation(observation), reward, done, info
 
     def observation(self, observation):

@@ -88,21 +88,27 @@ class _FusedView(Wrapper):
         observations = self.env.reset(**kwargs)
         return {"obs": self._slice_obs(observations["obs"])}
 
-    def step(self, action):
+    def step(self, action, obs_out=None, term_obs_out=None, reward_out=None):
+        """One fused step. The optional `*_out` tensors (contiguous, right shape) make the kernel write
+        the observation / terminal observation / scalar reward straight into caller storage — e.g. the
+        `(T, N, …)` rollout slabs of the PPO loop (ppo…:258-272) — instead of the view's own buffers."""
         task = self.task
         if action.device != task.device or action.dtype != torch.float32 or not action.is_contiguous():
             action = action.to(task.device, torch.float32).contiguous()
-        task.engine.step_view(self.VIEW, action, self.action_buf, task.reset_buf, self._obs, self._term_obs,
-                              self._rews, self._reward, self._done, self._timeout_u8, self._progress,
+        obs = self._obs if obs_out is None else obs_out
+        term_obs = self._term_obs if term_obs_out is None else term_obs_out
+        reward = self._reward if reward_out is None else reward_out
+        task.engine.step_view(self.VIEW, action, self.action_buf, task.reset_buf, obs, term_obs,
+                              self._rews, reward, self._done, self._timeout_u8, self._progress,
                               self.episode_returns, self.episode_lengths, self.returned_episode_returns,
                               self.returned_episode_lengths)
         task._obs_stale = True
         infos = task.extras
         infos["rews"] = self._rews
-        infos["terminal_observation"] = self._term_obs
+        infos["terminal_observation"] = term_obs
         infos["time_outs"] = self._timeout_u8.view(torch.bool)
         infos["progress_buffer"] = self._progress
-        return {"obs": self._obs}, self._reward, self._done, infos
+        return {"obs": obs}, reward, self._done, infos
 
     # ---- the same call with HOST buffers (pinned): action in, (obs, reward, done) out
     def step_host(self, action_host):
@@ -210,8 +216,8 @@ class RecordEpisodeStatisticsTorch(Wrapper):
         self.returned_episode_lengths = z(self.num_envs, torch.int32)
         return observations
 
-    def step(self, action):
-        observations, rewards, dones, infos = super().step(action)
+    def step(self, action, **out):
+        observations, rewards, dones, infos = self.env.step(action, **out) if out else super().step(action)
         if self._fused is None:
             self.episode_returns += infos["rews"]
             self.episode_lengths += 1

@@ -215,7 +215,8 @@ def train(args, log=print):
     T, N = args.num_steps, args.num_envs
     oshape, ashape = envs.single_observation_space.shape, envs.single_action_space.shape
     z = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
-    obs, actions = z(T, N, *oshape), z(T, N, *ashape)
+    obs_all, actions = z(T + 1, N, *oshape), z(T, N, *ashape)   # obs_all[t + 1] is written by env step t
+    obs = obs_all[:T]
     logprobs, rewards, next_dones, next_timeouts, values, next_values = (z(T, N) for _ in range(6))
     advantages, returns = z(T, N), z(T, N)
     term_obs_all = z(T, N, *oshape)
@@ -223,18 +224,20 @@ def train(args, log=print):
     def rollout(first_obs):
         """T env steps + V(terminal obs) + GAE (ppo…:256-296). No host sync anywhere, so the whole
         thing can be captured in a CUDA graph."""
-        cur = first_obs
         with torch.no_grad():
+            obs_all[0] = first_obs
             for step in range(T):
-                obs[step] = cur
+                cur = obs_all[step]
                 action, logprob, _, value = agent.get_action_and_value(cur)
                 values[step] = value.flatten()
                 actions[step] = action
                 logprobs[step] = logprob
-                cur, rewards[step], next_done, info = envs.step(action)
+                # the step kernel writes next obs / terminal obs / reward straight into the rollout slabs
+                _, _, next_done, info = envs.step(action, obs_out=obs_all[step + 1],
+                                                  term_obs_out=term_obs_all[step], reward_out=rewards[step])
                 next_dones[step] = next_done
                 next_timeouts[step] = info["time_outs"]
-                term_obs_all[step] = info["terminal_observation"]
+            cur = obs_all[T]
             # V(terminal_observation) for the whole rollout in one batched pass (ppo…:272 does it per step)
             next_values.copy_(agent.get_value(term_obs_all.view(T * N, *oshape)).view(T, N))
             gae_kernel(rewards, values, next_values, next_dones, next_timeouts, args.gamma, args.gae_lambda,
