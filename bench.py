@@ -153,7 +153,7 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- native arm
@@ -309,12 +309,21 @@ def run_native(args):
         }
         if sweep:
             line["sweep"] = sweep
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything libraries print (e.g. NCCL's version
+    banner) was diverted to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
