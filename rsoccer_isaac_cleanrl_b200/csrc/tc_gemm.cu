@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -160,6 +161,64 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// One 32-column chunk of one accumulator row through the fused epilogue (v = 32 fp32 from TMEM).
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col, const GemmArgs& g,
+                                               const float* bias_s, bool bias_in_smem) {
+      if (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16) {
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + col;
+        uint32_t packed[16];
+        if (EPI == EPI_BIAS_TANH_BF16) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = bias_in_smem ? *reinterpret_cast<const float4*>(bias_s + col + 4 * j)
+                                           : __ldg(reinterpret_cast<const float4*>(g.bias + col + 4 * j));
+            const float a = tanh_fast(__uint_as_float(v[4 * j]) + bv.x);
+            const float b = tanh_fast(__uint_as_float(v[4 * j + 1]) + bv.y);
+            const float c2 = tanh_fast(__uint_as_float(v[4 * j + 2]) + bv.z);
+            const float d = tanh_fast(__uint_as_float(v[4 * j + 3]) + bv.w);
+            __nv_bfloat162 p = __floats2bfloat162_rn(a, b), q2 = __floats2bfloat162_rn(c2, d);
+            packed[2 * j] = *reinterpret_cast<uint32_t*>(&p);
+            packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&q2);
+          }
+        } else {
+          const uint4* arow = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 y4 = __ldg(arow + j);
+            const uint32_t yy[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yy[i]);
+              const float ya = __bfloat162float(y2.x), yb = __bfloat162float(y2.y);
+              const float a = __uint_as_float(v[8 * j + 2 * i]) * (1.0f - ya * ya);
+              const float b = __uint_as_float(v[8 * j + 2 * i + 1]) * (1.0f - yb * yb);
+              __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+              packed[4 * j + i] = *reinterpret_cast<uint32_t*>(&p);
+            }
+          }
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      } else if (EPI == EPI_ATOMIC_F32) {
+        float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(orow + i, __uint_as_float(v[i]));
+      } else {
+        float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = __uint_as_float(v[4 * j]) + (g.bias ? __ldg(g.bias + col + 4 * j) : 0.0f);
+          o.y = __uint_as_float(v[4 * j + 1]) + (g.bias ? __ldg(g.bias + col + 4 * j + 1) : 0.0f);
+          o.z = __uint_as_float(v[4 * j + 2]) + (g.bias ? __ldg(g.bias + col + 4 * j + 2) : 0.0f);
+          o.w = __uint_as_float(v[4 * j + 3]) + (g.bias ? __ldg(g.bias + col + 4 * j + 3) : 0.0f);
+          reinterpret_cast<float4*>(orow)[j] = o;
+        }
+      }
+}
+
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so
 // CTAs working at the same time share A rows through L2). The accumulator is double-buffered in TMEM
 // (2 x BN columns): the MMA warp fills buffer (i+1)&1 while the epilogue warps drain buffer i&1, and the
@@ -267,63 +326,127 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
-        if (row < g.M) {
-          const int col = n0 + c;
-          if (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16) {
-            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + col;
-            uint32_t packed[16];
-            if (EPI == EPI_BIAS_TANH_BF16) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bv = bias_in_smem ? *reinterpret_cast<const float4*>(bias_s + col + 4 * j)
-                                               : __ldg(reinterpret_cast<const float4*>(g.bias + col + 4 * j));
-                const float a = tanh_fast(__uint_as_float(v[4 * j]) + bv.x);
-                const float b = tanh_fast(__uint_as_float(v[4 * j + 1]) + bv.y);
-                const float c2 = tanh_fast(__uint_as_float(v[4 * j + 2]) + bv.z);
-                const float d = tanh_fast(__uint_as_float(v[4 * j + 3]) + bv.w);
-                __nv_bfloat162 p = __floats2bfloat162_rn(a, b), q2 = __floats2bfloat162_rn(c2, d);
-                packed[2 * j] = *reinterpret_cast<uint32_t*>(&p);
-                packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&q2);
-              }
-            } else {
-              const uint4* arow = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + col);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 y4 = __ldg(arow + j);
-                const uint32_t yy[4] = {y4.x, y4.y, y4.z, y4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yy[i]);
-                  const float ya = __bfloat162float(y2.x), yb = __bfloat162float(y2.y);
-                  const float a = __uint_as_float(v[8 * j + 2 * i]) * (1.0f - ya * ya);
-                  const float b = __uint_as_float(v[8 * j + 2 * i + 1]) * (1.0f - yb * yb);
-                  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-                  packed[4 * j + i] = *reinterpret_cast<uint32_t*>(&p);
-                }
-              }
-            }
-            uint4* o4 = reinterpret_cast<uint4*>(orow);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          } else if (EPI == EPI_ATOMIC_F32) {
-            float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(orow + i, __uint_as_float(v[i]));
-          } else {
-            float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o;
-              o.x = __uint_as_float(v[4 * j]) + (g.bias ? __ldg(g.bias + col + 4 * j) : 0.0f);
-              o.y = __uint_as_float(v[4 * j + 1]) + (g.bias ? __ldg(g.bias + col + 4 * j + 1) : 0.0f);
-              o.z = __uint_as_float(v[4 * j + 2]) + (g.bias ? __ldg(g.bias + col + 4 * j + 2) : 0.0f);
-              o.w = __uint_as_float(v[4 * j + 3]) + (g.bias ? __ldg(g.bias + col + 4 * j + 3) : 0.0f);
-              reinterpret_cast<float4*>(orow)[j] = o;
-            }
-          }
-        }
+        if (row < g.M) epilogue_chunk<EPI>(v, row, n0 + c, g, bias_s, bias_in_smem);
       }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld): hand the buffer back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// Weight-stationary variant for the forward / dgrad GEMMs (K-major, K <= 512, N % 128 == 0).
+// With the B tile streamed per k-block the kernel above moves 32 KB of shared memory per 2 MFLOP
+// (64 FLOP/B) and saturates the ~42 B/clk/SM that L2 can deliver long before the tensor core.
+// Here one CTA per SM owns one 128-column slice of the weights, loads it ONCE (K/64 x 16 KB, stays
+// resident), and streams only the activation tiles (16 KB per k-block = 128 FLOP/B) through a 4-stage
+// ring while walking its share of the M tiles; accumulators are double-buffered in TMEM as above.
+constexpr int WS_STAGES = 4;
+constexpr int WS_MAX_KB = 8;  // K <= 512
+struct SmemWS {
+  static constexpr int B_BYTES = WS_MAX_KB * 128 * BK * 2;       // 128 KB resident weight slice
+  static constexpr int A_BYTES = BM * BK * 2;                    // 16 KB per stage
+  static constexpr int TOTAL = B_BYTES + WS_STAGES * A_BYTES + 1024 + 256 + 2048;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+          const __grid_constant__ GemmArgs g) {
+  constexpr int BN = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + SmemWS::B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_a + WS_STAGES * SmemWS::A_BYTES);
+  uint64_t* empty_bar = full_bar + WS_STAGES;
+  uint64_t* tfull_bar = empty_bar + WS_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* b_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
+  float* bias_s = reinterpret_cast<float*>(smem_a + WS_STAGES * SmemWS::A_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
+  const int nkb = g.K / BK;
+  // CTA c owns column slice c % n_tiles and the M tiles c / n_tiles, + gridDim.x / n_tiles, ...
+  const int n0 = (blockIdx.x % n_tiles) * BN;
+  const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    mbar_init(b_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  const bool bias_in_smem = (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_BIAS_F32) && g.bias != nullptr && g.N <= 512;
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < g.N; i += THREADS) bias_s[i] = __ldg(g.bias + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer: the weight slice once, then activation tiles
+      mbar_expect_tx(b_bar, (uint32_t)nkb * 128 * BK * 2);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem_b + kb * (128 * BK * 2), &map_b, b_bar, kb * BK, n0);
+      uint32_t it = 0;
+      for (int mt = m_first; mt < m_tiles; mt += m_step) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % WS_STAGES, ph = (it / WS_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], SmemWS::A_BYTES);
+          tma_load_2d(smem_a + s * SmemWS::A_BYTES, &map_a, &full_bar[s], kb * BK, mt * BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer
+      constexpr uint32_t idesc = make_idesc(BM, BN, false);
+      mbar_wait(b_bar, 0);
+      uint32_t it = 0, lt = 0;
+      for (int mt = m_first; mt < m_tiles; mt += m_step, ++lt) {
+        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], bph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % WS_STAGES, ph = (it / WS_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = make_desc_k128(smem_u32(smem_a + s * SmemWS::A_BYTES));
+          const uint64_t bdesc = make_desc_k128(smem_u32(smem_b + kb * (128 * BK * 2)));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {  // ---- epilogue
+    const int q = warp & 3;
+    uint32_t lt = 0;
+    for (int mt = m_first; mt < m_tiles; mt += m_step, ++lt) {
+      const int row = mt * BM + q * 32 + lane;
+      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+      mbar_wait(&tfull_bar[buf], bph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
+        if (row < g.M) epilogue_chunk<EPI>(v, row, n0 + c, g, bias_s, bias_in_smem);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
@@ -367,6 +490,24 @@ static bool make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int 
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int EPI>
+static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t st) {
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemWS::TOTAL);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int n_tiles = g.N / 128, m_tiles = (g.M + BM - 1) / BM;
+  int per_slice = std::min(std::max(sms / n_tiles, 1), m_tiles);   // CTAs per column slice
+  k_gemm_ws<EPI><<<per_slice * n_tiles, THREADS, SmemWS::TOTAL, st>>>(ma, mb, g);
+  return cudaGetLastError();
 }
 
 template <int BN, int EPI, bool MN>
@@ -570,6 +711,17 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
   g.out = out; g.ldo = ldo; g.bias = bias; g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ld_aux = ld_aux;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
+  // forward with enough M tiles per SM: weight-stationary kernel (measured: forward 257 -> 244 us per
+  // MLP at M = 131072; dgrad, whose epilogue also streams the aux tile, is 8 % slower with it and
+  // stays on the streaming kernel). VSS_GEMM_WS=0/2 disables it / also enables it for dgrad (tuning).
+  static const int ws_mode = getenv("VSS_GEMM_WS") ? atoi(getenv("VSS_GEMM_WS")) : 1;
+  if (ws_mode && !mn_major && splits == 1 && bn == 128 && K <= 512 && M >= 128 * 148 &&
+      (epilogue == EPI_BIAS_TANH_BF16 || (ws_mode == 2 && epilogue == EPI_DTANH_BF16))) {
+    e = epilogue == EPI_BIAS_TANH_BF16 ? launch_ws<EPI_BIAS_TANH_BF16>(ma, mb, g, st)
+                                       : launch_ws<EPI_DTANH_BF16>(ma, mb, g, st);
+    if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
+    return VSS_OK;
+  }
 #define TC_CASE(BNV, EPIV, MNV) \
   if (bn == BNV && epilogue == EPIV && (mn_major != 0) == MNV) e = launch<BNV, EPIV, MNV>(ma, mb, g, splits, st); else
   TC_CASE(128, EPI_BIAS_TANH_BF16, false) TC_CASE(64, EPI_BIAS_TANH_BF16, false)
