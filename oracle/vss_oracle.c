@@ -384,17 +384,23 @@ static int circle_vs_box(const body_t* B, double H, double px, double py, double
   const double dx = px - B->x, dy = py - B->y;
   const double lx = dx * B->c + dy * B->s, ly = -dx * B->s + dy * B->c;
   double nlx, nly, clx, cly;
-  if (fabs(lx) < H && fabs(ly) < H) { /* centre inside the box: face of least penetration */
-    const double pxd = H - fabs(lx), pyd = H - fabs(ly);
-    if (pxd < pyd) { nlx = sgn(lx); nly = 0.0; *depth = pxd + rho; clx = sgn(lx) * H; cly = ly; }
-    else { nlx = 0.0; nly = sgn(ly); *depth = pyd + rho; clx = lx; cly = sgn(ly) * H; }
-  } else {
+  int face = fabs(lx) <= H && fabs(ly) <= H; /* centre inside (or exactly on) the box */
+  if (!face) {
     const double qx = clampd(lx, -H, H), qy = clampd(ly, -H, H);
     const double ex = lx - qx, ey = ly - qy;
     const double d2 = ex * ex + ey * ey;
     if (d2 >= rho * rho) return 0;
-    const double d = sqrt(d2);
-    nlx = ex / d; nly = ey / d; *depth = rho - d; clx = qx; cly = qy;
+    if (d2 > 1e-20) {
+      const double d = sqrt(d2);
+      nlx = ex / d; nly = ey / d; *depth = rho - d; clx = qx; cly = qy;
+    } else {
+      face = 1; /* within rounding of the surface: use the face rule */
+    }
+  }
+  if (face) { /* face of least penetration */
+    const double pxd = H - fabs(lx), pyd = H - fabs(ly);
+    if (pxd < pyd) { nlx = sgn(lx); nly = 0.0; *depth = pxd + rho; clx = sgn(lx) * H; cly = ly; }
+    else { nlx = 0.0; nly = sgn(ly); *depth = pyd + rho; clx = lx; cly = sgn(ly) * H; }
   }
   *nx = nlx * B->c - nly * B->s; *ny = nlx * B->s + nly * B->c;
   *cpx = B->x + clx * B->c - cly * B->s; *cpy = B->y + clx * B->s + cly * B->c;
@@ -454,9 +460,11 @@ static void body_vs_walls(const phys_t* q, body_t* Q, double lx, double ly, doub
         const double qx = ax > q->HL ? ax : q->HL, qy = ay > q->GH ? ay : q->GH;
         const double ex = ax - qx, ey = ay - qy;
         const double d2 = ex * ex + ey * ey;
-        if (d2 < rho * rho) {
+        if (d2 < rho * rho && d2 > 1e-20) {
           const double d = sqrt(d2);
           nx = sx * ex / d; ny = sy * ey / d; depth = rho - d; hit = 1;
+        } else if (d2 < rho * rho) { /* on the block's surface within rounding: push out along x */
+          nx = -sx; ny = 0.0; depth = rho; hit = 1;
         }
       }
     } else { /* goal back wall x = +-(HL+GD) */
@@ -612,17 +620,33 @@ ORC_API void orc_step(const vss_params* p, uint64_t seed, int64_t global_offset,
     /* post_physics_step, vss.py:189-203 */
     s->progress[n] += 1;
     float rw[NB][4];
-    rewards_one(p, prev_ball, prev_rpos, s->ball_pos + 2 * n, (const float(*)[2])(s->r_pos + 2 * NB * n),
-                (const float(*)[2])act, rw);
+    /* safety net (engine-specific, not in the reference): a field whose state is not finite is
+     * re-randomised on the spot and reported as done with zero reward and no timeout */
+    int finite = isfinite(s->ball_pos[2 * n]) && isfinite(s->ball_pos[2 * n + 1]) &&
+                 isfinite(s->ball_vel[2 * n]) && isfinite(s->ball_vel[2 * n + 1]);
+    for (int k = 0; k < NB; ++k) {
+      const int64_t i = n * NB + k;
+      finite = finite && isfinite(s->r_pos[2 * i]) && isfinite(s->r_pos[2 * i + 1]) && isfinite(s->r_vel[2 * i]) &&
+               isfinite(s->r_vel[2 * i + 1]) && isfinite(s->r_rot[2 * i]) && isfinite(s->r_rot[2 * i + 1]) &&
+               isfinite(s->r_w[i]);
+    }
+    if (finite) {
+      rewards_one(p, prev_ball, prev_rpos, s->ball_pos + 2 * n, (const float(*)[2])(s->r_pos + 2 * NB * n),
+                  (const float(*)[2])act, rw);
+    } else {
+      reset_one(p, seed, (uint64_t)(global_offset + n), s, n);
+      memset(rw, 0, sizeof(rw));
+    }
     memcpy(rew + n * VSS_REW_PER_FIELD, rw, sizeof(rw));
     orc_compute_dones(1, s->ball_pos + 2 * n, s->progress + n, (float)p->max_episode_length, field_width,
                       goal_height, reset_buf + n);
+    if (!finite) reset_buf[n] = 1;
     if (term_obs) obs_one(s, n, term_obs + n * VSS_OBS_PER_FIELD);            /* :195-196 */
     if (progress_f) progress_f[n] = (float)s->progress[n];                    /* :198-200 */
-    if (reset_buf[n] != 0) reset_one(p, seed, (uint64_t)(global_offset + n), s, n); /* :202 */
+    if (reset_buf[n] != 0 && finite) reset_one(p, seed, (uint64_t)(global_offset + n), s, n); /* :202 */
     obs_one(s, n, obs + n * VSS_OBS_PER_FIELD);                               /* :203 */
     /* VecTask.step: timeout_buf = (progress_buf >= max_len - 1) & (reset_buf != 0) */
-    timeout[n] = (uint8_t)((s->progress[n] >= p->max_episode_length - 1) && (reset_buf[n] != 0));
+    timeout[n] = (uint8_t)(finite && (s->progress[n] >= p->max_episode_length - 1) && (reset_buf[n] != 0));
   }
 }
 

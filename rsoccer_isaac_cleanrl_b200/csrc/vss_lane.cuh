@@ -235,17 +235,23 @@ VSS_HD Hit circle_vs_box(const Body& B, float H, float px, float py, float rho) 
   const float dx = px - B.x, dy = py - B.y;
   const float lx = dx * B.c + dy * B.s, ly = -dx * B.s + dy * B.c;
   float nlx, nly, clx, cly;
-  if (fabsf(lx) < H && fabsf(ly) < H) {
-    const float pxd = H - fabsf(lx), pyd = H - fabsf(ly);
-    if (pxd < pyd) { nlx = sgnf(lx); nly = 0.0f; r.depth = pxd + rho; clx = sgnf(lx) * H; cly = ly; }
-    else { nlx = 0.0f; nly = sgnf(ly); r.depth = pyd + rho; clx = lx; cly = sgnf(ly) * H; }
-  } else {
+  bool face = fabsf(lx) <= H && fabsf(ly) <= H;  // centre inside (or exactly on) the box
+  if (!face) {
     const float qx = clampf(lx, -H, H), qy = clampf(ly, -H, H);
     const float ex = lx - qx, ey = ly - qy;
     const float d2 = ex * ex + ey * ey;
     if (d2 >= rho * rho) return r;
-    const float d = sqrtf(d2);
-    nlx = ex / d; nly = ey / d; r.depth = rho - d; clx = qx; cly = qy;
+    if (d2 > 1e-20f) {
+      const float d = sqrtf(d2);
+      nlx = ex / d; nly = ey / d; r.depth = rho - d; clx = qx; cly = qy;
+    } else {
+      face = true;  // centre within rounding of the surface: no direction to normalise, use the face rule
+    }
+  }
+  if (face) {  // face of least penetration
+    const float pxd = H - fabsf(lx), pyd = H - fabsf(ly);
+    if (pxd < pyd) { nlx = sgnf(lx); nly = 0.0f; r.depth = pxd + rho; clx = sgnf(lx) * H; cly = ly; }
+    else { nlx = 0.0f; nly = sgnf(ly); r.depth = pyd + rho; clx = lx; cly = sgnf(ly) * H; }
   }
   r.hit = true;
   r.nx = nlx * B.c - nly * B.s; r.ny = nlx * B.s + nly * B.c;
@@ -358,9 +364,11 @@ VSS_HD bool point_vs_walls(Body& Q, float lx, float ly, float rho, float mu, flo
         const float qx = fmaxf(ax, P.HL), qy = fmaxf(ay, P.GH);
         const float ex = ax - qx, ey = ay - qy;
         const float d2 = ex * ex + ey * ey;
-        if (d2 < rho * rho) {
+        if (d2 < rho * rho && d2 > 1e-20f) {
           const float d = sqrtf(d2);
           nx = sx * ex / d; ny = sy * ey / d; depth = rho - d; hit = true;
+        } else if (d2 < rho * rho) {  // on the block's surface within rounding: push out along x
+          nx = -sx; ny = 0.0f; depth = rho; hit = true;
         }
       }
     } else {  // goal back wall x = +-(HL+GD)
@@ -735,17 +743,40 @@ VSS_HD void lane_inject(float* S, long long env, const StepArgs& a) {
   }
 }
 
+// All dynamic state words of the field are finite.
+VSS_HD bool state_finite(const float* S) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int w = 0; w < VSS_STATE_FLOATS; ++w) {
+    const bool is_act = w >= 4 && ((w - 4) % 9) >= 7;
+    if (!is_act) acc = fmaf(S[w * LDS], 0.0f, acc);  // 0 * finite = 0; 0 * inf = NaN; NaN stays NaN
+  }
+  return acc == 0.0f;
+}
+
+enum : int { LANE_RUNNING = 0, LANE_DONE = 1, LANE_SANITISED = 2 };
+
 // Phase 1d: post_physics_step — progress, rewards, dones, per-field outputs (vss.py:189-193,
-// 218-265). Returns the done flag of this step.
+// 218-265). Returns LANE_DONE if the episode ended this step (masked reset follows in phase 3).
+// Safety net (not in the reference): a field whose state is not finite is re-randomised on the
+// spot and reported as done with zero reward (LANE_SANITISED), so that one bad field cannot
+// poison a training run.
 template <int VIEW>
-VSS_HD bool lane_phase1d(float* S, long long env, const StepArgs& a, const DevParams& P) {
+VSS_HD int lane_phase1d(float* S, long long env, const StepArgs& a, const DevParams& P, const RngKey& key) {
   constexpr int AGENTS = ViewShape<VIEW>::AGENTS;
   const int progress = (int)fbits(S[VSS_W_PROGRESS * LDS]) + 1;
   S[VSS_W_PROGRESS * LDS] = bitsf((uint32_t)progress);
   float rew[VSS_REW_PER_FIELD];
-  rewards_lane(S, P, rew);
-  const bool done = is_goal(S[0], S[LDS], P) || progress >= P.max_len;
-  const bool tmo = done && progress >= P.max_len - 1;  // VecTask.step timeout_buf
+  const bool finite = state_finite(S);
+  if (finite) {
+    rewards_lane(S, P, rew);
+  } else {
+    reset_lane(S, P, key);
+#pragma unroll
+    for (int k = 0; k < VSS_REW_PER_FIELD; ++k) rew[k] = 0.0f;
+  }
+  const bool done = !finite || is_goal(S[0], S[LDS], P) || progress >= P.max_len;
+  const bool tmo = done && finite && progress >= P.max_len - 1;  // VecTask.step timeout_buf
   a.reset_buf[env] = done ? 1 : 0;
   if (VIEW == VIEW_FULL) {
     float* rp = a.rew + env * VSS_REW_PER_FIELD;
@@ -780,7 +811,7 @@ VSS_HD bool lane_phase1d(float* S, long long env, const StepArgs& a, const DevPa
       }
     }
   }
-  return done;
+  return !done ? LANE_RUNNING : (finite ? LANE_DONE : LANE_SANITISED);
 }
 
 // Phase 5: state out (+ zero the view's action buffer row of a done field, wrappers.py:105-107)

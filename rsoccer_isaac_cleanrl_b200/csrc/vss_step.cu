@@ -87,8 +87,9 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   if (INJECT) { if (active) lane_inject(S, env, a); }
   else physics_tile<SYNC>(T, lane, active, P, a.sync_level);
   if (SYNC) __syncthreads();
-  bool done = false;
-  if (active) done = lane_phase1d<VIEW>(S, env, a, P);
+  int code = LANE_RUNNING;
+  if (active) code = lane_phase1d<VIEW>(S, env, a, P, key);
+  const bool done = code == LANE_DONE;   // needs the masked reset of phase 3
   __syncwarp();
   if (SYNC && a.sync_level >= 2) __syncthreads();
   // 2. terminal observation + observation of the fields that keep their state (vss.py:195-196)
@@ -104,7 +105,7 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask);
   // 5. state out
   if (SYNC && a.sync_level >= 2) __syncthreads();
-  if (active) lane_phase5<VIEW>(S, env, a, done);
+  if (active) lane_phase5<VIEW>(S, env, a, code != LANE_RUNNING);
 }
 
 // Advances the device-resident step index after a step (stream-ordered, so graph replays see it).

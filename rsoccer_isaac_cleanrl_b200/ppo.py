@@ -184,7 +184,7 @@ class FlatAdam:
         self.flat.sub_((self.m / denom) * (self.lr_t / bc1))
 
 
-def train(args, log=print):
+def train(args, log=print, hook=None):
     import torch.distributed as dist
     from .envs import RecordEpisodeStatisticsTorch, make_env
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -368,6 +368,11 @@ def train(args, log=print):
                 break
         torch.cuda.synchronize()
         t_upd += time.time() - tu0
+        if hook is not None:  # diagnostics: called once per update with the live tensors
+            hook(update, dict(obs=obs_all, actions=actions, logprobs=logprobs, rewards=rewards, values=values,
+                              next_values=next_values, advantages=advantages, returns=returns, flat=flat,
+                              flat_grad=flat_grad, term_obs=term_obs_all, next_dones=next_dones,
+                              agent=agent, env=unwrapped_env, stats=mb_stats))
         stats["rollout_wall"].append(tu0 - tr0)
         stats["update_wall"].append(time.time() - tu0)
         sps = int(global_step / (time.time() - start_time))

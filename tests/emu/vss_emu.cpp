@@ -24,7 +24,7 @@ static void emu_step_t(const StepArgs& a, const DevParams& P) {
     float* T = Tbuf.data();
     const long long env0 = tile * 32;
     const int valid = (int)std::min(32LL, a.n - env0);
-    bool done[32] = {false};
+    bool done[32] = {false}, ended[32] = {false};
     uint32_t done_mask = 0;
     for (int lane = 0; lane < valid; ++lane) lane_phase1a<VIEW>(T + lane, env0 + lane, a, P, make_key(a, env0 + lane));
     if (INJECT) {
@@ -41,7 +41,9 @@ static void emu_step_t(const StepArgs& a, const DevParams& P) {
       }
     }
     for (int lane = 0; lane < valid; ++lane) {
-      done[lane] = lane_phase1d<VIEW>(T + lane, env0 + lane, a, P);
+      const int code = lane_phase1d<VIEW>(T + lane, env0 + lane, a, P, make_key(a, env0 + lane));
+      done[lane] = code == LANE_DONE;
+      ended[lane] = code != LANE_RUNNING;
       if (done[lane]) done_mask |= 1u << lane;
     }
     float* ob = a.obs + env0 * (PER_FIELD * 4);
@@ -50,7 +52,7 @@ static void emu_step_t(const StepArgs& a, const DevParams& P) {
     for (int lane = 0; lane < valid; ++lane)
       if (done[lane]) reset_lane(T + lane, P, make_key(a, env0 + lane));
     for (int lane = 0; lane < 32; ++lane) write_obs_fields(T, g_tab.v, lane, PER_FIELD, ob, done_mask);
-    for (int lane = 0; lane < valid; ++lane) lane_phase5<VIEW>(T + lane, env0 + lane, a, done[lane]);
+    for (int lane = 0; lane < valid; ++lane) lane_phase5<VIEW>(T + lane, env0 + lane, a, ended[lane]);
   }
 }
 

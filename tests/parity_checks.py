@@ -312,3 +312,76 @@ def check_golden_injected(Backend, golden_path):
     out2 = be2.step(g["acts"], rb2, post_state=post)
     np.testing.assert_allclose(out2["rew"][..., 3], g["energy_rew"] * 0.5, rtol=1e-6, atol=1e-7)
     return n
+
+
+# --------------------------------------------------------------------------- robustness
+def chase_actions(obs, noise):
+    """All six robots steer at the ball (heavy contact: scrums, pushing along walls)."""
+    rel = obs[..., 0:2] - obs[..., 4:6]
+    c, s = obs[..., 8], obs[..., 9]
+    fwd = rel[..., 0] * c + rel[..., 1] * s
+    lat = -rel[..., 0] * s + rel[..., 1] * c
+    turn = np.arctan2(lat, fwd)
+    return (np.stack([1.0 - 1.5 * turn, 1.0 + 1.5 * turn], -1) + 0.2 * noise).astype(np.float32)
+
+
+def check_degenerate_contact(Backend, golden_path):
+    """Regression: ball centre exactly on a box surface used to give a 0/0 contact normal."""
+    g = np.load(golden_path)
+    n = 40
+    be, p = make_backend_pair(Backend, n, 1, 0)
+    s = np.zeros((60, be.ld), np.float32)
+    s[:, :n] = g["state"][:, None]
+    be.set_state(s)
+    rb = np.zeros(n, np.int64)
+    st = oracle_from_backend(be)
+    rb_ref = rb.copy()
+    acts = np.broadcast_to(g["actions"], (n, 2, 3, 2)).copy()
+    out = be.step(acts, rb)
+    ref = orc.step(p, 1, 0, st, acts, rb_ref)
+    for k in ("obs", "term_obs", "rew"):
+        assert np.isfinite(out[k]).all() and np.isfinite(ref[k]).all(), k
+    assert np.isfinite(be.get_state()[:58, :n]).all()
+
+
+def check_chase_stress(Backend, n=2048, steps=150, seed=7):
+    """Contact-heavy rollout: every state word stays finite and inside the field box."""
+    be, p = make_backend_pair(Backend, n, seed, 0)
+    rb = np.ones(n, np.int64)
+    obs = be.reset_dones(rb)
+    rb[:] = 0
+    rng = np.random.default_rng(3)
+    for t in range(steps):
+        out = be.step(chase_actions(obs, rng.uniform(-1.2, 1.2, (n, 2, 3, 2))), rb)
+        obs = out["obs"]
+        assert np.isfinite(out["obs"]).all() and np.isfinite(out["term_obs"]).all() and np.isfinite(out["rew"]).all(), t
+    st = be.get_state()[:58, :n]
+    assert np.isfinite(st).all()
+    assert np.abs(st[0]).max() <= 0.85 + 1e-5 and np.abs(st[1]).max() <= 0.65 + 1e-5
+
+
+def check_nonfinite_guard(Backend, n=96):
+    """Safety net: a field whose state is not finite is re-randomised on the spot, reported done with
+    zero reward and no timeout; its neighbours are untouched; backend and oracle agree."""
+    be, p = make_backend_pair(Backend, n, 3, 0)
+    rb = np.ones(n, np.int64)
+    be.reset_dones(rb)
+    rb[:] = 0
+    s = be.get_state()
+    poisoned = [0, 33, 95]
+    s[0, poisoned[0]] = np.nan          # ball x
+    s[4 + 9 * 2 + 6, poisoned[1]] = np.inf  # a yaw rate
+    s[4 + 9 * 5 + 2, poisoned[2]] = -np.inf  # a velocity
+    be.set_state(s)
+    st = oracle_from_backend(be)
+    rb_ref = rb.copy()
+    acts = np.random.default_rng(0).uniform(-1, 1, (n, 2, 3, 2)).astype(np.float32)
+    out = be.step(acts, rb)
+    ref = orc.step(p, 3, 0, st, acts, rb_ref)
+    for k in ("obs", "term_obs", "rew"):
+        assert np.isfinite(out[k]).all(), k
+    assert all(rb[i] == 1 for i in poisoned) and np.array_equal(rb, rb_ref)
+    assert np.all(out["rew"][poisoned] == 0) and np.all(out["timeout"][poisoned] == 0)
+    assert np.array_equal(bits(out["obs"][poisoned]), bits(out["term_obs"][poisoned]))   # fresh state in both
+    compare_full_step(out, ref, rb, rb_ref, n, "non-finite guard", exact_physics=False)
+    assert np.isfinite(be.get_state()[:58, :n]).all()

@@ -33,3 +33,15 @@ def test_rollout_tracks_oracle_physics():
 @pytest.mark.parametrize("view", [orc.VIEW_SA, orc.VIEW_CMA, orc.VIEW_DMA])
 def test_views(view):
     pc.check_views(EmuBackend, view)
+
+
+def test_degenerate_contact_normal_regression():
+    pc.check_degenerate_contact(EmuBackend, os.path.join(GOLDEN, "degenerate_ball_on_box_corner.npz"))
+
+
+def test_nonfinite_state_guard():
+    pc.check_nonfinite_guard(EmuBackend)
+
+
+def test_contact_heavy_rollout_stays_finite():
+    pc.check_chase_stress(EmuBackend)

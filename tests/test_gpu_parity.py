@@ -137,3 +137,15 @@ def test_full_size_properties(Gpu):
     # energy reward off at the default weights; goal reward is in {-10, 0, 10}
     assert np.all(out["rew"][..., 3] == 0) and set(np.unique(out["rew"][..., 0])) <= {-10.0, 0.0, 10.0}
     assert np.array_equal(out["rew"][:, 0, :, 1], -out["rew"][:, 1, :, 1])
+
+
+def test_degenerate_contact_normal_regression(Gpu):
+    pc.check_degenerate_contact(Gpu, os.path.join(GOLDEN, "degenerate_ball_on_box_corner.npz"))
+
+
+def test_nonfinite_state_guard(Gpu):
+    pc.check_nonfinite_guard(Gpu)
+
+
+def test_contact_heavy_rollout_stays_finite(Gpu):
+    pc.check_chase_stress(Gpu, n=65536, steps=300)
