@@ -96,7 +96,8 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
   float* ob = a.obs + env0 * (PER_FIELD * 4);
   float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
-  write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, done_mask);
+  if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD>(T, tab, lane, valid, tob, ob, done_mask);
+  else write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, done_mask);
   __syncwarp();
   // 3. masked reset (vss.py:202, 267-333)
   if (done) reset_lane(S, P, key);

@@ -48,7 +48,10 @@ static void emu_step_t(const StepArgs& a, const DevParams& P) {
     }
     float* ob = a.obs + env0 * (PER_FIELD * 4);
     float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
-    for (int lane = 0; lane < 32; ++lane) write_obs_tile(T, g_tab.v, lane, valid, PER_FIELD, tob, ob, done_mask);
+    for (int lane = 0; lane < 32; ++lane) {
+      if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD>(T, g_tab.v, lane, valid, tob, ob, done_mask);
+      else write_obs_tile(T, g_tab.v, lane, valid, PER_FIELD, tob, ob, done_mask);
+    }
     for (int lane = 0; lane < valid; ++lane)
       if (done[lane]) reset_lane(T + lane, P, make_key(a, env0 + lane));
     for (int lane = 0; lane < 32; ++lane) write_obs_fields(T, g_tab.v, lane, PER_FIELD, ob, done_mask);
