@@ -227,11 +227,33 @@ def run_native(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = BYTES_PER_FIELD_STEP * n / (ms * 1e-3 / args.steps) / 1e9
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, scaled per field
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_step_traffic.json")))
+        traffic = tr["dram_bytes_per_field_step"] * n
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_step<full>", "algorithmic_bytes_per_launch": BYTES_PER_FIELD_STEP * n,
+                "traffic": traffic, "kernel": "k_step<full>", "algorithmic_bytes_per_launch": BYTES_PER_FIELD_STEP * n,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"}
 
-    launches = args.steps + args.warmup
+    launches = 2 * args.steps  # timed region: K x (k_step + the 1-thread k_bump that advances the step index)
+
+    # ---- GAE reverse scan (BASELINE roofline row: 28 B per (t, env)), T = 128, N = 65536
+    gae_res = None
+    if world == 1:
+        from rsoccer_isaac_cleanrl_b200.engine import gae as gae_kernel
+        Tn, Nn = 128, 65536
+        gin = [torch.randn((Tn, Nn), device="cuda") for _ in range(3)]
+        gd = (torch.rand((Tn, Nn), device="cuda") < 0.01).float()
+        gto = gd * (torch.rand((Tn, Nn), device="cuda") < 0.5).float()
+        adv, ret = torch.empty_like(gd), torch.empty_like(gd)
+        # 7 x 33.5 MB per call = 235 MB: larger than L2, so consecutive calls do not hit in cache
+        ms_g = time_steps(torch, dist, 1, lambda i: gae_kernel(*gin, gd, gto, 0.99, 0.95, adv, ret), 50, 5)
+        gbs = 28.0 * Tn * Nn / (ms_g * 1e-3 / 50) / 1e9
+        gae_res = {"elements_per_s": Tn * Nn * 50 / (ms_g * 1e-3), "us_per_call": ms_g * 1e3 / 50, "achieved_gbs": gbs,
+                   "frac": gbs / peak, "workload": f"vss_gae T={Tn} N={Nn}, 28 B per (t, env)"}
+        del gin, gd, gto, adv, ret
     # ---- e2e: the user-facing call with HOST buffers (SingleAgent view): pinned policy action ->
     #      device, fused view step, view obs/reward/done -> pinned host, every step.
     e2e = None
@@ -305,7 +327,7 @@ def run_native(args):
                                                "(> 126 MB L2 when envs_per_gpu >= 65536)",
                        "parallelism": f"fields sharded over {world} GPU(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "ppo": ppo_res,
+            "clocks": clocks, "ppo": ppo_res, "gae": gae_res,
         }
         if sweep:
             line["sweep"] = sweep
