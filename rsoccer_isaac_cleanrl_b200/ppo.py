@@ -324,7 +324,9 @@ def train(args, log=print, hook=None):
         stop = False
         for epoch in range(args.update_epochs):
             b_inds = torch.randperm(args.batch_size, device=device)
-            for start in range(0, args.batch_size, args.minibatch_size):
+            # full minibatches only (the reference's loop at ppo…:310 also visits a shorter remainder when
+            # batch_size is not a multiple of num_minibatches; with the default flags there is none)
+            for start in range(0, args.batch_size - args.minibatch_size + 1, args.minibatch_size):
                 mb_inds.copy_(b_inds[start:start + args.minibatch_size])
                 optimizer.sync_lr()
                 if fb_graph is not None:

@@ -144,3 +144,33 @@ def test_play_matches_with_team_policies(tmp_path):
     score, length = play.play_matches(envs, blue, yellow, 200)
     assert -1.0 <= score <= 1.0 and 1.0 <= length <= 400.0
     assert set(play.baseline_teams(str(tmp_path))) == {"zero", "ou"}   # no base_nets checkpoints present
+
+
+def test_cuda_graph_replay_advances_the_ou_stream():
+    """A captured vss_step_view launch must not freeze the OU-noise counter: the step index lives on
+    the device and is bumped by a stream-ordered kernel, so every replay draws new noise."""
+    from rsoccer_isaac_cleanrl_b200.envs import VSS, SingleAgent
+    envs = VSS(_cfg(256), "cuda:0", "cuda:0", 0, True, seed=11)
+    view = SingleAgent(envs)
+    act = torch.zeros((256, 2), device="cuda")
+    view.step(act)                       # eager warm-up
+    torch.cuda.synchronize()
+    assert envs.engine.step_count == 1
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        view.step(act)
+    bufs = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        bufs.append(view.action_buf.clone())
+    assert envs.engine.step_count == 4
+    assert not torch.equal(bufs[0], bufs[1]) and not torch.equal(bufs[1], bufs[2])
+    # and the replayed sequence equals the eager sequence from the same start
+    envs2 = VSS(_cfg(256), "cuda:0", "cuda:0", 0, True, seed=11)
+    view2 = SingleAgent(envs2)
+    for _ in range(4):
+        view2.step(act)
+    torch.cuda.synchronize()
+    assert torch.equal(view2.action_buf, bufs[2])
+    assert torch.equal(envs2.engine.get_state(), envs.engine.get_state())

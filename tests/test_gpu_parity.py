@@ -42,7 +42,6 @@ def test_rollout_tracks_oracle_physics(Gpu):
 
 @pytest.mark.parametrize("n", [1, 31, 33, 4097])
 def test_ragged_sizes(Gpu, n):
-    pc.check_rollout.__wrapped__ if hasattr(pc.check_rollout, "__wrapped__") else None
     be, p = pc.make_backend_pair(Gpu, n, 3, 10)
     rb = np.ones(n, np.int64)
     be.reset_dones(rb)
