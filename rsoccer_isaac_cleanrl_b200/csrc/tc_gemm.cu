@@ -154,69 +154,109 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;   // 8 / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/ +
+                               4 * 32 * 80 /*epilogue staging*/;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// One 32-column chunk of one accumulator row through the fused epilogue (v = 32 fp32 from TMEM).
+constexpr int STAGE_PITCH = 80;                       // bytes per staged row: 64 B of bf16 + 16 B pad (conflict-free STS.128)
+constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH;
+
+// One 32-column chunk of a warp's 32 accumulator rows through the fused epilogue (v = this lane's
+// row, 32 fp32 from TMEM). bf16 results are re-staged through shared memory so that every global
+// store instruction writes whole 64-byte row segments of 8 rows (4x fewer L1TEX wavefronts than
+// one 16-byte piece of 32 different rows per instruction, which bound the first version).
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col, const GemmArgs& g,
-                                               const float* bias_s, bool bias_in_smem) {
-      if (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16) {
-        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + col;
-        uint32_t packed[16];
-        if (EPI == EPI_BIAS_TANH_BF16) {
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m_base, int lane, int col, const GemmArgs& g,
+                                               const float* bias_s, bool bias_in_smem, uint8_t* stage) {
+  const int row = m_base + lane;
+  if (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16) {
+    uint32_t packed[16];
+    if (EPI == EPI_BIAS_TANH_BF16) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bv = bias_in_smem ? *reinterpret_cast<const float4*>(bias_s + col + 4 * j)
-                                           : __ldg(reinterpret_cast<const float4*>(g.bias + col + 4 * j));
-            const float a = tanh_fast(__uint_as_float(v[4 * j]) + bv.x);
-            const float b = tanh_fast(__uint_as_float(v[4 * j + 1]) + bv.y);
-            const float c2 = tanh_fast(__uint_as_float(v[4 * j + 2]) + bv.z);
-            const float d = tanh_fast(__uint_as_float(v[4 * j + 3]) + bv.w);
-            __nv_bfloat162 p = __floats2bfloat162_rn(a, b), q2 = __floats2bfloat162_rn(c2, d);
-            packed[2 * j] = *reinterpret_cast<uint32_t*>(&p);
-            packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&q2);
-          }
-        } else {
-          const uint4* arow = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + col);
+      for (int j = 0; j < 8; ++j) {
+        const float4 bv = bias_in_smem ? *reinterpret_cast<const float4*>(bias_s + col + 4 * j)
+                                       : __ldg(reinterpret_cast<const float4*>(g.bias + col + 4 * j));
+        const float a = tanh_fast(__uint_as_float(v[4 * j]) + bv.x);
+        const float b = tanh_fast(__uint_as_float(v[4 * j + 1]) + bv.y);
+        const float c2 = tanh_fast(__uint_as_float(v[4 * j + 2]) + bv.z);
+        const float d = tanh_fast(__uint_as_float(v[4 * j + 3]) + bv.w);
+        __nv_bfloat162 p = __floats2bfloat162_rn(a, b), q2 = __floats2bfloat162_rn(c2, d);
+        packed[2 * j] = *reinterpret_cast<uint32_t*>(&p);
+        packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&q2);
+      }
+    } else {
+      // aux tile (the activations whose tanh' multiplies the accumulator): coalesced 64-byte row
+      // segments -> shared memory -> each lane reads back its own row
+      __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 y4 = __ldg(arow + j);
-            const uint32_t yy[4] = {y4.x, y4.y, y4.z, y4.w};
+      for (int k = 0; k < 4; ++k) {
+        const int r = k * 8 + (lane >> 2), c16 = lane & 3;
+        uint4 y4 = make_uint4(0, 0, 0, 0);
+        if (m_base + r < g.M) y4 = __ldg(reinterpret_cast<const uint4*>(g.aux + (size_t)(m_base + r) * g.ld_aux + col) + c16);
+        *reinterpret_cast<uint4*>(stage + r * STAGE_PITCH + c16 * 16) = y4;
+      }
+      __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yy[i]);
-              const float ya = __bfloat162float(y2.x), yb = __bfloat162float(y2.y);
-              const float a = __uint_as_float(v[8 * j + 2 * i]) * (1.0f - ya * ya);
-              const float b = __uint_as_float(v[8 * j + 2 * i + 1]) * (1.0f - yb * yb);
-              __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-              packed[4 * j + i] = *reinterpret_cast<uint32_t*>(&p);
-            }
-          }
-        }
-        uint4* o4 = reinterpret_cast<uint4*>(orow);
+      for (int j = 0; j < 4; ++j) {
+        const uint4 y4 = *reinterpret_cast<const uint4*>(stage + lane * STAGE_PITCH + j * 16);
+        const uint32_t yy[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      } else if (EPI == EPI_ATOMIC_F32) {
-        float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(orow + i, __uint_as_float(v[i]));
-      } else {
-        float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o;
-          o.x = __uint_as_float(v[4 * j]) + (g.bias ? __ldg(g.bias + col + 4 * j) : 0.0f);
-          o.y = __uint_as_float(v[4 * j + 1]) + (g.bias ? __ldg(g.bias + col + 4 * j + 1) : 0.0f);
-          o.z = __uint_as_float(v[4 * j + 2]) + (g.bias ? __ldg(g.bias + col + 4 * j + 2) : 0.0f);
-          o.w = __uint_as_float(v[4 * j + 3]) + (g.bias ? __ldg(g.bias + col + 4 * j + 3) : 0.0f);
-          reinterpret_cast<float4*>(orow)[j] = o;
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yy[i]);
+          const float ya = __bfloat162float(y2.x), yb = __bfloat162float(y2.y);
+          const float a = __uint_as_float(v[8 * j + 2 * i]) * (1.0f - ya * ya);
+          const float b = __uint_as_float(v[8 * j + 2 * i + 1]) * (1.0f - yb * yb);
+          __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+          packed[4 * j + i] = *reinterpret_cast<uint32_t*>(&p);
         }
       }
+      __syncwarp();
+    }
+    if (EPI == EPI_BIAS_TANH_BF16) {  // measured: the forward epilogue is not bound by its stores; write directly
+      if (row < g.M) {
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + col);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      }
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(stage + lane * STAGE_PITCH + j * 16) =
+          make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    __syncwarp();
+    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(g.out) + col;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = k * 8 + (lane >> 2), c16 = lane & 3;
+      const uint4 o = *reinterpret_cast<const uint4*>(stage + r * STAGE_PITCH + c16 * 16);
+      if (m_base + r < g.M) *(reinterpret_cast<uint4*>(obase + (size_t)(m_base + r) * g.ldo) + c16) = o;
+    }
+    __syncwarp();
+  } else if (EPI == EPI_ATOMIC_F32) {
+    if (row < g.M) {
+      float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(orow + i, __uint_as_float(v[i]));
+    }
+  } else {
+    if (row < g.M) {
+      float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o;
+        o.x = __uint_as_float(v[4 * j]) + (g.bias ? __ldg(g.bias + col + 4 * j) : 0.0f);
+        o.y = __uint_as_float(v[4 * j + 1]) + (g.bias ? __ldg(g.bias + col + 4 * j + 1) : 0.0f);
+        o.z = __uint_as_float(v[4 * j + 2]) + (g.bias ? __ldg(g.bias + col + 4 * j + 2) : 0.0f);
+        o.w = __uint_as_float(v[4 * j + 3]) + (g.bias ? __ldg(g.bias + col + 4 * j + 3) : 0.0f);
+        reinterpret_cast<float4*>(orow)[j] = o;
+      }
+    }
+  }
 }
 
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so
@@ -235,6 +275,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(smem + STAGES * Smem<BN>::STAGE_BYTES + 256);  // [<= 512]
+  uint8_t* stage = smem + STAGES * Smem<BN>::STAGE_BYTES + 256 + 2048 + ((threadIdx.x >> 5) & 3) * STAGE_BYTES_PER_WARP;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
@@ -318,7 +359,6 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       const int r = t % tiles_per_split;
       const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
-      const int row = m0 + q * 32 + lane;
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
       mbar_wait(&tfull_bar[buf], bph);
       tc_fence_after();
@@ -326,7 +366,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
-        if (row < g.M) epilogue_chunk<EPI>(v, row, n0 + c, g, bias_s, bias_in_smem);
+        epilogue_chunk<EPI>(v, m0 + q * 32, lane, n0 + c, g, bias_s, bias_in_smem, stage);
       }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld): hand the buffer back
       tc_fence_before();
@@ -353,7 +393,7 @@ constexpr int WS_MAX_KB = 8;  // K <= 512
 struct SmemWS {
   static constexpr int B_BYTES = WS_MAX_KB * 128 * BK * 2;       // 128 KB resident weight slice
   static constexpr int A_BYTES = BM * BK * 2;                    // 16 KB per stage
-  static constexpr int TOTAL = B_BYTES + WS_STAGES * A_BYTES + 1024 + 256 + 2048;
+  static constexpr int TOTAL = B_BYTES + WS_STAGES * A_BYTES + 1024 + 256 + 2048 + 4 * 32 * 80;
 };
 
 template <int EPI>
@@ -372,6 +412,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* b_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
   float* bias_s = reinterpret_cast<float*>(smem_a + WS_STAGES * SmemWS::A_BYTES + 256);
+  uint8_t* stage = smem_a + WS_STAGES * SmemWS::A_BYTES + 256 + 2048 + ((threadIdx.x >> 5) & 3) * STAGE_BYTES_PER_WARP;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
@@ -437,7 +478,6 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int q = warp & 3;
     uint32_t lt = 0;
     for (int mt = m_first; mt < m_tiles; mt += m_step, ++lt) {
-      const int row = mt * BM + q * 32 + lane;
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
       mbar_wait(&tfull_bar[buf], bph);
       tc_fence_after();
@@ -445,7 +485,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
-        if (row < g.M) epilogue_chunk<EPI>(v, row, n0 + c, g, bias_s, bias_in_smem);
+        epilogue_chunk<EPI>(v, mt * BM + q * 32, lane, n0 + c, g, bias_s, bias_in_smem, stage);
       }
       tc_fence_before();
       __syncwarp();
