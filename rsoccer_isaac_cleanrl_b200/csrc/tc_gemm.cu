@@ -9,7 +9,7 @@
 //   warp 1      TMEM allocator + MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16)
 //               into one of two TMEM accumulator buffers; tcgen05.commit releases smem stages and
 //               signals the accumulator
-//   warps 2-5   epilogue: tcgen05.ld 32 TMEM lanes x 32 columns per warp, fused bias+tanh /
+//   warps 2-5   epilogue (one warp per TMEM lane quarter): tcgen05.ld 32 lanes x 32 columns, fused bias+tanh /
 //               tanh-derivative / split-K fp32 atomics, vectorised global stores
 // Every mbarrier wait is bounded (trap instead of hanging the GPU).
 #include <cuda.h>
@@ -31,7 +31,8 @@ constexpr int BM = 128;       // CTA tile rows = UMMA M
 constexpr int BK = 64;        // k-block: 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;    // bf16
 constexpr int STAGES = 3;    // 3 x 32 KB: two CTAs per SM, so one CTA's epilogue overlaps the other's MMAs
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 4;       // one warp per TMEM lane quarter (8 = two per quarter was measured: no gain, the kernel is operand-feed bound)
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 enum Epilogue : int {
   EPI_BIAS_TANH_BF16 = 0,  // out_bf16 = tanh(acc + bias[n])                       (forward hidden layer)
@@ -155,7 +156,7 @@ struct Smem {
   static constexpr int B_BYTES = BN * BK * 2;   // 8 / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/ +
-                               4 * 32 * 80 /*epilogue staging*/;
+                               EPI_WARPS * 32 * 80 /*epilogue staging*/;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -275,7 +276,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(smem + STAGES * Smem<BN>::STAGE_BYTES + 256);  // [<= 512]
-  uint8_t* stage = smem + STAGES * Smem<BN>::STAGE_BYTES + 256 + 2048 + ((threadIdx.x >> 5) & 3) * STAGE_BYTES_PER_WARP;
+  uint8_t* stage = smem + STAGES * Smem<BN>::STAGE_BYTES + 256 + 2048 + (((threadIdx.x >> 5) + EPI_WARPS - 2) % EPI_WARPS) * STAGE_BYTES_PER_WARP;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
@@ -285,7 +286,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
@@ -354,7 +355,9 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
-    const int q = warp & 3;
+    const int q = warp & 3;                              // TMEM lane quarter this warp may touch
+    constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);  // column share of this warp within the quarter
+    const int c_begin = ((warp - 2) >> 2) * COLS_PER_WARP;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       const int r = t % tiles_per_split;
@@ -363,7 +366,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       mbar_wait(&tfull_bar[buf], bph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_begin; c < c_begin + COLS_PER_WARP; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
         epilogue_chunk<EPI>(v, m0 + q * 32, lane, n0 + c, g, bias_s, bias_in_smem, stage);
@@ -393,7 +396,7 @@ constexpr int WS_MAX_KB = 8;  // K <= 512
 struct SmemWS {
   static constexpr int B_BYTES = WS_MAX_KB * 128 * BK * 2;       // 128 KB resident weight slice
   static constexpr int A_BYTES = BM * BK * 2;                    // 16 KB per stage
-  static constexpr int TOTAL = B_BYTES + WS_STAGES * A_BYTES + 1024 + 256 + 2048 + 4 * 32 * 80;
+  static constexpr int TOTAL = B_BYTES + WS_STAGES * A_BYTES + 1024 + 256 + 2048 + EPI_WARPS * 32 * 80;
 };
 
 template <int EPI>
@@ -412,7 +415,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* b_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
   float* bias_s = reinterpret_cast<float*>(smem_a + WS_STAGES * SmemWS::A_BYTES + 256);
-  uint8_t* stage = smem_a + WS_STAGES * SmemWS::A_BYTES + 256 + 2048 + ((threadIdx.x >> 5) & 3) * STAGE_BYTES_PER_WARP;
+  uint8_t* stage = smem_a + WS_STAGES * SmemWS::A_BYTES + 256 + 2048 + (((threadIdx.x >> 5) + EPI_WARPS - 2) % EPI_WARPS) * STAGE_BYTES_PER_WARP;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
@@ -423,7 +426,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
     mbar_init(b_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -475,14 +478,16 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       }
     }
   } else {  // ---- epilogue
-    const int q = warp & 3;
+    const int q = warp & 3;                              // TMEM lane quarter this warp may touch
+    constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);  // column share of this warp within the quarter
+    const int c_begin = ((warp - 2) >> 2) * COLS_PER_WARP;
     uint32_t lt = 0;
     for (int mt = m_first; mt < m_tiles; mt += m_step, ++lt) {
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
       mbar_wait(&tfull_bar[buf], bph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_begin; c < c_begin + COLS_PER_WARP; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
         epilogue_chunk<EPI>(v, mt * BM + q * 32, lane, n0 + c, g, bias_s, bias_in_smem, stage);
