@@ -65,3 +65,20 @@ def test_no_cpu_fallback():
         R.Engine(16, "cuda:0")
     with pytest.raises(RuntimeError):
         R.Engine(16, "cpu")
+
+
+def test_argument_validation_without_a_device():
+    """Bad arguments are rejected before any CUDA call: empty batches, null pointers, bad views."""
+    from rsoccer_isaac_cleanrl_b200 import _lib
+    lib = _lib.load_library()
+    p = _lib.default_params()
+    h = C.c_void_p()
+    assert lib.vss_create(C.byref(h), C.byref(p), 0, 0, 0, 1) == -1 and b"num_envs" in lib.vss_last_error()
+    assert lib.vss_create(None, C.byref(p), 16, 0, 0, 1) == -1
+    p.substeps = 1000
+    assert lib.vss_create(C.byref(h), C.byref(p), 16, 0, 0, 1) == -1 and b"substeps" in lib.vss_last_error()
+    assert lib.vss_step(None, None, None, None, None, None, None, None, None) == -1
+    assert lib.vss_gae(None, None, None, None, None, None, None, 128, 16, 0.99, 0.95, None) == -1
+    assert lib.vss_gemm_bf16_tn(None, 8, None, 8, None, 8, 128, 128, 64, 0, None, None, 0, 1, 0, None) == -1
+    assert lib.vss_destroy(None) == 0
+    assert lib.vss_num_envs(None) == 0
