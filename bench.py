@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-ppo", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also time N in {1K..1M} (config 5) into `sweep`")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the N in {1K..1M} sweep (BASELINE configs[4])")
     ap.add_argument("--ppo-env-id", default="sa")
     ap.add_argument("--ppo-envs", type=int, default=4096, help="agents per GPU of the PPO leg (configs[1])")
     ap.add_argument("--ppo-updates", type=int, default=6)
@@ -271,16 +271,18 @@ def run_native(args):
         launches += k_e2e + 3
 
     sweep = None
-    if args.sweep and world == 1:
+    if not args.no_sweep:
+        # BASELINE configs[4]: random-action step throughput from 1K to 1M fields per GPU (same full
+        # VSS.step contract; sizes below ~64K fields fit in L2 and are launch/latency bound)
         sweep = []
         del envs, acts
         for ne in (1024, 4096, 16384, 65536, 262144, 1048576):
             e2, a2 = make_task(torch, ne, rank, local)
             f = lambda i: e2.step(a2[i & 3])
-            m = time_steps(torch, dist, 1, f, 200, 20)
-            sweep.append({"envs": ne, "env_steps_per_s": ne * 200 / (m * 1e-3), "us_per_step": m * 1e3 / 200,
+            m = time_steps(torch, dist, world, f, 200, 20)
+            sweep.append({"envs_per_gpu": ne, "env_steps_per_s": world * ne * 200 / (m * 1e-3),
+                          "us_per_step": m * 1e3 / 200,
                           "hbm_frac": BYTES_PER_FIELD_STEP * ne / (m * 1e-3 / 200) / 1e9 / peak})
-            launches += 220
             del e2, a2
 
     # ---- PPO SPS (BASELINE configs[1]: ppo-sa, 4096 envs per GPU, OU-noise opponents as in training)

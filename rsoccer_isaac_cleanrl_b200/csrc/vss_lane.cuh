@@ -639,10 +639,13 @@ VSS_HD void ou_lane(float a[VSS_ACT_PER_FIELD], const DevParams& P, const RngKey
 #if defined(__CUDA_ARCH__)
 VSS_HD F4 ld4(const float* p) { const float4 v = *reinterpret_cast<const float4*>(p); return F4{v.x, v.y, v.z, v.w}; }
 VSS_HD void st4(float* p, const F4& v) { *reinterpret_cast<float4*>(p) = make_float4(v.x, v.y, v.z, v.w); }
+// streaming store (evict-first): observations are written once and never re-read by this kernel
+VSS_HD void st4_stream(float* p, const F4& v) { __stcs(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, v.w)); }
 VSS_HD float ldg(const float* p) { return __ldg(p); }
 #else
 VSS_HD F4 ld4(const float* p) { return F4{p[0], p[1], p[2], p[3]}; }
 VSS_HD void st4(float* p, const F4& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
+VSS_HD void st4_stream(float* p, const F4& v) { st4(p, v); }
 VSS_HD float ldg(const float* p) { return *p; }
 #endif
 
@@ -876,8 +879,8 @@ VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, i
         const F4 v{bitsf(fbits(T[off[sl][0] + e]) ^ sgn[sl][0]), bitsf(fbits(T[off[sl][1] + e]) ^ sgn[sl][1]),
                    bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
         const int idx = 4 * (e * PER_FIELD + j);
-        if (tob) st4(tob + idx, v);
-        if (keep) st4(ob + idx, v);
+        if (tob) st4_stream(tob + idx, v);
+        if (keep) st4_stream(ob + idx, v);
       }
     }
   }
