@@ -45,6 +45,7 @@ struct GemmArgs {
   int M, N, K;             // problem; K multiple of 64, N multiple of BN
   int k_blocks_per_split;  // k-blocks (of 64) handled by one K-split
   int splits;              // number of K-splits (tiles = m_tiles * n_tiles * splits)
+  int ws_stages;           // weight-stationary kernel: depth of the activation ring
   void* out;               // bf16 or f32, row-major [M, ldo]
   int ldo;
   const float* bias;       // [N] or null
@@ -300,14 +301,13 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer
-      uint32_t it = 0;  // k-blocks issued so far (ring position, continues across tiles)
+      uint32_t s = 0, ph = 0;  // ring position and phase (continue across tiles; no divisions on this path)
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int split = t / tiles_per_split, r = t % tiles_per_split;
         const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
         const int kb0 = split * g.k_blocks_per_split;
         const int nkb = min(g.k_blocks_per_split, total_kb - kb0);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Smem<BN>::STAGE_BYTES;
           uint8_t* sb = sa + Smem<BN>::A_BYTES;
@@ -321,13 +321,14 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &map_b, &full_bar[s], n0 + 64 * i, (kb0 + kb) * BK);
           }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(BM, BN, MN);
-      uint32_t it = 0, lt = 0;
+      uint32_t s = 0, ph = 0, lt = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
         const int split = t / tiles_per_split;
         const int kb0 = split * g.k_blocks_per_split;
@@ -336,8 +337,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         mbar_wait(&tempty_bar[buf], bph ^ 1);  // the epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Smem<BN>::STAGE_BYTES);
@@ -349,6 +349,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_bf16(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
           umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[buf]);  // accumulator complete
       }
@@ -391,12 +392,18 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // Here one CTA per SM owns one 128-column slice of the weights, loads it ONCE (K/64 x 16 KB, stays
 // resident), and streams only the activation tiles (16 KB per k-block = 128 FLOP/B) through a 4-stage
 // ring while walking its share of the M tiles; accumulators are double-buffered in TMEM as above.
-constexpr int WS_STAGES = 4;
-constexpr int WS_MAX_KB = 8;  // K <= 512
+constexpr int WS_MAX_KB = 8;        // K <= 512
+constexpr int WS_MAX_STAGES = 12;
 struct SmemWS {
-  static constexpr int B_BYTES = WS_MAX_KB * 128 * BK * 2;       // 128 KB resident weight slice
   static constexpr int A_BYTES = BM * BK * 2;                    // 16 KB per stage
-  static constexpr int TOTAL = B_BYTES + WS_STAGES * A_BYTES + 1024 + 256 + 2048 + EPI_WARPS * 32 * 80;
+  static constexpr int KB_BYTES = 128 * BK * 2;                  // 16 KB of resident weights per k-block
+  static constexpr int TAIL = 1024 + 256 + 2048 + EPI_WARPS * 32 * 80;  // align slack, barriers, bias, staging
+  static constexpr int BUDGET = 226 * 1024;                      // dynamic shared memory per CTA (227 KB max)
+  // Depth of the activation ring. Measured at M = 131072, N = 512: K = 256 -> 74 us with 4 stages,
+  // 69 us with 9; K = 512 -> 93 us with 4 stages, 104 us with 5 (the last 16 KB of shared memory
+  // are better left to L1). So: as deep as fits below ~208 KB.
+  static int stages(int nkb) { return std::min(WS_MAX_STAGES, (208 * 1024 - TAIL - nkb * KB_BYTES) / A_BYTES); }
+  static int total(int nkb) { return nkb * KB_BYTES + stages(nkb) * A_BYTES + TAIL; }
 };
 
 template <int EPI>
@@ -406,26 +413,28 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   constexpr int BN = 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int nkb = g.K / BK;
+  const uint32_t nst = (uint32_t)g.ws_stages;   // depth of the activation ring (host: SmemWS::stages)
   uint8_t* smem_b = smem;
-  uint8_t* smem_a = smem + SmemWS::B_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_a + WS_STAGES * SmemWS::A_BYTES);
-  uint64_t* empty_bar = full_bar + WS_STAGES;
-  uint64_t* tfull_bar = empty_bar + WS_STAGES;
+  uint8_t* smem_a = smem + nkb * SmemWS::KB_BYTES;
+  uint8_t* tail = smem_a + nst * SmemWS::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + WS_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + WS_MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* b_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
-  float* bias_s = reinterpret_cast<float*>(smem_a + WS_STAGES * SmemWS::A_BYTES + 256);
-  uint8_t* stage = smem_a + WS_STAGES * SmemWS::A_BYTES + 256 + 2048 + (((threadIdx.x >> 5) + EPI_WARPS - 2) % EPI_WARPS) * STAGE_BYTES_PER_WARP;
+  float* bias_s = reinterpret_cast<float*>(tail + 256);
+  uint8_t* stage = tail + 256 + 2048 + (((threadIdx.x >> 5) + EPI_WARPS - 2) % EPI_WARPS) * STAGE_BYTES_PER_WARP;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
-  const int nkb = g.K / BK;
   // CTA c owns column slice c % n_tiles and the M tiles c / n_tiles, + gridDim.x / n_tiles, ...
   const int n0 = (blockIdx.x % n_tiles) * BN;
   const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (uint32_t s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
     mbar_init(b_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -441,15 +450,15 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer: the weight slice once, then activation tiles
-      mbar_expect_tx(b_bar, (uint32_t)nkb * 128 * BK * 2);
-      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem_b + kb * (128 * BK * 2), &map_b, b_bar, kb * BK, n0);
-      uint32_t it = 0;
+      mbar_expect_tx(b_bar, (uint32_t)nkb * SmemWS::KB_BYTES);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem_b + kb * SmemWS::KB_BYTES, &map_b, b_bar, kb * BK, n0);
+      uint32_t s = 0, ph = 0;  // ring position and phase, advanced without divisions
       for (int mt = m_first; mt < m_tiles; mt += m_step) {
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % WS_STAGES, ph = (it / WS_STAGES) & 1;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], SmemWS::A_BYTES);
           tma_load_2d(smem_a + s * SmemWS::A_BYTES, &map_a, &full_bar[s], kb * BK, mt * BM);
+          if (++s == nst) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -457,22 +466,22 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (lane == 0) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(BM, BN, false);
       mbar_wait(b_bar, 0);
-      uint32_t it = 0, lt = 0;
+      uint32_t s = 0, ph = 0, lt = 0;
       for (int mt = m_first; mt < m_tiles; mt += m_step, ++lt) {
         const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
         mbar_wait(&tempty_bar[buf], bph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % WS_STAGES, ph = (it / WS_STAGES) & 1;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint64_t adesc = make_desc_k128(smem_u32(smem_a + s * SmemWS::A_BYTES));
-          const uint64_t bdesc = make_desc_k128(smem_u32(smem_b + kb * (128 * BK * 2)));
+          const uint64_t bdesc = make_desc_k128(smem_u32(smem_b + kb * SmemWS::KB_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty_bar[s]);
+          if (++s == nst) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[buf]);
       }
@@ -538,11 +547,11 @@ static bool make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int 
 }
 
 template <int EPI>
-static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t st) {
+static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, GemmArgs g, cudaStream_t st) {
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemWS::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemWS::BUDGET);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -551,7 +560,9 @@ static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const
   }
   const int n_tiles = g.N / 128, m_tiles = (g.M + BM - 1) / BM;
   int per_slice = std::min(std::max(sms / n_tiles, 1), m_tiles);   // CTAs per column slice
-  k_gemm_ws<EPI><<<per_slice * n_tiles, THREADS, SmemWS::TOTAL, st>>>(ma, mb, g);
+  const int nkb = g.K / BK;
+  g.ws_stages = SmemWS::stages(nkb);
+  k_gemm_ws<EPI><<<per_slice * n_tiles, THREADS, SmemWS::total(nkb), st>>>(ma, mb, g);
   return cudaGetLastError();
 }
 
