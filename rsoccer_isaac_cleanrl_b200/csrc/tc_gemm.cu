@@ -582,8 +582,9 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Ge
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     max_ctas = 2 * sms;  // two resident CTAs per SM (smem and TMEM both allow exactly two)
   }
+  const int resident = BN == 256 ? max_ctas / 2 : max_ctas;  // 128x256 tiles: 144 KB smem + all 512 TMEM columns
   const long long tiles = (long long)((g.M + BM - 1) / BM) * (g.N / BN) * splits;
-  const unsigned grid = (unsigned)std::min<long long>(tiles, max_ctas);
+  const unsigned grid = (unsigned)std::min<long long>(tiles, resident);
   k_gemm_tn<BN, EPI, MN><<<grid, THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
   return cudaGetLastError();
 }
@@ -750,7 +751,13 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
   if ((epilogue == EPI_BIAS_TANH_BF16 && !bias) || (epilogue == EPI_DTANH_BF16 && !aux)) {
     g_tc_error = "vss_gemm_bf16_tn: missing bias/aux"; return VSS_E_INVALID;
   }
-  const int bn = (N % 128 == 0) ? 128 : 64;
+  // tile width: 256 (tuning knob VSS_GEMM_BN256: 1 = dgrad, 2 = dgrad + wgrad) raises the FLOP per
+  // operand byte from 64 to 85 at the price of one CTA per SM
+  static const int bn256 = getenv("VSS_GEMM_BN256") ? atoi(getenv("VSS_GEMM_BN256")) : 0;
+  int bn = (N % 128 == 0) ? 128 : 64;
+  if (N % 256 == 0 && M >= 128 * 148 && ((bn256 >= 1 && epilogue == EPI_DTANH_BF16 && !mn_major) ||
+                                        (bn256 >= 2 && epilogue == EPI_ATOMIC_F32 && mn_major)))
+    bn = 256;
   CUtensorMap ma, mb;
   const bool ok = mn_major ? (make_map(&ma, A, K, M, lda, BK) && make_map(&mb, B, K, N, ldb, BK))
                            : (make_map(&ma, A, M, K, lda, BM) && make_map(&mb, B, N, K, ldb, bn));
@@ -785,6 +792,7 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
   TC_CASE(128, EPI_ATOMIC_F32, false) TC_CASE(64, EPI_ATOMIC_F32, false)
   TC_CASE(128, EPI_BIAS_F32, false) TC_CASE(64, EPI_BIAS_F32, false)
   TC_CASE(128, EPI_ATOMIC_F32, true) TC_CASE(64, EPI_ATOMIC_F32, true)
+  TC_CASE(256, EPI_DTANH_BF16, false) TC_CASE(256, EPI_ATOMIC_F32, true)
   { g_tc_error = "vss_gemm_bf16_tn: unsupported epilogue / layout combination"; return VSS_E_INVALID; }
 #undef TC_CASE
   if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
