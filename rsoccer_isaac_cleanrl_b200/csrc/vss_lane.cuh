@@ -34,8 +34,11 @@ namespace vss {
 constexpr int LDS = 33;       // shared-memory column stride in words
 constexpr int W_PREV = 60;    // 7 words of pre-physics reward terms: ball potential, 6 robot-ball distances
 constexpr int SM_WORDS = 67;  // words per field staged in shared memory
-constexpr int QUEUE_WORDS = 48; // per-warp (field, robot) wall-task queue: 32 x 6 bytes
-constexpr int TILE_WORDS = SM_WORDS * 33 + QUEUE_WORDS;  // shared-memory words per warp
+constexpr int TILE_STATE_WORDS = SM_WORDS * LDS;  // the staged columns of one 32-field tile
+// Task queues, per warp of the CTA: 32 x 6 (field, robot) wall tasks of 2 bytes + 32 ball-wall tasks
+// of 1 byte (the per-field contact tasks, 32 x 4 bytes, reuse the same space in an earlier phase)
+constexpr int QUEUE_WORDS = 104;
+constexpr int TILE_WORDS = TILE_STATE_WORDS + QUEUE_WORDS;  // shared-memory words per warp
 constexpr int F4_PER_FIELD = VSS_OBS_PER_FIELD / 4;  // 78 float4 per (2,3,52) observation
 constexpr int F4_PER_ROW = VSS_NUM_OBS / 4;          // 13
 constexpr int RESET_MAX_ATTEMPTS = 64;
@@ -109,6 +112,15 @@ VSS_HD uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 VSS_HD float bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 #endif
 
+// Quick division / reciprocal square root for the contact code (2 ulp on the device; the physics is
+// compared with the fp64 oracle under a tolerance, unlike the rewards, which use the _rn forms above).
+#if defined(__CUDA_ARCH__)
+VSS_HD float qdiv(float a, float b) { return __fdividef(a, b); }
+VSS_HD float qrsqrt(float a) { return rsqrtf(a); }
+#else
+VSS_HD float qdiv(float a, float b) { return a / b; }
+VSS_HD float qrsqrt(float a) { return 1.0f / sqrtf(a); }
+#endif
 VSS_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 VSS_HD float sgnf(float v) { return v < 0.0f ? -1.0f : 1.0f; }
 
@@ -200,7 +212,7 @@ VSS_HD void resolve(Body& P, Body& Q, float nx, float ny, float depth, float cpx
   const float rpx = cpx - P.x, rpy = cpy - P.y, rqx = cpx - Q.x, rqy = cpy - Q.y;
   const float wsum = P.invm + Q.invm;
   if (!(wsum > 0.0f)) return;
-  const float wp = P.invm / wsum, wq = Q.invm / wsum;
+  const float iw = qdiv(1.0f, wsum), wp = P.invm * iw, wq = Q.invm * iw;
   P.x -= nx * depth * wp; P.y -= ny * depth * wp;
   Q.x += nx * depth * wq; Q.y += ny * depth * wq;
   float vrx = (Q.vx - Q.w * rqy) - (P.vx - P.w * rpy);
@@ -209,7 +221,7 @@ VSS_HD void resolve(Body& P, Body& Q, float nx, float ny, float depth, float cpx
   if (vn >= 0.0f) return;
   const float rnp = rpx * ny - rpy * nx, rnq = rqx * ny - rqy * nx;
   const float kn = wsum + rnp * rnp * P.invi + rnq * rnq * Q.invi;
-  const float jn = -e1 * vn / kn;
+  const float jn = qdiv(-e1 * vn, kn);
   P.vx -= jn * nx * P.invm; P.vy -= jn * ny * P.invm; P.w -= jn * rnp * P.invi;
   Q.vx += jn * nx * Q.invm; Q.vy += jn * ny * Q.invm; Q.w += jn * rnq * Q.invi;
   if (mu > 0.0f) {
@@ -219,7 +231,7 @@ VSS_HD void resolve(Body& P, Body& Q, float nx, float ny, float depth, float cpx
     const float vt = vrx * tx + vry * ty;
     const float rtp = rpx * ty - rpy * tx, rtq = rqx * ty - rqy * tx;
     const float kt = wsum + rtp * rtp * P.invi + rtq * rtq * Q.invi + kt_extra;
-    const float jt = clampf(-vt / kt, -mu * jn, mu * jn);
+    const float jt = clampf(qdiv(-vt, kt), -mu * jn, mu * jn);
     P.vx -= jt * tx * P.invm; P.vy -= jt * ty * P.invm; P.w -= jt * rtp * P.invi;
     Q.vx += jt * tx * Q.invm; Q.vy += jt * ty * Q.invm; Q.w += jt * rtq * Q.invi;
   }
@@ -242,8 +254,8 @@ VSS_HD Hit circle_vs_box(const Body& B, float H, float px, float py, float rho) 
     const float d2 = ex * ex + ey * ey;
     if (d2 >= rho * rho) return r;
     if (d2 > 1e-20f) {
-      const float d = sqrtf(d2);
-      nlx = ex / d; nly = ey / d; r.depth = rho - d; clx = qx; cly = qy;
+      const float id = qrsqrt(d2);
+      nlx = ex * id; nly = ey * id; r.depth = rho - d2 * id; clx = qx; cly = qy;
     } else {
       face = true;  // centre within rounding of the surface: no direction to normalise, use the face rule
     }
@@ -365,8 +377,8 @@ VSS_HD bool point_vs_walls(Body& Q, float lx, float ly, float rho, float mu, flo
         const float ex = ax - qx, ey = ay - qy;
         const float d2 = ex * ex + ey * ey;
         if (d2 < rho * rho && d2 > 1e-20f) {
-          const float d = sqrtf(d2);
-          nx = sx * ex / d; ny = sy * ey / d; depth = rho - d; hit = true;
+          const float id = qrsqrt(d2);
+          nx = sx * ex * id; ny = sy * ey * id; depth = rho - d2 * id; hit = true;
         } else if (d2 < rho * rho) {  // on the block's surface within rounding: push out along x
           nx = -sx; ny = 0.0f; depth = rho; hit = true;
         }
@@ -437,9 +449,9 @@ VSS_HD float rsqrt_fast(float x) {
 #endif
 }
 
-// Phases A-C of a substep for one field. Returns the 6-bit mask of robots that need the wall
-// phase D, which the caller runs as (field, robot) tasks spread over the lanes of the warp.
-VSS_HD uint32_t substep_pre_lane(float* S, const DevParams& P) {
+// Phases A-B of a substep for one field plus the broadphase of phase C. Returns the 21-bit
+// candidate mask: bits 0-5 ball-robot r, bits 6-20 robot pairs in lexicographic order.
+VSS_HD uint32_t substep_integrate_lane(float* S, const DevParams& P) {
   // A. wheel drive + integration
 #pragma unroll 2
   for (int r = 0; r < 6; ++r) {
@@ -491,6 +503,12 @@ VSS_HD uint32_t substep_pre_lane(float* S, const DevParams& P) {
         ++bit;
       }
   }
+  return mask;
+}
+
+// Narrow phase + impulses of the flagged pairs of one field, in fixed order. Touches only that
+// field's column, so any thread of the CTA can run it.
+VSS_HD void contacts_task(float* S, uint32_t mask, const DevParams& P) {
   uint32_t mb = mask & 63u;
   while (mb) {
     const int r = ffs32(mb) - 1;
@@ -510,19 +528,34 @@ VSS_HD uint32_t substep_pre_lane(float* S, const DevParams& P) {
                         (4ull << 36) | (5ull << 39) | (5ull << 42);
     robot_robot(S, (int)((PI >> (3 * p)) & 7), (int)((PJ >> (3 * p)) & 7), P);
   }
-  // D. which robots can touch a wall
+}
+
+// D. which robots can touch a wall (bits 0-5)
+VSS_HD uint32_t robots_near_walls_lane(const float* S, const DevParams& P) {
   uint32_t walls = 0;
 #pragma unroll
   for (int r = 0; r < 6; ++r) walls |= robot_near_walls(S, r, P) ? (1u << r) : 0u;
   return walls;
 }
+VSS_HD bool ball_near_walls(const float* S, const DevParams& P) {
+  return !(fabsf(S[0]) + P.rb <= P.HL && fabsf(S[LDS]) + P.rb <= P.HW);  // else: cannot touch any wall family
+}
+VSS_HD void ball_walls_task(float* S, const DevParams& P) {
+  Body ball = load_ball(S, P);
+  if (point_vs_walls(ball, 0.0f, 0.0f, P.rb, P.mu_bw, 2.5f * P.inv_mb, P)) store_ball(S, ball);
+}
+
+// Phases A-C of a substep for one field. Returns the 6-bit mask of robots that need the wall
+// phase D, which the caller runs as (field, robot) tasks spread over the lanes of the warp.
+VSS_HD uint32_t substep_pre_lane(float* S, const DevParams& P) {
+  const uint32_t mask = substep_integrate_lane(S, P);
+  contacts_task(S, mask, P);
+  return robots_near_walls_lane(S, P);
+}
 
 // Phase E of a substep: ball vs walls.
 VSS_HD void substep_ball_walls_lane(float* S, const DevParams& P) {
-  const float bx = fabsf(S[0]), by = fabsf(S[LDS]);
-  if (bx + P.rb <= P.HL && by + P.rb <= P.HW) return;  // cannot touch any wall family
-  Body ball = load_ball(S, P);
-  if (point_vs_walls(ball, 0.0f, 0.0f, P.rb, P.mu_bw, 2.5f * P.inv_mb, P)) store_ball(S, ball);
+  if (ball_near_walls(S, P)) ball_walls_task(S, P);
 }
 
 // ---- rewards and dones: envs/vss.py:218-265, 578-655 -----------------------------------

@@ -26,13 +26,25 @@ namespace vss {
 __constant__ ObsTable c_obs_table = make_obs_table();
 
 constexpr int TAB_WORDS = 80;  // 78 table entries, padded
-// Physics of one tile (replaces gym.simulate): per substep, phases A-C per lane, then the robot-wall
-// contacts as (field, robot) tasks compacted over the warp — any lane can work on any field of the
-// tile because the state columns live in shared memory — then the ball-wall phase per lane.
+constexpr int CTR_WORDS = 4;   // task counters of the CTA-wide queues
+
+// Shared-memory layout of a CTA of W warps (words):
+//   [0, TAB_WORDS)                     observation permutation/sign table
+//   + W * TILE_STATE_WORDS             the staged state columns, one 32-field tile per warp
+//   + W * QUEUE_WORDS                  task queues
+//   + CTR_WORDS                        task counters
+__host__ __device__ constexpr size_t smem_words(int wpb) {
+  return TAB_WORDS + (size_t)wpb * TILE_WORDS + CTR_WORDS;
+}
+
+// Physics of one tile (replaces gym.simulate), warp-local version: per substep, phases A-C per lane,
+// then the robot-wall contacts as (field, robot) tasks compacted over the warp — any lane can work
+// on any field of the tile because the state columns live in shared memory — then the ball-wall
+// phase per lane.
 template <bool SYNC>
-__device__ __forceinline__ void physics_tile(float* T, int lane, bool active, const DevParams& P, int sync_level) {
+__device__ __forceinline__ void physics_tile(float* T, uint8_t* queue, int lane, bool active, const DevParams& P,
+                                             int sync_level) {
   float* S = T + lane;
-  uint8_t* queue = reinterpret_cast<uint8_t*>(T + SM_WORDS * LDS);
 #pragma unroll 1
   for (int it = 0; it < P.substeps; ++it) {
     // keep the warps of a CTA in the same code region: the kernel is instruction-fetch bound
@@ -64,6 +76,92 @@ __device__ __forceinline__ void physics_tile(float* T, int lane, bool active, co
   }
 }
 
+// CTA-wide version. Contacts are rare per field (a few per cent of the fields per substep) but
+// almost certain per 32-field warp, so with one lane per field the contact code runs at 2-4
+// active lanes and takes 40 % of the issue slots. Here every phase that diverges is turned into
+// tasks that the whole CTA compacts into one queue; thread t runs task t, so the contact code
+// executes on one or two dense warps instead of on all of them. Tasks of one phase touch disjoint
+// state (different fields, or different bodies of a field), so the result does not depend on
+// which thread runs them; barriers separate the phases.
+//   queue (bytes, per CTA of W warps): contact tasks u32 [0, 128 W)  (field << 21 | pair mask);
+//   robot-wall tasks u16 [0, 384 W)  (field << 3 | robot);  ball-wall tasks u8 [384 W, 416 W).
+__device__ __forceinline__ float* field_column(float* tiles, int f) {
+  return tiles + (f >> 5) * TILE_STATE_WORDS + (f & 31);
+}
+__device__ __forceinline__ void physics_cta(float* tiles, uint32_t* queue, uint32_t* ctr, bool active,
+                                            const DevParams& P) {
+  const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31;
+  float* S = field_column(tiles, tid);
+  uint16_t* qrobot = reinterpret_cast<uint16_t*>(queue);
+  uint8_t* qball = reinterpret_cast<uint8_t*>(queue) + 12 * nthreads;
+  const uint32_t lt = (1u << lane) - 1u;
+  if (tid == 0) { ctr[0] = 0; ctr[1] = 0; ctr[2] = 0; }
+  __syncthreads();
+#pragma unroll 1
+  for (int it = 0; it < P.substeps; ++it) {
+    if (tid == 0) { ctr[1] = 0; ctr[2] = 0; }  // (their readers are behind the barrier that ended the last substep)
+    // A-B + broadphase, one lane per field
+    const uint32_t m = active ? substep_integrate_lane(S, P) : 0u;
+    {
+      const uint32_t has = __ballot_sync(0xffffffffu, m != 0u);
+      uint32_t base = 0;
+      if (lane == 0 && has) base = atomicAdd(&ctr[0], (uint32_t)__popc(has));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (m) queue[base + __popc(has & lt)] = ((uint32_t)tid << 21) | m;
+    }
+    __syncthreads();
+    // C. narrow phase + impulses, one thread per field that has candidates
+    {
+      const int n = (int)ctr[0];
+      for (int t = tid; t < n; t += nthreads) {
+        const uint32_t q = queue[t];
+        contacts_task(field_column(tiles, (int)(q >> 21)), q & 0x1fffffu, P);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) ctr[0] = 0;
+    // D-E. wall candidates, one lane per field
+    {
+      uint32_t w = active ? robots_near_walls_lane(S, P) : 0u;
+      const bool bw = active && ball_near_walls(S, P);
+      const int cnt = __popc(w);
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const uint32_t hasb = __ballot_sync(0xffffffffu, bw);
+      uint32_t base = 0, baseb = 0;
+      if (lane == 0) {
+        if (total) base = atomicAdd(&ctr[1], (uint32_t)total);
+        if (hasb) baseb = atomicAdd(&ctr[2], (uint32_t)__popc(hasb));
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      baseb = __shfl_sync(0xffffffffu, baseb, 0);
+      int pos = (int)base + incl - cnt;
+      while (w) {
+        const int r = __ffs((int)w) - 1;
+        w &= w - 1;
+        qrobot[pos++] = (uint16_t)((tid << 3) | r);
+      }
+      if (bw) qball[baseb + __popc(hasb & lt)] = (uint8_t)tid;
+    }
+    __syncthreads();
+    {
+      const int nr = (int)ctr[1], nb = (int)ctr[2];
+      for (int t = tid; t < nr; t += nthreads) {  // robot tasks from the first warps up ...
+        const int q = qrobot[t];
+        robot_walls_task(field_column(tiles, q >> 3), q & 7, P);
+      }
+      for (int t = nthreads - 1 - tid; t < nb; t += nthreads)  // ... ball tasks from the last warps down
+        ball_walls_task(field_column(tiles, (int)qball[t]), P);
+    }
+    __syncthreads();
+  }
+}
+
 template <int VIEW, bool INJECT, bool SYNC>
 __global__ void __launch_bounds__(384)
 k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) {
@@ -75,7 +173,10 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long env0 = tile * 32;
   if (!SYNC && env0 >= a.n) return;  // (with block-level syncs every warp must stay until the end)
-  float* T = smem + TAB_WORDS + warp * TILE_WORDS;
+  float* tiles = smem + TAB_WORDS;
+  float* T = tiles + warp * TILE_STATE_WORDS;
+  uint32_t* queue = reinterpret_cast<uint32_t*>(tiles + (blockDim.x >> 5) * TILE_STATE_WORDS);
+  uint32_t* ctr = queue + (blockDim.x >> 5) * QUEUE_WORDS;
   float* S = T + lane;
   const long long env = env0 + lane;
   const bool active = env < a.n;
@@ -85,7 +186,8 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   // 1. per lane: load, actions, physics, rewards, dones
   if (active) lane_phase1a<VIEW>(S, env, a, P, key);
   if (INJECT) { if (active) lane_inject(S, env, a); }
-  else physics_tile<SYNC>(T, lane, active, P, a.sync_level);
+  else if (SYNC && a.sync_level >= 4) physics_cta(tiles, queue, ctr, active, P);
+  else physics_tile<SYNC>(T, reinterpret_cast<uint8_t*>(queue + warp * QUEUE_WORDS), lane, active, P, a.sync_level);
   if (SYNC) __syncthreads();
   int code = LANE_RUNNING;
   if (active) code = lane_phase1d<VIEW>(S, env, a, P, key);
@@ -124,7 +226,7 @@ k_reset_dones(float* state, long long n, long long ld, unsigned long long goff, 
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long env0 = tile * 32;
   if (env0 >= n) return;
-  float* T = smem + TAB_WORDS + warp * TILE_WORDS;
+  float* T = smem + TAB_WORDS + warp * TILE_STATE_WORDS;
   float* S = T + lane;
   const long long env = env0 + lane;
   const bool active = env < n;
@@ -237,9 +339,10 @@ static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* s
   if (forced_wpb >= 1 && forced_wpb <= 12) wpb = forced_wpb;
   if (forced_sync >= 0) sync = forced_sync;
   if (wpb == 1) sync = 0;
+  if (sync >= 4 && wpb > 8) sync = 2;  // the CTA-wide task queues index fields with 8 bits
   *warps_per_block = wpb;
   *grid = (unsigned)((tiles + wpb - 1) / wpb);
-  *smem = sizeof(float) * (TAB_WORDS + (size_t)wpb * TILE_WORDS);
+  *smem = sizeof(float) * smem_words(wpb);
   if (sync_level) *sync_level = sync;
   return 0;
 }
