@@ -231,6 +231,46 @@ VSS_API int vss_head_forward(const void* h, int ldh, const float* W, const float
 VSS_API int vss_head_backward(const float* dout, const void* h, int ldh, const float* W, void* dz, int ldz,
                               float* dW, float* db, int M, int n_out, void* stream);
 
+/* ---- the small pieces of the PPO loop, one launch each (ppo_continuous_action_isaacgym.py) ------
+ * Normal(mean, exp(logstd)).sample() and .log_prob(action).sum(1) of Agent.get_action_and_value
+ * (ppo...:155-164). mean/action (M,A) f32, logstd (A), logprob (M); A in {2,6}. Normals come from
+ * Philox4x32-10 keyed by (seed, *counter, row); `counter` is a device word that the call advances
+ * (stream-ordered, so CUDA-graph replays draw fresh noise). */
+VSS_API int vss_policy_sample(const float* mean, const float* logstd, int64_t M, int A, uint64_t seed,
+                              uint32_t* counter, float* action, float* logprob, void* stream);
+/* One PPO minibatch loss and its gradient w.r.t. the network outputs (ppo...:314-352):
+ *   j = inds[i] (or i when inds is NULL) gathers the rollout arrays b_* (flattened (T*N,...) f32);
+ *   mean (B,A) / value (B) are the fresh network outputs for those rows; logstd (A).
+ *   ratio, approx-KL, clip fraction, advantage normalisation (mean / unbiased std + 1e-8) when
+ *   norm_adv, clipped surrogate, value loss (clipped when clip_vloss; b_val may be NULL otherwise),
+ *   entropy bonus; loss = pg - ent_coef * entropy + vf_coef * v_loss.
+ * Outputs: d_mean (B,A), d_value (B) = d loss / d output; d_logstd (A) is ACCUMULATED (caller
+ * zeroes); stats[8] = {pg_loss, v_loss, entropy, old_approx_kl, approx_kl, clipfrac, loss, 0};
+ * scratch = 2 doubles of device workspace. */
+VSS_API int vss_ppo_loss(const float* mean, const float* value, const float* logstd, const float* b_action,
+                         const float* b_logprob, const float* b_adv, const float* b_ret, const float* b_val,
+                         const int64_t* inds, int64_t B, int A, float clip_coef, float ent_coef, float vf_coef,
+                         int norm_adv, int clip_vloss, float* d_mean, float* d_value, float* d_logstd, float* stats,
+                         double* scratch, void* stream);
+/* bf16 copies of fp32 matrices in one launch: dst[r, c] = src[r, c], or dst[c, r] = src[r, c] when
+ * transpose; src (rows, cols) contiguous, dst row stride ld_dst elements (K padding of the first
+ * layer: the caller zeroes the pad columns once). Up to VSS_MAX_CONVERT_JOBS matrices per call. */
+#define VSS_MAX_CONVERT_JOBS 8
+typedef struct vss_convert_job {
+  const float* src;
+  void* dst;
+  int32_t rows, cols, ld_dst, transpose;
+} vss_convert_job;
+VSS_API int vss_convert_bf16_batch(const vss_convert_job* jobs, int njobs, void* stream);
+/* nn.utils.clip_grad_norm_(max_grad_norm) + Adam.step() (torch semantics, no weight decay) on flat
+ * buffers of n f32 (ppo...:353-354). The gradient is first scaled by grad_scale (1 / world size after
+ * a sum all-reduce). state (device, 3 f32) = {step count, learning rate, 0}; the call increments the
+ * step count on the device, so it can be replayed from a CUDA graph. grads holds the clipped
+ * gradient afterwards. */
+VSS_API int vss_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
+                          float grad_scale, float max_grad_norm, float beta1, float beta2, float eps, void* stream);
+VSS_API const char* vss_ppo_last_error(void);
+
 /* Philox4x32-10 known-answer hook (host side; same code as the device generator). */
 VSS_API void vss_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

@@ -42,6 +42,15 @@ class VssParams(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ConvertJob(C.Structure):
+    """`vss_convert_job` of include/vss_b200.h."""
+
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("ld_dst", C.c_int32), ("transpose", C.c_int32)]
+
+
+MAX_CONVERT_JOBS = 8
+
 # every symbol include/vss_b200.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
 _SYMBOLS = {
@@ -67,6 +76,13 @@ _SYMBOLS = {
     "vss_head_backward": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP, C.c_int, C.c_int, _VP]),
     "vss_colsum_bf16": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_gather_pad_bf16": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
+    "vss_policy_sample": (C.c_int, [_VP, _VP, C.c_int64, C.c_int, C.c_uint64, _VP, _VP, _VP, _VP]),
+    "vss_ppo_loss": (C.c_int, [_VP] * 9 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int] +
+                     [_VP] * 6),
+    "vss_convert_bf16_batch": (C.c_int, [C.POINTER(ConvertJob), C.c_int, _VP]),
+    "vss_clip_adam": (C.c_int, [_VP] * 4 + [C.c_int64, _VP, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                            _VP]),
+    "vss_ppo_last_error": (C.c_char_p, []),
     "vss_philox4x32_10": (None, [_VP, _VP, _VP]),
     "vss_last_error": (C.c_char_p, []),
     "vss_version": (C.c_char_p, []),

@@ -23,7 +23,7 @@
 
 #if defined(__CUDACC__)
 #define VSS_HD __host__ __device__ __forceinline__
-#define VSS_HD_COLD __host__ __device__ __noinline__  // rare paths kept out of the hot instruction stream
+#define VSS_HD_COLD inline __host__ __device__ __noinline__  // rare paths kept out of the hot instruction stream
 #else
 #define VSS_HD inline
 #define VSS_HD_COLD inline

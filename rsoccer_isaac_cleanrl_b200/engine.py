@@ -191,12 +191,14 @@ def gather_pad_bf16(src, idx, ncol_pad):
     return dst
 
 
-def head_forward(h, W, b):
+def head_forward(h, W, b, out=None):
     """out [M,n_out] f32 = h [M,256] bf16 @ W[n_out,256].T + b (CUDA-core kernel, one warp per row)."""
     lib = _lib.load_library()
     M, n_out = h.shape[0], W.shape[0]
     assert h.dtype == torch.bfloat16 and h.shape[1] == 256 and h.stride(1) == 1 and W.shape[1] == 256
-    out = torch.empty((M, n_out), device=h.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((M, n_out), device=h.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == M * n_out
     rc = lib.vss_head_forward(h.data_ptr(), h.stride(0), W.contiguous().data_ptr(), b.contiguous().data_ptr(),
                               out.data_ptr(), M, n_out, torch.cuda.current_stream(h.device).cuda_stream)
     if rc != 0:
@@ -204,16 +206,96 @@ def head_forward(h, W, b):
     return out
 
 
-def head_backward(dout, h, W):
-    """(dz [M,256] bf16, dW [n_out,256] f32, db [n_out] f32) of the head, tanh' of h fused into dz."""
+def head_backward(dout, h, W, dW=None, db=None):
+    """(dz [M,256] bf16, dW [n_out,256] f32, db [n_out] f32) of the head, tanh' of h fused into dz.
+    dW / db, when given, are accumulated into (contiguous f32 buffers such as the .grad views)."""
     lib = _lib.load_library()
     M, n_out = dout.shape
     dout = dout.contiguous()
     dz = torch.empty((M, 256), device=h.device, dtype=torch.bfloat16)
-    dW = torch.zeros((n_out, 256), device=h.device, dtype=torch.float32)
-    db = torch.zeros(n_out, device=h.device, dtype=torch.float32)
+    if dW is None:
+        dW = torch.zeros((n_out, 256), device=h.device, dtype=torch.float32)
+    if db is None:
+        db = torch.zeros(n_out, device=h.device, dtype=torch.float32)
+    assert dW.is_contiguous() and db.is_contiguous() and dW.numel() == n_out * 256 and db.numel() == n_out
     rc = lib.vss_head_backward(dout.data_ptr(), h.data_ptr(), h.stride(0), W.contiguous().data_ptr(), dz.data_ptr(), 256,
                                dW.data_ptr(), db.data_ptr(), M, n_out, torch.cuda.current_stream(h.device).cuda_stream)
     if rc != 0:
         raise RuntimeError(lib.vss_gemm_last_error().decode())
     return dz, dW, db
+
+
+def _ppo_check(lib, rc):
+    if rc != 0:
+        raise RuntimeError(lib.vss_ppo_last_error().decode())
+
+
+def policy_sample(mean, logstd, seed, counter, action=None, logprob=None):
+    """action = mean + exp(logstd) * N(0,1), logprob = Normal.log_prob(action).sum(1) in one launch
+    (Agent.get_action_and_value without a given action, ppo…:155-164). `counter` is a device uint32
+    word (int32 tensor of one element) advanced by the call."""
+    lib = _lib.load_library()
+    M, A = mean.shape
+    assert mean.dtype == torch.float32 and mean.is_contiguous() and logstd.numel() == A and logstd.is_contiguous()
+    assert counter.dtype == torch.int32 and counter.numel() == 1
+    if action is None:
+        action = torch.empty_like(mean)
+    if logprob is None:
+        logprob = torch.empty(M, device=mean.device, dtype=torch.float32)
+    assert action.is_contiguous() and logprob.is_contiguous() and action.numel() == M * A and logprob.numel() == M
+    _ppo_check(lib, lib.vss_policy_sample(mean.data_ptr(), logstd.data_ptr(), M, A, int(seed) & (2**64 - 1),
+                                          counter.data_ptr(), action.data_ptr(), logprob.data_ptr(),
+                                          torch.cuda.current_stream(mean.device).cuda_stream))
+    return action, logprob
+
+
+PPO_STATS = ("pg_loss", "v_loss", "entropy", "old_approx_kl", "approx_kl", "clipfrac", "loss")
+
+
+def ppo_loss(mean, value, logstd, b_action, b_logprob, b_adv, b_ret, b_val, inds, clip_coef, ent_coef, vf_coef,
+             norm_adv, clip_vloss, d_logstd, d_mean=None, d_value=None, stats=None, scratch=None):
+    """One PPO minibatch loss and its gradients w.r.t. the network outputs (ppo…:314-352) in two
+    launches. Returns (d_mean, d_value, stats[8]); d_logstd is accumulated in place."""
+    lib = _lib.load_library()
+    B, A = mean.shape
+    dev = mean.device
+    for t in (mean, value, logstd, b_action, b_logprob, b_adv, b_ret, d_logstd):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert value.numel() == B and d_logstd.numel() == A and (inds is None or (inds.dtype == torch.long and inds.numel() == B))
+    d_mean = torch.empty_like(mean) if d_mean is None else d_mean
+    d_value = torch.empty((B, 1), device=dev, dtype=torch.float32) if d_value is None else d_value
+    stats = torch.empty(8, device=dev, dtype=torch.float32) if stats is None else stats
+    scratch = torch.empty(2, device=dev, dtype=torch.float64) if scratch is None else scratch
+    _ppo_check(lib, lib.vss_ppo_loss(
+        mean.data_ptr(), value.data_ptr(), logstd.data_ptr(), b_action.data_ptr(), b_logprob.data_ptr(),
+        b_adv.data_ptr(), b_ret.data_ptr(), None if b_val is None else b_val.data_ptr(),
+        None if inds is None else inds.data_ptr(), B, A, float(clip_coef), float(ent_coef), float(vf_coef),
+        int(bool(norm_adv)), int(bool(clip_vloss)), d_mean.data_ptr(), d_value.data_ptr(), d_logstd.data_ptr(),
+        stats.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return d_mean, d_value, stats
+
+
+def convert_bf16_batch(jobs):
+    """jobs: list of (src f32 [R,C] contiguous, dst bf16 2-D with unit column stride, transpose)."""
+    lib = _lib.load_library()
+    for start in range(0, len(jobs), _lib.MAX_CONVERT_JOBS):
+        chunk = jobs[start:start + _lib.MAX_CONVERT_JOBS]
+        arr = (_lib.ConvertJob * len(chunk))()
+        for k, (src, dst, tr) in enumerate(chunk):
+            assert src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 2
+            assert dst.dtype == torch.bfloat16 and dst.stride(1) == 1
+            R, Cc = src.shape
+            assert dst.shape[0] >= (Cc if tr else R) and dst.shape[1] >= (R if tr else Cc)
+            arr[k] = _lib.ConvertJob(src.data_ptr(), dst.data_ptr(), R, Cc, dst.stride(0), int(bool(tr)))
+        _ppo_check(lib, lib.vss_convert_bf16_batch(arr, len(chunk), torch.cuda.current_stream(chunk[0][0].device).cuda_stream))
+
+
+def clip_adam(params, grads, exp_avg, exp_avg_sq, state, grad_scale, max_grad_norm, beta1, beta2, eps):
+    """clip_grad_norm_ + Adam.step() on flat f32 buffers (ppo…:353-354); state = device [t, lr, 0]."""
+    lib = _lib.load_library()
+    for t in (params, grads, exp_avg, exp_avg_sq, state):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    _ppo_check(lib, lib.vss_clip_adam(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                      params.numel(), state.data_ptr(), float(grad_scale), float(max_grad_norm),
+                                      float(beta1), float(beta2), float(eps),
+                                      torch.cuda.current_stream(params.device).cuda_stream))

@@ -161,8 +161,9 @@ class FlatAdam:
     def __init__(self, flat, flat_grad, lr, eps=1e-5, betas=(0.9, 0.999)):
         self.flat, self.grad, self.eps, self.b1, self.b2 = flat, flat_grad, eps, betas[0], betas[1]
         self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
-        self.t = torch.zeros((), device=flat.device, dtype=torch.float32)
-        self.lr_t = torch.full((), lr, device=flat.device, dtype=torch.float32)
+        self.state = torch.zeros(3, device=flat.device, dtype=torch.float32)  # [step count, lr, scratch]
+        self.t, self.lr_t = self.state[0], self.state[1]
+        self.lr_t.fill_(lr)
         self.param_groups = [{"lr": lr}]
         self._lr_host = lr
 
@@ -182,6 +183,13 @@ class FlatAdam:
         bc2 = 1 - torch.pow(self.b2, self.t)
         denom = (self.v.sqrt() / bc2.sqrt()).add_(self.eps)
         self.flat.sub_((self.m / denom) * (self.lr_t / bc1))
+
+    def clip_and_step_fused(self, max_grad_norm, grad_scale=1.0):
+        """clip_grad_norm_(max_grad_norm) on grad * grad_scale, then step(): three launches
+        (`vss_clip_adam`) instead of ~25."""
+        from .engine import clip_adam
+        clip_adam(self.flat, self.grad, self.m, self.v, self.state, grad_scale, max_grad_norm, self.b1, self.b2,
+                  self.eps)
 
 
 def train(args, log=print, hook=None):
@@ -221,9 +229,42 @@ def train(args, log=print, hook=None):
     advantages, returns = z(T, N), z(T, N)
     term_obs_all = z(T, N, *oshape)
 
+    fused = backend == "tc"
+    if fused:
+        from .engine import gather_pad_bf16, policy_sample, ppo_loss
+        from .tc_mlp import MlpWeights, backward_explicit, forward_explicit
+        mw_actor, mw_critic = MlpWeights(agent.actor_mean), MlpWeights(agent.critic)
+        sample_ctr = torch.zeros(1, device=device, dtype=torch.int32)
+        sample_seed = args.seed + 7919 * (rank + 1)
+        logstd_flat = agent.actor_logstd.detach().view(-1)
+        k0 = mw_actor.k0
+
+    def rollout_fused(first_obs):
+        """rollout() with every per-step piece as one launch: pad/convert the observation once for
+        both networks, 2 x (4 tcgen05 GEMMs + head), the sampling kernel writing action and log-prob
+        into the rollout slabs, the critic head writing values[step], the env step."""
+        with torch.no_grad():
+            obs_all[0] = first_obs
+            mw_actor.refresh(); mw_critic.refresh()
+            for step in range(T):
+                x16 = gather_pad_bf16(obs_all[step], None, k0)
+                mean, _ = forward_explicit(mw_actor, x16)
+                forward_explicit(mw_critic, x16, out=values[step])
+                policy_sample(mean, logstd_flat, sample_seed, sample_ctr, action=actions[step], logprob=logprobs[step])
+                _, _, next_done, info = envs.step(actions[step], obs_out=obs_all[step + 1],
+                                                  term_obs_out=term_obs_all[step], reward_out=rewards[step])
+                next_dones[step] = next_done
+                next_timeouts[step] = info["time_outs"]
+            forward_explicit(mw_critic, gather_pad_bf16(term_obs_all.view(T * N, -1), None, k0), out=next_values)
+            gae_kernel(rewards, values, next_values, next_dones, next_timeouts, args.gamma, args.gae_lambda,
+                       advantages, returns)
+        return obs_all[T]
+
     def rollout(first_obs):
         """T env steps + V(terminal obs) + GAE (ppo…:256-296). No host sync anywhere, so the whole
         thing can be captured in a CUDA graph."""
+        if fused:
+            return rollout_fused(first_obs)
         with torch.no_grad():
             obs_all[0] = first_obs
             for step in range(T):
@@ -249,13 +290,33 @@ def train(args, log=print, hook=None):
     b_advantages, b_returns, b_values = advantages.reshape(-1), returns.reshape(-1), values.reshape(-1)
     mb_inds = torch.zeros(args.minibatch_size, dtype=torch.long, device=device)
     clipfrac_sum = torch.zeros((), device=device)
-    mb_stats = {k: torch.zeros((), device=device) for k in
-                ("v_loss", "pg_loss", "entropy", "old_approx_kl", "approx_kl")}
+    stats_buf = torch.zeros(8, device=device)  # vss_ppo_loss: pg_loss v_loss entropy old_kl kl clipfrac loss
+    loss_scratch = torch.zeros(2, device=device, dtype=torch.float64)
+    mb_stats = {"pg_loss": stats_buf[0], "v_loss": stats_buf[1], "entropy": stats_buf[2],
+                "old_approx_kl": stats_buf[3], "approx_kl": stats_buf[4]}
+
+    def forward_backward_fused():
+        """forward_backward() without autograd: gather+pad once, both MLPs forward, ONE loss kernel
+        that also produces d loss / d (mean, value, logstd), explicit backward into flat_grad."""
+        x16 = gather_pad_bf16(b_obs, mb_inds, k0)
+        mw_actor.refresh(); mw_critic.refresh()
+        mean, hs_a = forward_explicit(mw_actor, x16)
+        value, hs_c = forward_explicit(mw_critic, x16)
+        flat_grad.zero_()
+        d_mean, d_value, _ = ppo_loss(mean, value, logstd_flat, b_actions, b_logprobs, b_advantages, b_returns,
+                                      b_values, mb_inds, args.clip_coef, args.ent_coef, args.vf_coef, args.norm_adv,
+                                      args.clip_vloss, agent.actor_logstd.grad.view(-1), stats=stats_buf,
+                                      scratch=loss_scratch)
+        clipfrac_sum.add_(stats_buf[5])
+        backward_explicit(mw_actor, hs_a, d_mean)
+        backward_explicit(mw_critic, hs_c, d_value)
 
     def forward_backward():
         """One minibatch: clipped-surrogate loss and its gradient into flat_grad (ppo…:314-352).
         Reads the static index buffer mb_inds; no host sync (the reference's `.item()` at :322 is
         replaced by device-side accumulation), so it can be replayed as a CUDA graph."""
+        if fused:
+            return forward_backward_fused()
         _, newlogprob, entropy, newvalue = agent.get_action_and_value(b_obs[mb_inds], b_actions[mb_inds])
         logratio = newlogprob - b_logprobs[mb_inds]
         ratio = logratio.exp()
@@ -285,6 +346,8 @@ def train(args, log=print, hook=None):
     def clip_and_step():
         """nn.utils.clip_grad_norm_ + Adam on the flat buffer (ppo…:353-354); flat_grad holds the SUM
         over ranks at this point."""
+        if fused:
+            return optimizer.clip_and_step_fused(args.max_grad_norm, 1.0 / world)
         if world > 1:
             flat_grad.div_(world)
         gnorm = torch.linalg.vector_norm(flat_grad)

@@ -12,8 +12,8 @@ gradients (column sums) and the pad/convert of the observations are small CUDA-c
 """
 import torch
 
-from .engine import (EPI_ATOMIC_F32, EPI_BIAS_TANH_BF16, EPI_DTANH_BF16, colsum_bf16, gather_pad_bf16, gemm_bf16,
-                     head_backward, head_forward)
+from .engine import (EPI_ATOMIC_F32, EPI_BIAS_TANH_BF16, EPI_DTANH_BF16, colsum_bf16, convert_bf16_batch,
+                     gather_pad_bf16, gemm_bf16, head_backward, head_forward)
 
 _SM_TARGET = 296  # ~2 CTAs' worth of split-K work per SM for the wgrad grids
 
@@ -76,3 +76,61 @@ def mlp_params(seq):
 
 def mlp_forward(seq, x):
     return TCMlp.apply(x, *mlp_params(seq))
+
+
+# ---- explicit (autograd-free) training path used by ppo.train -------------------------------
+class MlpWeights:
+    """bf16 operand copies of one MLP's fp32 master weights: W_l (K-padded for the first layer) for
+    the forward GEMMs and W_l^T for the dgrad GEMMs. `refresh()` rewrites all seven in ONE launch;
+    the PPO loop calls it once per rollout and once per minibatch instead of converting per call."""
+
+    def __init__(self, seq):
+        self.seq = seq
+        self.ws = [seq[i].weight for i in (0, 2, 4, 6)]
+        self.bs = [seq[i].bias for i in (0, 2, 4, 6)]
+        self.head_w, self.head_b = seq[8].weight, seq[8].bias
+        dev = self.ws[0].device
+        self.n_in = self.ws[0].shape[1]
+        self.k0 = (self.n_in + 63) // 64 * 64
+        bf = torch.bfloat16
+        self.w16 = [torch.zeros((self.ws[0].shape[0], self.k0), device=dev, dtype=bf)]
+        self.w16 += [torch.empty(tuple(w.shape), device=dev, dtype=bf) for w in self.ws[1:]]
+        self.wt16 = [None] + [torch.empty((w.shape[1], w.shape[0]), device=dev, dtype=bf) for w in self.ws[1:]]
+        self.dw0 = torch.zeros((self.ws[0].shape[0], self.k0), device=dev, dtype=torch.float32)
+        self.refresh()
+
+    def refresh(self):
+        jobs = [(w.detach(), w16, False) for w, w16 in zip(self.ws, self.w16)]
+        jobs += [(w.detach(), wt, True) for w, wt in zip(self.ws[1:], self.wt16[1:])]
+        convert_bf16_batch(jobs)
+
+
+def forward_explicit(mw, x16, out=None):
+    """(out [M,n_out] f32, activations) for x16 [M,k0] bf16 (already gathered / padded)."""
+    hs = [x16]
+    for l in range(4):
+        h = torch.empty((x16.shape[0], mw.w16[l].shape[0]), device=x16.device, dtype=torch.bfloat16)
+        gemm_bf16(hs[-1], mw.w16[l], h, EPI_BIAS_TANH_BF16, bias=mw.bs[l])
+        hs.append(h)
+    return head_forward(hs[4], mw.head_w, mw.head_b, out=out), hs
+
+
+def backward_explicit(mw, hs, dout):
+    """Accumulates d loss / d parameters into the parameters' .grad buffers (contiguous f32, e.g.
+    views of the flat gradient) given dout = d loss / d out. Same kernels as TCMlp.backward, but the
+    split-K wgrad atomics, the column sums and the head kernel write straight into .grad."""
+    M = dout.shape[0]
+    dz = head_backward(dout, hs[4], mw.head_w, dW=mw.head_w.grad, db=mw.head_b.grad)[0]
+    for l in (3, 2, 1, 0):
+        n_out, k_in = dz.shape[1], hs[l].shape[1]
+        if l == 0:
+            mw.dw0.zero_()
+            gemm_bf16(dz, hs[0], mw.dw0, EPI_ATOMIC_F32, splits=_splits(n_out, k_in, M), mn_major=True)
+            mw.ws[0].grad.add_(mw.dw0[:, :mw.n_in])
+        else:
+            gemm_bf16(dz, hs[l], mw.ws[l].grad, EPI_ATOMIC_F32, splits=_splits(n_out, k_in, M), mn_major=True)
+        colsum_bf16(dz, out=mw.bs[l].grad)
+        if l > 0:
+            dz_prev = torch.empty((M, k_in), device=dz.device, dtype=torch.bfloat16)
+            gemm_bf16(dz, mw.wt16[l], dz_prev, EPI_DTANH_BF16, aux=hs[l])
+            dz = dz_prev
