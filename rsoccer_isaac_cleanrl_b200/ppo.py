@@ -238,6 +238,22 @@ def train(args, log=print, hook=None):
         sample_seed = args.seed + 7919 * (rank + 1)
         logstd_flat = agent.actor_logstd.detach().view(-1)
         k0 = mw_actor.k0
+        # the critic runs beside the actor on a second stream (fork/join inside the captured graphs): at
+        # 4096 rows one network's GEMMs fill less than half of the SMs
+        side = torch.cuda.Stream(device=device) if os.environ.get("VSS_PPO_TWO_STREAMS", "1") != "0" else None
+
+    def on_side(fn):
+        """Run fn() on the side stream, ordered after everything queued so far on the current one.
+        The caller joins with `join_side()` before the tensors fn touched are released or read."""
+        if side is None:
+            return fn()
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            return fn()
+
+    def join_side():
+        if side is not None:
+            torch.cuda.current_stream(device).wait_stream(side)
 
     def rollout_fused(first_obs):
         """rollout() with every per-step piece as one launch: pad/convert the observation once for
@@ -248,13 +264,15 @@ def train(args, log=print, hook=None):
             mw_actor.refresh(); mw_critic.refresh()
             for step in range(T):
                 x16 = gather_pad_bf16(obs_all[step], None, k0)
+                critic_out = on_side(lambda: forward_explicit(mw_critic, x16, out=values[step]))
                 mean, _ = forward_explicit(mw_actor, x16)
-                forward_explicit(mw_critic, x16, out=values[step])
                 policy_sample(mean, logstd_flat, sample_seed, sample_ctr, action=actions[step], logprob=logprobs[step])
                 _, _, next_done, info = envs.step(actions[step], obs_out=obs_all[step + 1],
                                                   term_obs_out=term_obs_all[step], reward_out=rewards[step])
                 next_dones[step] = next_done
                 next_timeouts[step] = info["time_outs"]
+                join_side()
+                del critic_out
             forward_explicit(mw_critic, gather_pad_bf16(term_obs_all.view(T * N, -1), None, k0), out=next_values)
             gae_kernel(rewards, values, next_values, next_dones, next_timeouts, args.gamma, args.gae_lambda,
                        advantages, returns)
@@ -300,16 +318,18 @@ def train(args, log=print, hook=None):
         that also produces d loss / d (mean, value, logstd), explicit backward into flat_grad."""
         x16 = gather_pad_bf16(b_obs, mb_inds, k0)
         mw_actor.refresh(); mw_critic.refresh()
-        mean, hs_a = forward_explicit(mw_actor, x16)
-        value, hs_c = forward_explicit(mw_critic, x16)
         flat_grad.zero_()
+        value, hs_c = on_side(lambda: forward_explicit(mw_critic, x16))
+        mean, hs_a = forward_explicit(mw_actor, x16)
+        join_side()
         d_mean, d_value, _ = ppo_loss(mean, value, logstd_flat, b_actions, b_logprobs, b_advantages, b_returns,
                                       b_values, mb_inds, args.clip_coef, args.ent_coef, args.vf_coef, args.norm_adv,
                                       args.clip_vloss, agent.actor_logstd.grad.view(-1), stats=stats_buf,
                                       scratch=loss_scratch)
         clipfrac_sum.add_(stats_buf[5])
+        on_side(lambda: backward_explicit(mw_critic, hs_c, d_value))
         backward_explicit(mw_actor, hs_a, d_mean)
-        backward_explicit(mw_critic, hs_c, d_value)
+        join_side()
 
     def forward_backward():
         """One minibatch: clipped-surrogate loss and its gradient into flat_grad (ppo…:314-352).
