@@ -47,7 +47,7 @@ for (n_out, k_in) in [(256, 64), (512, 256), (512, 512), (256, 512)]:   # wgrad:
     x = torch.randn(M, k_in, device=dev).to(torch.bfloat16)
     dw = torch.zeros(n_out, k_in, device=dev)
     tiles = (n_out // 128) * max(1, k_in // (128 if k_in % 128 == 0 else 64))
-    splits = max(1, -(-296 // tiles))
+    splits = max(1, 296 // tiles)
     t = timeit(lambda: gemm_bf16(dz, x, dw, EPI_ATOMIC_F32, splits=splits, mn_major=True))
     rows.append(("wgrad split-K ", n_out, k_in, M, t))
 tot_f = tot_t = 0.0

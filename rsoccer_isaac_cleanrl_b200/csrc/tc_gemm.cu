@@ -83,6 +83,23 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
 }
+// The same load delivered to the same shared-memory offset of every CTA of the cluster whose bit is
+// set in cta_mask; each destination CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_multicast(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
+                                                      int c_outer, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -101,6 +118,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// commit that arrives on the mbarrier at the same offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -156,7 +178,10 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;   // 8 / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/ +
+  // ring depth: BN <= 128 -> 3 x 32 KB and two CTAs per SM; BN = 256 -> one CTA per SM, so the same
+  // 192 KB in flight take 4 x 48 KB (with 3 the TMA latency was exposed: measured 15 % slower)
+  static constexpr int NSTAGES = BN == 256 ? 4 : STAGES;
+  static constexpr int TOTAL = NSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/ +
                                EPI_WARPS * 32 * 80 /*epilogue staging*/;
 };
 
@@ -265,28 +290,41 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m_ba
 // CTAs working at the same time share A rows through L2). The accumulator is double-buffered in TMEM
 // (2 x BN columns): the MMA warp fills buffer (i+1)&1 while the epilogue warps drain buffer i&1, and the
 // TMA producer runs ahead across tile boundaries through the smem ring.
-template <int BN, int EPI, bool MN>
+//
+// CL = 2: the CTAs are launched as clusters of two that work on horizontally adjacent tiles (same rows
+// of A, neighbouring column blocks of B). Each CTA fetches HALF of the A tile and multicasts it into
+// both CTAs' shared memory, so a CTA pulls 24 KB instead of 32 KB per k-block through L2 — the kernel
+// is bound by that feed (~42 B/clk/SM), not by the tensor pipe. A stage may be refilled only when
+// BOTH CTAs' MMAs have read it: the MMA issuer's tcgen05.commit arrives on the empty barrier of both
+// CTAs (multicast), and the barrier counts two arrivals.
+template <int BN, int EPI, bool MN, int CL>
 __global__ void __launch_bounds__(THREADS, 2)
 k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ GemmArgs g) {
+  static_assert(CL == 1 || CL == 2, "cluster of one or two CTAs");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Smem<BN>::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Smem<BN>::NSTAGES * Smem<BN>::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Smem<BN>::NSTAGES;
+  uint64_t* tfull_bar = empty_bar + Smem<BN>::NSTAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* bias_s = reinterpret_cast<float*>(smem + STAGES * Smem<BN>::STAGE_BYTES + 256);  // [<= 512]
-  uint8_t* stage = smem + STAGES * Smem<BN>::STAGE_BYTES + 256 + 2048 + (((threadIdx.x >> 5) + EPI_WARPS - 2) % EPI_WARPS) * STAGE_BYTES_PER_WARP;
+  float* bias_s = reinterpret_cast<float*>(smem + Smem<BN>::NSTAGES * Smem<BN>::STAGE_BYTES + 256);  // [<= 512]
+  uint8_t* stage = smem + Smem<BN>::NSTAGES * Smem<BN>::STAGE_BYTES + 256 + 2048 + (((threadIdx.x >> 5) + EPI_WARPS - 2) % EPI_WARPS) * STAGE_BYTES_PER_WARP;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
   const int tiles_per_split = n_tiles * m_tiles;
   const int total_tiles = tiles_per_split * g.splits;
   const int total_kb = g.K / BK;
+  // tile walk: cluster c takes tile groups c, c + #clusters, ...; rank r of the cluster takes tile CL * group + r
+  // (n-tile fastest and n_tiles % CL == 0, so a group shares its A rows and its K-split)
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int t_begin = (blockIdx.x / CL) * CL + crank, t_step = (gridDim.x / CL) * CL;
+  constexpr uint16_t CL_MASK = (1u << CL) - 1u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < Smem<BN>::NSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -296,13 +334,14 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     for (int i = threadIdx.x; i < g.N; i += THREADS) bias_s[i] = __ldg(g.bias + i);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer
       uint32_t s = 0, ph = 0;  // ring position and phase (continue across tiles; no divisions on this path)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_begin; t < total_tiles; t += t_step) {
         const int split = t / tiles_per_split, r = t % tiles_per_split;
         const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
         const int kb0 = split * g.k_blocks_per_split;
@@ -311,17 +350,23 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Smem<BN>::STAGE_BYTES;
           uint8_t* sb = sa + Smem<BN>::A_BYTES;
-          mbar_expect_tx(&full_bar[s], Smem<BN>::STAGE_BYTES);
+          mbar_expect_tx(&full_bar[s], Smem<BN>::STAGE_BYTES);  // (CL = 2: half of the A bytes come from the peer)
           if (!MN) {
-            tma_load_2d(sa, &map_a, &full_bar[s], (kb0 + kb) * BK, m0);
+            if (CL == 1) tma_load_2d(sa, &map_a, &full_bar[s], (kb0 + kb) * BK, m0);
+            else  // rows [64 r, 64 r + 64) of the A tile (the map's box is 64 rows) into both CTAs
+              tma_load_2d_multicast(sa + crank * 8192, &map_a, &full_bar[s], (kb0 + kb) * BK, m0 + 64 * crank, CL_MASK);
             tma_load_2d(sb, &map_b, &full_bar[s], (kb0 + kb) * BK, n0);
           } else {  // source tensors are [K, M] / [K, N]: 64 x 64 boxes, inner coordinate = m / n
+            if (CL == 1) {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &map_a, &full_bar[s], m0 + 64 * i, (kb0 + kb) * BK);
+              for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &map_a, &full_bar[s], m0 + 64 * i, (kb0 + kb) * BK);
+            } else {
+              tma_load_2d_multicast(sa + crank * 8192, &map_a, &full_bar[s], m0 + 64 * crank, (kb0 + kb) * BK, CL_MASK);
+            }
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &map_b, &full_bar[s], n0 + 64 * i, (kb0 + kb) * BK);
           }
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == Smem<BN>::NSTAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -329,7 +374,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (lane == 0) {  // ---- MMA issuer
       constexpr uint32_t idesc = make_idesc(BM, BN, MN);
       uint32_t s = 0, ph = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      for (int t = t_begin; t < total_tiles; t += t_step, ++lt) {
         const int split = t / tiles_per_split;
         const int kb0 = split * g.k_blocks_per_split;
         const int nkb = min(g.k_blocks_per_split, total_kb - kb0);
@@ -348,8 +393,9 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_bf16(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
-          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          // frees the smem stage when these MMAs retire (in both CTAs of a cluster: the peer fills half of it)
+          if (CL == 1) umma_commit(&empty_bar[s]); else umma_commit_multicast(&empty_bar[s], CL_MASK);
+          if (++s == Smem<BN>::NSTAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[buf]);  // accumulator complete
       }
@@ -360,7 +406,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);  // column share of this warp within the quarter
     const int c_begin = ((warp - 2) >> 2) * COLS_PER_WARP;
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+    for (int t = t_begin; t < total_tiles; t += t_step, ++lt) {
       const int r = t % tiles_per_split;
       const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
@@ -380,6 +426,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();  // no CTA leaves while its peer can still multicast data or arrivals into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
@@ -566,11 +613,11 @@ static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, GemmA
   return cudaGetLastError();
 }
 
-template <int BN, int EPI, bool MN>
+template <int BN, int EPI, bool MN, int CL = 1>
 static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tn<BN, EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tn<BN, EPI, MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Smem<BN>::TOTAL);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -584,9 +631,19 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Ge
   }
   const int resident = BN == 256 ? max_ctas / 2 : max_ctas;  // 128x256 tiles: 144 KB smem + all 512 TMEM columns
   const long long tiles = (long long)((g.M + BM - 1) / BM) * (g.N / BN) * splits;
-  const unsigned grid = (unsigned)std::min<long long>(tiles, resident);
-  k_gemm_tn<BN, EPI, MN><<<grid, THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
-  return cudaGetLastError();
+  unsigned grid = (unsigned)std::min<long long>(tiles, resident);
+  if (CL == 1) {
+    k_gemm_tn<BN, EPI, MN, 1><<<grid, THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
+    return cudaGetLastError();
+  }
+  grid -= grid % CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Smem<BN>::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_gemm_tn<BN, EPI, MN, CL>, ma, mb, g);
 }
 
 }  // namespace tc
@@ -751,16 +808,22 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
   if ((epilogue == EPI_BIAS_TANH_BF16 && !bias) || (epilogue == EPI_DTANH_BF16 && !aux)) {
     g_tc_error = "vss_gemm_bf16_tn: missing bias/aux"; return VSS_E_INVALID;
   }
-  // tile width: 256 (tuning knob VSS_GEMM_BN256: 1 = dgrad, 2 = dgrad + wgrad) raises the FLOP per
-  // operand byte from 64 to 85 at the price of one CTA per SM
-  static const int bn256 = getenv("VSS_GEMM_BN256") ? atoi(getenv("VSS_GEMM_BN256")) : 0;
+  // tile width: 256 (tuning knob VSS_GEMM_BN256, bit 0 = dgrad, bit 1 = wgrad) raises the FLOP per
+  // operand byte from 64 to 85 at the price of one CTA per SM. Measured at minibatch 131072: wgrad
+  // 512x512 79 us vs 87 us with 128x128 tiles (default: on); dgrad 131 vs 107 us (default: off)
+  static const int bn256 = getenv("VSS_GEMM_BN256") ? atoi(getenv("VSS_GEMM_BN256")) : 2;
   int bn = (N % 128 == 0) ? 128 : 64;
-  if (N % 256 == 0 && M >= 128 * 148 && ((bn256 >= 1 && epilogue == EPI_DTANH_BF16 && !mn_major) ||
-                                        (bn256 >= 2 && epilogue == EPI_ATOMIC_F32 && mn_major)))
+  if (N % 256 == 0 && (((bn256 & 1) && epilogue == EPI_DTANH_BF16 && !mn_major && M >= 128 * 148) ||
+                       ((bn256 & 2) && epilogue == EPI_ATOMIC_F32 && mn_major)))
     bn = 256;
+  // clusters of two CTAs sharing the A tile by TMA multicast (dgrad and wgrad of the 512-wide layers);
+  // VSS_GEMM_CLUSTER=0 disables it (tuning)
+  static const int cluster_mode = getenv("VSS_GEMM_CLUSTER") ? atoi(getenv("VSS_GEMM_CLUSTER")) : 1;
+  const bool clustered = cluster_mode && bn == 128 && N % 256 == 0 && M >= (mn_major ? 128 : 128 * 148) &&
+                         ((epilogue == EPI_DTANH_BF16 && !mn_major) || (epilogue == EPI_ATOMIC_F32 && mn_major));
   CUtensorMap ma, mb;
   const bool ok = mn_major ? (make_map(&ma, A, K, M, lda, BK) && make_map(&mb, B, K, N, ldb, BK))
-                           : (make_map(&ma, A, M, K, lda, BM) && make_map(&mb, B, N, K, ldb, bn));
+                           : (make_map(&ma, A, M, K, lda, clustered ? BM / 2 : BM) && make_map(&mb, B, N, K, ldb, bn));
   if (!ok) {
     g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA;
   }
@@ -782,6 +845,12 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
       (epilogue == EPI_BIAS_TANH_BF16 || (ws_mode == 2 && epilogue == EPI_DTANH_BF16))) {
     e = epilogue == EPI_BIAS_TANH_BF16 ? launch_ws<EPI_BIAS_TANH_BF16>(ma, mb, g, st)
                                        : launch_ws<EPI_DTANH_BF16>(ma, mb, g, st);
+    if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
+    return VSS_OK;
+  }
+  if (clustered) {
+    e = mn_major ? launch<128, EPI_ATOMIC_F32, true, 2>(ma, mb, g, splits, st)
+                 : launch<128, EPI_DTANH_BF16, false, 2>(ma, mb, g, splits, st);
     if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
     return VSS_OK;
   }

@@ -20,7 +20,9 @@ _SM_TARGET = 296  # ~2 CTAs' worth of split-K work per SM for the wgrad grids
 
 def _splits(n_out, k_in, batch):
     tiles = (n_out // 128) * max(1, k_in // (128 if k_in % 128 == 0 else 64))
-    return max(1, min((batch + 63) // 64, -(-_SM_TARGET // tiles)))
+    # floor, not ceil: with more tiles than resident CTAs (2 per SM) a few CTAs would run a second tile
+    # alone and the launch would take two tile-times
+    return max(1, min((batch + 63) // 64, _SM_TARGET // tiles))
 
 
 class TCMlp(torch.autograd.Function):

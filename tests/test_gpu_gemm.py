@@ -57,6 +57,21 @@ def test_dgrad_fused_tanh_derivative():
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
+@pytest.mark.parametrize("M,N_out,K_in", [(131072, 512, 512), (128 * 148 + 77, 256, 512), (40000, 512, 256)])
+def test_dgrad_cluster_multicast_path(M, N_out, K_in):
+    """M >= 128 * 148 and k_in % 256 == 0: pairs of CTAs share the dZ tile through TMA multicast."""
+    from rsoccer_isaac_cleanrl_b200.engine import EPI_DTANH_BF16, gemm_bf16
+    dz, wt = _rand((M, N_out), 15), _rand((K_in, N_out), 16, N_out ** -0.5)
+    y = torch.tanh(_rand((M, K_in), 17).float()).to(torch.bfloat16)
+    out = torch.empty((M, K_in), device="cuda", dtype=torch.bfloat16)
+    gemm_bf16(dz, wt, out, EPI_DTANH_BF16, aux=y)
+    ref = (dz.float() @ wt.float().t()) * (1 - y.float() ** 2)
+    assert (out.float() - ref).abs().max().item() < 3e-2
+    out2 = torch.empty_like(out)
+    gemm_bf16(dz, wt, out2, EPI_DTANH_BF16, aux=y)
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("batch,N_out,K_in,splits", [(4096, 256, 64, 8), (8192, 512, 256, 16), (4000, 512, 512, 7),
                                                      (131072, 256, 512, 32)])
 def test_wgrad_mn_major_split_k(batch, N_out, K_in, splits):
