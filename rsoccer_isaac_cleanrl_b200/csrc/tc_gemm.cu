@@ -196,9 +196,23 @@ constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH;
 // row, 32 fp32 from TMEM). bf16 results are re-staged through shared memory so that every global
 // store instruction writes whole 64-byte row segments of 8 rows (4x fewer L1TEX wavefronts than
 // one 16-byte piece of 32 different rows per instruction, which bound the first version).
+// The aux rows of one 32x32 chunk in the coalesced pattern (lane -> row 8k + lane/4, 16-byte piece lane%4).
+struct AuxChunk { uint4 y[4]; };
+__device__ __forceinline__ AuxChunk load_aux_chunk(const GemmArgs& g, int m_base, int lane, int col) {
+  AuxChunk a;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = k * 8 + (lane >> 2), c16 = lane & 3;
+    a.y[k] = make_uint4(0, 0, 0, 0);
+    if (m_base + r < g.M) a.y[k] = __ldg(reinterpret_cast<const uint4*>(g.aux + (size_t)(m_base + r) * g.ld_aux + col) + c16);
+  }
+  return a;
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m_base, int lane, int col, const GemmArgs& g,
-                                               const float* bias_s, bool bias_in_smem, uint8_t* stage) {
+                                               const float* bias_s, bool bias_in_smem, uint8_t* stage,
+                                               const AuxChunk* pre = nullptr) {
   const int row = m_base + lane;
   if (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16) {
     uint32_t packed[16];
@@ -219,12 +233,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m_ba
       // aux tile (the activations whose tanh' multiplies the accumulator): coalesced 64-byte row
       // segments -> shared memory -> each lane reads back its own row
       __syncwarp();
+      const AuxChunk aux = pre ? *pre : load_aux_chunk(g, m_base, lane, col);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = k * 8 + (lane >> 2), c16 = lane & 3;
-        uint4 y4 = make_uint4(0, 0, 0, 0);
-        if (m_base + r < g.M) y4 = __ldg(reinterpret_cast<const uint4*>(g.aux + (size_t)(m_base + r) * g.ld_aux + col) + c16);
-        *reinterpret_cast<uint4*>(stage + r * STAGE_PITCH + c16 * 16) = y4;
+        *reinterpret_cast<uint4*>(stage + r * STAGE_PITCH + c16 * 16) = aux.y[k];
       }
       __syncwarp();
 #pragma unroll
@@ -406,17 +419,42 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);  // column share of this warp within the quarter
     const int c_begin = ((warp - 2) >> 2) * COLS_PER_WARP;
     uint32_t lt = 0;
+    AuxChunk aux_next[4];
     for (int t = t_begin; t < total_tiles; t += t_step, ++lt) {
       const int r = t % tiles_per_split;
       const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-      mbar_wait(&tfull_bar[buf], bph);
-      tc_fence_after();
+      if (EPI == EPI_DTANH_BF16 && BN == 128 && EPI_WARPS == 4) {
+        // The aux rows come from DRAM: issued when they are needed, every chunk exposed a full memory
+        // round trip (ncu: long_scoreboard 8 per issue, tensor pipe 19 % at K = 256). They are kept one
+        // tile ahead in registers instead — chunk c of the NEXT tile is requested as soon as chunk c of
+        // this tile has been copied to the staging buffer.
+        if (lt == 0) {
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) aux_next[ci] = load_aux_chunk(g, m0 + q * 32, lane, n0 + 32 * ci);
+        }
+        const int tn = t + t_step;
+        const int rn = tn % tiles_per_split;
+        const int m0n = (rn / n_tiles) * BM, n0n = (rn % n_tiles) * BN;
+        mbar_wait(&tfull_bar[buf], bph);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(32 * ci), v);
+          const AuxChunk cur = aux_next[ci];
+          if (tn < total_tiles) aux_next[ci] = load_aux_chunk(g, m0n + q * 32, lane, n0n + 32 * ci);
+          epilogue_chunk<EPI>(v, m0 + q * 32, lane, n0 + 32 * ci, g, bias_s, bias_in_smem, stage, &cur);
+        }
+      } else {
+        mbar_wait(&tfull_bar[buf], bph);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = c_begin; c < c_begin + COLS_PER_WARP; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
-        epilogue_chunk<EPI>(v, m0 + q * 32, lane, n0 + c, g, bias_s, bias_in_smem, stage);
+        for (int c = c_begin; c < c_begin + COLS_PER_WARP; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
+          epilogue_chunk<EPI>(v, m0 + q * 32, lane, n0 + c, g, bias_s, bias_in_smem, stage);
+        }
       }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld): hand the buffer back
       tc_fence_before();
@@ -811,14 +849,18 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
   // tile width: 256 (tuning knob VSS_GEMM_BN256, bit 0 = dgrad, bit 1 = wgrad) raises the FLOP per
   // operand byte from 64 to 85 at the price of one CTA per SM. Measured at minibatch 131072: wgrad
   // 512x512 79 us vs 87 us with 128x128 tiles (default: on); dgrad 131 vs 107 us (default: off)
-  static const int bn256 = getenv("VSS_GEMM_BN256") ? atoi(getenv("VSS_GEMM_BN256")) : 2;
+  const char* bn_env = getenv("VSS_GEMM_BN256");
+  const int bn256 = bn_env ? atoi(bn_env) : 2;
   int bn = (N % 128 == 0) ? 128 : 64;
   if (N % 256 == 0 && (((bn256 & 1) && epilogue == EPI_DTANH_BF16 && !mn_major && M >= 128 * 148) ||
                        ((bn256 & 2) && epilogue == EPI_ATOMIC_F32 && mn_major)))
     bn = 256;
-  // clusters of two CTAs sharing the A tile by TMA multicast (dgrad and wgrad of the 512-wide layers);
-  // VSS_GEMM_CLUSTER=0 disables it (tuning)
-  static const int cluster_mode = getenv("VSS_GEMM_CLUSTER") ? atoi(getenv("VSS_GEMM_CLUSTER")) : 1;
+  // VSS_GEMM_CLUSTER=1: clusters of two CTAs sharing the A tile by TMA multicast (dgrad and wgrad of
+  // the 512-wide layers). Off by default: measured equal to unicast at minibatch 131072 (dgrad 108.7
+  // vs 108.6 us) — L2 already merges the same line requested by up to ~4 CTAs close in time, so a
+  // pair saves no L2 bandwidth. Read per call so that tests can switch it.
+  const char* cluster_env = getenv("VSS_GEMM_CLUSTER");
+  const int cluster_mode = cluster_env ? atoi(cluster_env) : 0;
   const bool clustered = cluster_mode && bn == 128 && N % 256 == 0 && M >= (mn_major ? 128 : 128 * 148) &&
                          ((epilogue == EPI_DTANH_BF16 && !mn_major) || (epilogue == EPI_ATOMIC_F32 && mn_major));
   CUtensorMap ma, mb;

@@ -58,9 +58,11 @@ def test_dgrad_fused_tanh_derivative():
 
 
 @pytest.mark.parametrize("M,N_out,K_in", [(131072, 512, 512), (128 * 148 + 77, 256, 512), (40000, 512, 256)])
-def test_dgrad_cluster_multicast_path(M, N_out, K_in):
-    """M >= 128 * 148 and k_in % 256 == 0: pairs of CTAs share the dZ tile through TMA multicast."""
+def test_dgrad_cluster_multicast_path(M, N_out, K_in, monkeypatch):
+    """VSS_GEMM_CLUSTER=1, M >= 128 * 148 and k_in % 256 == 0: pairs of CTAs share the dZ tile through
+    TMA multicast (the knob is read on every call)."""
     from rsoccer_isaac_cleanrl_b200.engine import EPI_DTANH_BF16, gemm_bf16
+    monkeypatch.setenv("VSS_GEMM_CLUSTER", "1")
     dz, wt = _rand((M, N_out), 15), _rand((K_in, N_out), 16, N_out ** -0.5)
     y = torch.tanh(_rand((M, K_in), 17).float()).to(torch.bfloat16)
     out = torch.empty((M, K_in), device="cuda", dtype=torch.bfloat16)
@@ -74,8 +76,12 @@ def test_dgrad_cluster_multicast_path(M, N_out, K_in):
 
 @pytest.mark.parametrize("batch,N_out,K_in,splits", [(4096, 256, 64, 8), (8192, 512, 256, 16), (4000, 512, 512, 7),
                                                      (131072, 256, 512, 32)])
-def test_wgrad_mn_major_split_k(batch, N_out, K_in, splits):
+@pytest.mark.parametrize("cluster,bn256", [("0", "2"), ("1", "0"), ("0", "0")])
+def test_wgrad_mn_major_split_k(batch, N_out, K_in, splits, cluster, bn256, monkeypatch):
+    """Default 128x256 tiles, the 2-CTA multicast variant and plain 128x128 tiles."""
     from rsoccer_isaac_cleanrl_b200.engine import EPI_ATOMIC_F32, gemm_bf16
+    monkeypatch.setenv("VSS_GEMM_CLUSTER", cluster)
+    monkeypatch.setenv("VSS_GEMM_BN256", bn256)
     dz, x = _rand((batch, N_out), 8, 0.1), _rand((batch, K_in), 9)
     dw = torch.zeros((N_out, K_in), device="cuda")
     gemm_bf16(dz, x, dw, EPI_ATOMIC_F32, splits=splits, mn_major=True)
