@@ -215,6 +215,11 @@ VSS_API int vss_gae(const float* rewards, const float* values, const float* next
 VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, void* out, int ldo, int M,
                              int N, int K, int epilogue, const float* bias, const void* aux, int ld_aux,
                              int splits, int mn_major, void* stream);
+/* The same with one more output (dgrad epilogue 1 only, mn_major = 0, N <= 512): colsum[N] (f32) +=
+ * column sums of the bf16 output, i.e. the bias gradient of the layer below; NULL = plain GEMM. */
+VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int ldb, void* out, int ldo, int M,
+                                    int N, int K, int epilogue, const float* bias, const void* aux, int ld_aux,
+                                    int splits, int mn_major, float* colsum, void* stream);
 VSS_API const char* vss_gemm_last_error(void);
 /* out[N] (f32) += column sums of the bf16 matrix x [M,N] (row stride ld): bias gradients. */
 VSS_API int vss_colsum_bf16(const void* x, int ld, int M, int N, float* out, void* stream);
@@ -225,11 +230,12 @@ VSS_API int vss_gather_pad_bf16(const float* src, const int64_t* idx, int M, int
 
 /* Output head of the Agent MLPs (Linear 256 -> n_out in {1,2,6}, ppo...:138,151) and its backward
  * fused with tanh' of the last hidden layer: dz = (dout W) * (1 - h^2) (bf16), dW += dout^T h,
- * db += sum dout. h [M,256] bf16, W [n_out,256] f32, out/dout [M,n_out] f32. */
+ * db += sum dout; dz_colsum [256] += column sums of dz (bias gradient of the last hidden layer) when
+ * not NULL. h [M,256] bf16, W [n_out,256] f32, out/dout [M,n_out] f32. */
 VSS_API int vss_head_forward(const void* h, int ldh, const float* W, const float* b, float* out, int M, int n_out,
                              void* stream);
 VSS_API int vss_head_backward(const float* dout, const void* h, int ldh, const float* W, void* dz, int ldz,
-                              float* dW, float* db, int M, int n_out, void* stream);
+                              float* dW, float* db, float* dz_colsum, int M, int n_out, void* stream);
 
 /* ---- the small pieces of the PPO loop, one launch each (ppo_continuous_action_isaacgym.py) ------
  * Normal(mean, exp(logstd)).sample() and .log_prob(action).sum(1) of Agent.get_action_and_value

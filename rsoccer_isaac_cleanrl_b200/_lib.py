@@ -71,9 +71,11 @@ _SYMBOLS = {
     "vss_gae": (C.c_int, [_VP] * 7 + [C.c_int32, C.c_int64, C.c_double, C.c_double, _VP]),
     "vss_gemm_bf16_tn": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP,
                                   _VP, C.c_int, C.c_int, C.c_int, _VP]),
+    "vss_gemm_bf16_tn_colsum": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         _VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_gemm_last_error": (C.c_char_p, []),
     "vss_head_forward": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
-    "vss_head_backward": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP, C.c_int, C.c_int, _VP]),
+    "vss_head_backward": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
     "vss_colsum_bf16": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_gather_pad_bf16": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_policy_sample": (C.c_int, [_VP, _VP, C.c_int64, C.c_int, C.c_uint64, _VP, _VP, _VP, _VP]),

@@ -51,6 +51,7 @@ struct GemmArgs {
   const float* bias;       // [N] or null
   const __nv_bfloat16* aux;  // [M, ld_aux] for EPI_DTANH_BF16
   int ld_aux;
+  float* colsum;           // EPI_DTANH_BF16: [N] += column sums of the bf16 output (bias gradient of the layer below), or null
 };
 
 // ------------------------------------------------------------------------------- PTX wrappers
@@ -212,7 +213,7 @@ __device__ __forceinline__ AuxChunk load_aux_chunk(const GemmArgs& g, int m_base
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m_base, int lane, int col, const GemmArgs& g,
                                                const float* bias_s, bool bias_in_smem, uint8_t* stage,
-                                               const AuxChunk* pre = nullptr) {
+                                               const AuxChunk* pre = nullptr, float* colsum_s = nullptr) {
   const int row = m_base + lane;
   if (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16) {
     uint32_t packed[16];
@@ -275,6 +276,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m_ba
       const int r = k * 8 + (lane >> 2), c16 = lane & 3;
       const uint4 o = *reinterpret_cast<const uint4*>(stage + r * STAGE_PITCH + c16 * 16);
       if (m_base + r < g.M) *(reinterpret_cast<uint4*>(obase + (size_t)(m_base + r) * g.ldo) + c16) = o;
+    }
+    if (colsum_s) {  // bias gradient of the layer below: column sums of the (bf16-rounded) tile, lane = column
+      float sum = 0.0f;  // (rows past M were computed from zero-filled operands and hold zeros)
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        sum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stage + r * STAGE_PITCH + 2 * lane));
+      atomicAdd(colsum_s + col + lane, sum);
     }
     __syncwarp();
   } else if (EPI == EPI_ATOMIC_F32) {
@@ -345,6 +353,10 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const bool bias_in_smem = (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_BIAS_F32) && g.bias != nullptr && g.N <= 512;
   if (bias_in_smem)  // the whole bias vector once per CTA: the epilogue reads it as broadcast float4s
     for (int i = threadIdx.x; i < g.N; i += THREADS) bias_s[i] = __ldg(g.bias + i);
+  // dgrad: per-CTA column sums of the produced tiles live in the (otherwise unused) bias buffer
+  float* colsum_s = (EPI == EPI_DTANH_BF16 && g.colsum != nullptr) ? bias_s : nullptr;
+  if (colsum_s)
+    for (int i = threadIdx.x; i < g.N; i += THREADS) colsum_s[i] = 0.0f;
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
@@ -444,7 +456,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(32 * ci), v);
           const AuxChunk cur = aux_next[ci];
           if (tn < total_tiles) aux_next[ci] = load_aux_chunk(g, m0n + q * 32, lane, n0n + 32 * ci);
-          epilogue_chunk<EPI>(v, m0 + q * 32, lane, n0 + 32 * ci, g, bias_s, bias_in_smem, stage, &cur);
+          epilogue_chunk<EPI>(v, m0 + q * 32, lane, n0 + 32 * ci, g, bias_s, bias_in_smem, stage, &cur, colsum_s);
         }
       } else {
         mbar_wait(&tfull_bar[buf], bph);
@@ -453,7 +465,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         for (int c = c_begin; c < c_begin + COLS_PER_WARP; c += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
-          epilogue_chunk<EPI>(v, m0 + q * 32, lane, n0 + c, g, bias_s, bias_in_smem, stage);
+          epilogue_chunk<EPI>(v, m0 + q * 32, lane, n0 + c, g, bias_s, bias_in_smem, stage, nullptr, colsum_s);
         }
       }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld): hand the buffer back
@@ -464,6 +476,8 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (colsum_s)
+    for (int i = threadIdx.x; i < g.N; i += THREADS) atomicAdd(g.colsum + i, colsum_s[i]);
   if (CL > 1) cluster_sync();  // no CTA leaves while its peer can still multicast data or arrivals into it
   if (warp == 1) {
     tc_fence_after();
@@ -766,11 +780,14 @@ k_head_fwd(const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict
 template <int NO>
 __global__ void __launch_bounds__(256)
 k_head_bwd(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict__ W,
-           __nv_bfloat16* __restrict__ dz, int ldz, float* __restrict__ dW, float* __restrict__ db, int M) {
+           __nv_bfloat16* __restrict__ dz, int ldz, float* __restrict__ dW, float* __restrict__ db,
+           float* __restrict__ dz_colsum, int M) {
   __shared__ float red[8][NO][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  float w[NO][8], gw[NO][8], gb[NO];
+  float w[NO][8], gw[NO][8], gb[NO], gz[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) gz[c] = 0.f;
 #pragma unroll
   for (int j = 0; j < NO; ++j) {
     gb[j] = 0.f;
@@ -798,6 +815,10 @@ k_head_bwd(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ h, 
     o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
     o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
     *reinterpret_cast<uint4*>(dz + (size_t)m * ldz + 8 * lane) = o;
+    // bias gradient of the last hidden layer = column sums of dz as stored (bf16-rounded)
+    gz[0] += __bfloat162float(p0.x); gz[1] += __bfloat162float(p0.y); gz[2] += __bfloat162float(p1.x);
+    gz[3] += __bfloat162float(p1.y); gz[4] += __bfloat162float(p2.x); gz[5] += __bfloat162float(p2.y);
+    gz[6] += __bfloat162float(p3.x); gz[7] += __bfloat162float(p3.y);
   }
 #pragma unroll
   for (int j = 0; j < NO; ++j)
@@ -814,6 +835,16 @@ k_head_bwd(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ h, 
   if (lane == 0)
 #pragma unroll
     for (int j = 0; j < NO; ++j) atomicAdd(db + j, gb[j]);
+  if (dz_colsum) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) red[wib][0][8 * lane + c] = gz[c];
+    __syncthreads();
+    float sacc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sacc += red[k][0][threadIdx.x];
+    atomicAdd(dz_colsum + threadIdx.x, sacc);
+  }
 }
 
 }  // namespace tc
@@ -835,7 +866,20 @@ VSS_API const char* vss_gemm_last_error(void) { return g_tc_error.c_str(); }
 VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, void* out, int ldo, int M, int N, int K,
                              int epilogue, const float* bias, const void* aux, int ld_aux, int splits, int mn_major,
                              void* stream) {
+  return vss_gemm_bf16_tn_colsum(A, lda, B, ldb, out, ldo, M, N, K, epilogue, bias, aux, ld_aux, splits, mn_major,
+                                 nullptr, stream);
+}
+
+// The same, plus (dgrad epilogue only) colsum[N] += column sums of the bf16 output: the bias gradient of
+// the layer below comes out of the GEMM that produces dZ instead of a second pass over it.
+VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int ldb, void* out, int ldo, int M, int N,
+                                    int K, int epilogue, const float* bias, const void* aux, int ld_aux, int splits,
+                                    int mn_major, float* colsum, void* stream) {
   using namespace tc;
+  if (colsum && (epilogue != EPI_DTANH_BF16 || mn_major || N > 512)) {
+    g_tc_error = "vss_gemm_bf16_tn_colsum: column sums need the dgrad epilogue, K-major operands and N <= 512";
+    return VSS_E_INVALID;
+  }
   if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) { g_tc_error = "vss_gemm_bf16_tn: bad argument"; return VSS_E_INVALID; }
   if ((!mn_major && K % BK != 0) || N % 64 != 0 || lda % 8 != 0 || ldb % 8 != 0 || (mn_major && M % 128 != 0)) {
     g_tc_error = "vss_gemm_bf16_tn: K must be a multiple of 64 (K-major), N of 64, lda/ldb of 8, M of 128 (MN-major)";
@@ -877,13 +921,14 @@ VSS_API int vss_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, voi
   splits = (total_kb + g.k_blocks_per_split - 1) / g.k_blocks_per_split;
   g.splits = splits;
   g.out = out; g.ldo = ldo; g.bias = bias; g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ld_aux = ld_aux;
+  g.colsum = colsum;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
   // forward with enough M tiles per SM: weight-stationary kernel (measured: forward 257 -> 244 us per
   // MLP at M = 131072; dgrad, whose epilogue also streams the aux tile, is 8 % slower with it and
   // stays on the streaming kernel). VSS_GEMM_WS=0/2 disables it / also enables it for dgrad (tuning).
   static const int ws_mode = getenv("VSS_GEMM_WS") ? atoi(getenv("VSS_GEMM_WS")) : 1;
-  if (ws_mode && !mn_major && splits == 1 && bn == 128 && K <= 512 && M >= 128 * 148 &&
+  if (ws_mode && !colsum && !mn_major && splits == 1 && bn == 128 && K <= 512 && M >= 128 * 148 &&
       (epilogue == EPI_BIAS_TANH_BF16 || (ws_mode == 2 && epilogue == EPI_DTANH_BF16))) {
     e = epilogue == EPI_BIAS_TANH_BF16 ? launch_ws<EPI_BIAS_TANH_BF16>(ma, mb, g, st)
                                        : launch_ws<EPI_DTANH_BF16>(ma, mb, g, st);
@@ -958,15 +1003,15 @@ VSS_API int vss_head_forward(const void* h, int ldh, const float* W, const float
 // Backward of the head fused with tanh' of the last hidden layer (see k_head_bwd). dW [n_out,256] and
 // db [n_out] are accumulated (+=): the caller zeroes them. dz [M,256] bf16.
 VSS_API int vss_head_backward(const float* dout, const void* h, int ldh, const float* W, void* dz, int ldz, float* dW,
-                              float* db, int M, int n_out, void* stream) {
+                              float* db, float* dz_colsum, int M, int n_out, void* stream) {
   if (!dout || !h || !W || !dz || !dW || !db || M <= 0) { g_tc_error = "vss_head_backward: bad argument"; return VSS_E_INVALID; }
   const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h);
   __nv_bfloat16* zp = reinterpret_cast<__nv_bfloat16*>(dz);
   const int blocks = std::min((M + 7) / 8, 148 * 2);
   cudaStream_t st = (cudaStream_t)stream;
-  if (n_out == 1) tc::k_head_bwd<1><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, M);
-  else if (n_out == 2) tc::k_head_bwd<2><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, M);
-  else if (n_out == 6) tc::k_head_bwd<6><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, M);
+  if (n_out == 1) tc::k_head_bwd<1><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, dz_colsum, M);
+  else if (n_out == 2) tc::k_head_bwd<2><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, dz_colsum, M);
+  else if (n_out == 6) tc::k_head_bwd<6><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, dz_colsum, M);
   else { g_tc_error = "vss_head_backward: n_out must be 1, 2 or 6"; return VSS_E_INVALID; }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_tc_error = std::string("vss_head_backward: ") + cudaGetErrorString(e); return VSS_E_CUDA; }

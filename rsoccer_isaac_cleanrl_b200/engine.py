@@ -134,9 +134,10 @@ def gae(rewards, values, next_values, next_dones, next_timeouts, gamma=0.99, gae
 EPI_BIAS_TANH_BF16, EPI_DTANH_BF16, EPI_ATOMIC_F32, EPI_BIAS_F32 = 0, 1, 2, 3
 
 
-def gemm_bf16(a, b, out, epilogue, bias=None, aux=None, splits=1, mn_major=False):
+def gemm_bf16(a, b, out, epilogue, bias=None, aux=None, splits=1, mn_major=False, colsum=None):
     """tcgen05 GEMM (csrc/tc_gemm.cu). K-major: a [M,K], b [N,K]; MN-major: a [K,M], b [K,N]; bf16, last
-    dimension contiguous. out [M,N] bf16 (epilogues 0,1) or f32 (2,3)."""
+    dimension contiguous. out [M,N] bf16 (epilogues 0,1) or f32 (2,3). colsum [N] f32 (dgrad epilogue
+    only): += column sums of the output."""
     lib = _lib.load_library()
     if mn_major:
         K, M = a.shape
@@ -155,10 +156,13 @@ def gemm_bf16(a, b, out, epilogue, bias=None, aux=None, splits=1, mn_major=False
     if aux is not None:
         assert aux.dtype == torch.bfloat16 and aux.shape == (M, N) and aux.stride(1) == 1
         ld_aux = aux.stride(0)
-    rc = lib.vss_gemm_bf16_tn(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
-                              M, N, K, int(epilogue), None if bias is None else bias.data_ptr(),
-                              None if aux is None else aux.data_ptr(), ld_aux, int(splits), int(bool(mn_major)),
-                              torch.cuda.current_stream(a.device).cuda_stream)
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == N
+    rc = lib.vss_gemm_bf16_tn_colsum(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                                     out.stride(0), M, N, K, int(epilogue), None if bias is None else bias.data_ptr(),
+                                     None if aux is None else aux.data_ptr(), ld_aux, int(splits), int(bool(mn_major)),
+                                     None if colsum is None else colsum.data_ptr(),
+                                     torch.cuda.current_stream(a.device).cuda_stream)
     if rc != 0:
         raise RuntimeError(f"vss_gemm_bf16_tn failed ({rc}): {lib.vss_gemm_last_error().decode()}")
     return out
@@ -206,7 +210,7 @@ def head_forward(h, W, b, out=None):
     return out
 
 
-def head_backward(dout, h, W, dW=None, db=None):
+def head_backward(dout, h, W, dW=None, db=None, dz_colsum=None):
     """(dz [M,256] bf16, dW [n_out,256] f32, db [n_out] f32) of the head, tanh' of h fused into dz.
     dW / db, when given, are accumulated into (contiguous f32 buffers such as the .grad views)."""
     lib = _lib.load_library()
@@ -218,8 +222,11 @@ def head_backward(dout, h, W, dW=None, db=None):
     if db is None:
         db = torch.zeros(n_out, device=h.device, dtype=torch.float32)
     assert dW.is_contiguous() and db.is_contiguous() and dW.numel() == n_out * 256 and db.numel() == n_out
+    if dz_colsum is not None:  # += column sums of dz: the bias gradient of the last hidden layer
+        assert dz_colsum.dtype == torch.float32 and dz_colsum.is_contiguous() and dz_colsum.numel() == 256
     rc = lib.vss_head_backward(dout.data_ptr(), h.data_ptr(), h.stride(0), W.contiguous().data_ptr(), dz.data_ptr(), 256,
-                               dW.data_ptr(), db.data_ptr(), M, n_out, torch.cuda.current_stream(h.device).cuda_stream)
+                               dW.data_ptr(), db.data_ptr(), None if dz_colsum is None else dz_colsum.data_ptr(),
+                               M, n_out, torch.cuda.current_stream(h.device).cuda_stream)
     if rc != 0:
         raise RuntimeError(lib.vss_gemm_last_error().decode())
     return dz, dW, db

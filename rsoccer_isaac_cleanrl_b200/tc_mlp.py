@@ -120,9 +120,11 @@ def forward_explicit(mw, x16, out=None):
 def backward_explicit(mw, hs, dout):
     """Accumulates d loss / d parameters into the parameters' .grad buffers (contiguous f32, e.g.
     views of the flat gradient) given dout = d loss / d out. Same kernels as TCMlp.backward, but the
-    split-K wgrad atomics, the column sums and the head kernel write straight into .grad."""
+    split-K wgrad atomics and the head kernel write straight into .grad, and the bias gradients come
+    out of the dgrad / head kernels' epilogues (no separate column-sum pass over dZ)."""
     M = dout.shape[0]
-    dz = head_backward(dout, hs[4], mw.head_w, dW=mw.head_w.grad, db=mw.head_b.grad)[0]
+    # every bias gradient (column sums of dZ_l) is accumulated by the kernel that PRODUCES dZ_l
+    dz = head_backward(dout, hs[4], mw.head_w, dW=mw.head_w.grad, db=mw.head_b.grad, dz_colsum=mw.bs[3].grad)[0]
     for l in (3, 2, 1, 0):
         n_out, k_in = dz.shape[1], hs[l].shape[1]
         if l == 0:
@@ -131,8 +133,7 @@ def backward_explicit(mw, hs, dout):
             mw.ws[0].grad.add_(mw.dw0[:, :mw.n_in])
         else:
             gemm_bf16(dz, hs[l], mw.ws[l].grad, EPI_ATOMIC_F32, splits=_splits(n_out, k_in, M), mn_major=True)
-        colsum_bf16(dz, out=mw.bs[l].grad)
         if l > 0:
             dz_prev = torch.empty((M, k_in), device=dz.device, dtype=torch.bfloat16)
-            gemm_bf16(dz, mw.wt16[l], dz_prev, EPI_DTANH_BF16, aux=hs[l])
+            gemm_bf16(dz, mw.wt16[l], dz_prev, EPI_DTANH_BF16, aux=hs[l], colsum=mw.bs[l - 1].grad)
             dz = dz_prev
