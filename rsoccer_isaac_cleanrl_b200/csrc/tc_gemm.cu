@@ -190,6 +190,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr bool FWD_DIRECT_STORES = true;   // forward epilogue: re-staging through shared memory like dgrad was measured slower (K=64: 37.8 vs 32.0 us)
 constexpr int STAGE_PITCH = 80;                       // bytes per staged row: 64 B of bf16 + 16 B pad (conflict-free STS.128)
 constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH;
 
@@ -257,7 +258,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m_ba
       }
       __syncwarp();
     }
-    if (EPI == EPI_BIAS_TANH_BF16) {  // measured: the forward epilogue is not bound by its stores; write directly
+    if (EPI == EPI_BIAS_TANH_BF16 && FWD_DIRECT_STORES) {  // each lane writes 16-byte pieces of its own row
       if (row < g.M) {
         uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + col);
 #pragma unroll
@@ -493,10 +494,15 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // ring while walking its share of the M tiles; accumulators are double-buffered in TMEM as above.
 constexpr int WS_MAX_KB = 8;        // K <= 512
 constexpr int WS_MAX_STAGES = 12;
+// Epilogue warps of the weight-stationary kernel (one CTA per SM). 8 (two per TMEM lane quarter, half
+// of the 128 columns each) was measured slower: K = 512 105 vs 93 us, K = 256 72 vs 70 us — their 10 KB
+// of extra staging cost one stage of the activation ring, and the epilogue is not issue-bound.
+constexpr int WS_EPI_WARPS = 4;
+constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
 struct SmemWS {
   static constexpr int A_BYTES = BM * BK * 2;                    // 16 KB per stage
   static constexpr int KB_BYTES = 128 * BK * 2;                  // 16 KB of resident weights per k-block
-  static constexpr int TAIL = 1024 + 256 + 2048 + EPI_WARPS * 32 * 80;  // align slack, barriers, bias, staging
+  static constexpr int TAIL = 1024 + 256 + 2048 + WS_EPI_WARPS * 32 * 80;  // align slack, barriers, bias, staging
   static constexpr int BUDGET = 226 * 1024;                      // dynamic shared memory per CTA (227 KB max)
   // Depth of the activation ring. Measured at M = 131072, N = 512: K = 256 -> 74 us with 4 stages,
   // 69 us with 9; K = 512 -> 93 us with 4 stages, 104 us with 5 (the last 16 KB of shared memory
@@ -506,7 +512,7 @@ struct SmemWS {
 };
 
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(WS_THREADS, 1)
 k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ GemmArgs g) {
   constexpr int BN = 128;
@@ -524,7 +530,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* b_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
   float* bias_s = reinterpret_cast<float*>(tail + 256);
-  uint8_t* stage = tail + 256 + 2048 + (((threadIdx.x >> 5) + EPI_WARPS - 2) % EPI_WARPS) * STAGE_BYTES_PER_WARP;
+  uint8_t* stage = tail + 256 + 2048 + (((threadIdx.x >> 5) + WS_EPI_WARPS - 2) % WS_EPI_WARPS) * STAGE_BYTES_PER_WARP;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
@@ -534,14 +540,14 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], WS_EPI_WARPS); }
     mbar_init(b_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   const bool bias_in_smem = (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_BIAS_F32) && g.bias != nullptr && g.N <= 512;
   if (bias_in_smem)
-    for (int i = threadIdx.x; i < g.N; i += THREADS) bias_s[i] = __ldg(g.bias + i);
+    for (int i = threadIdx.x; i < g.N; i += WS_THREADS) bias_s[i] = __ldg(g.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -587,7 +593,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
   } else {  // ---- epilogue
     const int q = warp & 3;                              // TMEM lane quarter this warp may touch
-    constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);  // column share of this warp within the quarter
+    constexpr int COLS_PER_WARP = BN / (WS_EPI_WARPS / 4);  // column share of this warp within the quarter
     const int c_begin = ((warp - 2) >> 2) * COLS_PER_WARP;
     uint32_t lt = 0;
     for (int mt = m_first; mt < m_tiles; mt += m_step, ++lt) {
@@ -661,7 +667,7 @@ static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, GemmA
   int per_slice = std::min(std::max(sms / n_tiles, 1), m_tiles);   // CTAs per column slice
   const int nkb = g.K / BK;
   g.ws_stages = SmemWS::stages(nkb);
-  k_gemm_ws<EPI><<<per_slice * n_tiles, THREADS, SmemWS::total(nkb), st>>>(ma, mb, g);
+  k_gemm_ws<EPI><<<per_slice * n_tiles, WS_THREADS, SmemWS::total(nkb), st>>>(ma, mb, g);
   return cudaGetLastError();
 }
 
