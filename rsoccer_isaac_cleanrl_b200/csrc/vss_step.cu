@@ -324,17 +324,17 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-// Launch shape. Large batches: 8 warps per CTA with CTA-wide barriers at phase boundaries — the step
+// Launch shape. Large batches: 4 warps per CTA with CTA-wide barriers at phase boundaries — the step
 // kernel is instruction-fetch bound (profiles/r01_b_*.md), and warps that execute the same code
 // region at the same time share its lines in the instruction caches (+25 % measured). Small
 // batches: 1-2 warps per CTA so that at least 148 CTAs exist; no barriers (latency matters there).
 // VSS_WPB / VSS_SYNC environment variables override (tuning).
 static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* smem, int* sync_level = nullptr) {
   const int64_t tiles = (n + 31) / 32;
-  int wpb = 8, sync = 2;
+  int wpb = 4, sync = 2;  // 6 CTAs of 4 warps per SM (measured at 2^20 fields: 4 / 6 / 8 / 12 warps per CTA ->
+                          // 0.672 / 0.671 / 0.652 / 0.592 of the HBM roofline; at 2^16 fields 0.405 / 0.366 / 0.377)
   if (tiles < 148 * 2) { wpb = 1; sync = 0; }
   else if (tiles < 148 * 8) { wpb = 2; sync = 0; }
-  else if (tiles < 148 * 24) { wpb = 4; sync = 2; }
   static const int forced_wpb = env_int("VSS_WPB", 0), forced_sync = env_int("VSS_SYNC", -1);
   if (forced_wpb >= 1 && forced_wpb <= 12) wpb = forced_wpb;
   if (forced_sync >= 0) sync = forced_sync;
