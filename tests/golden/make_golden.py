@@ -327,6 +327,76 @@ def gen_agent():
     print("agent.npz", len(out), "arrays")
 
 
+# ------------------------------------------------------------------ one PPO minibatch update
+def gen_ppo_update():
+    """Executes the reference's own minibatch code (ppo…:314-354: loss, backward, clip_grad_norm_,
+    Adam step) on its own Agent (ppo…:121-164) and records the statistics, the gradient w.r.t. the
+    network outputs (captured with forward hooks) and a sample of the updated parameters."""
+    sys.modules.setdefault("gym", _gym_shim())
+    ns = dict(torch=torch, nn=torch.nn, np=np)
+    exec("from torch.distributions.normal import Normal\n" + _lines("ppo_continuous_action_isaacgym.py", 121, 164), ns)
+    body = textwrap.dedent(_lines("ppo_continuous_action_isaacgym.py", 314, 352))        # ... loss.backward()
+    body_step = textwrap.dedent(_lines("ppo_continuous_action_isaacgym.py", 353, 354))   # clip_grad_norm_, optimizer.step()
+    out = {}
+    for name, adim, clip_vloss in (("a2", 2, False), ("a6v", 6, True)):
+        torch.manual_seed(11)
+        envs = types.SimpleNamespace(single_observation_space=types.SimpleNamespace(shape=(52,)),
+                                     single_action_space=types.SimpleNamespace(shape=(adim,)))
+        agent = ns["Agent"](envs)
+        with torch.no_grad():
+            agent.actor_logstd.copy_(torch.linspace(-0.4, 0.1, adim).view(1, adim))
+            agent.actor_mean[8].weight.mul_(20.0)   # (initialised with std 0.01: make the mean matter)
+        R, B = 160, 64
+        b_obs, b_actions = torch.randn(R, 52), torch.randn(R, adim) * 0.7
+        with torch.no_grad():
+            _, lp, _, val = agent.get_action_and_value(b_obs, b_actions)
+        b_logprobs = lp + 0.3 * torch.randn(R)        # ratios on both sides of the clip range
+        b_values = val.view(-1) + 0.3 * torch.randn(R)
+        b_advantages, b_returns = torch.randn(R) * 1.5 + 0.2, torch.randn(R)
+        mb_inds = torch.randperm(R)[:B]
+        args = types.SimpleNamespace(clip_coef=0.2, norm_adv=True, clip_vloss=clip_vloss, ent_coef=0.005, vf_coef=4.0,
+                                     max_grad_norm=1.5)
+        optimizer = torch.optim.Adam(agent.parameters(), lr=1e-3, eps=1e-5)
+        captured = {}
+
+        def keep(key):
+            def hook(module, inputs, output):   # (returns None: the output is not replaced)
+                output.retain_grad()
+                captured[key] = output
+            return hook
+
+        hooks = [agent.actor_mean.register_forward_hook(keep("mean")), agent.critic.register_forward_hook(keep("value"))]
+        for k, v in dict(b_obs=b_obs, b_actions=b_actions, b_logprobs=b_logprobs, b_values=b_values,
+                         b_advantages=b_advantages, b_returns=b_returns, mb_inds=mb_inds,
+                         logstd=agent.actor_logstd.detach().clone().view(-1)).items():
+            out[f"{name}_{k}"] = v.numpy().copy()
+        env = dict(ns, agent=agent, b_obs=b_obs, b_actions=b_actions, b_logprobs=b_logprobs, b_values=b_values,
+                   b_advantages=b_advantages, b_returns=b_returns, mb_inds=mb_inds, args=args, optimizer=optimizer,
+                   clipfracs=[])
+        exec(body, env)
+        for h in hooks:
+            h.remove()
+        out[f"{name}_d_logstd"] = agent.actor_logstd.grad.view(-1).numpy().copy()
+        gn0 = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in agent.parameters()))
+        out[f"{name}_grad_norm"] = np.float64(gn0.item())
+        exec(body_step, env)
+        for k in ("pg_loss", "v_loss", "entropy_loss", "old_approx_kl", "approx_kl", "loss"):
+            out[f"{name}_{k}"] = np.float32(env[k].item())
+        out[f"{name}_clipfrac"] = np.float32(env["clipfracs"][0])
+        out[f"{name}_mean"] = captured["mean"].detach().numpy().copy()
+        out[f"{name}_value"] = captured["value"].detach().numpy().copy()
+        out[f"{name}_d_mean"] = captured["mean"].grad.numpy().copy()
+        out[f"{name}_d_value"] = captured["value"].grad.numpy().copy()
+        # after clip_grad_norm_: .grad holds the clipped gradient; logstd's is d_logstd * clip coefficient
+        gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in agent.parameters()))
+        out[f"{name}_clipped_grad_norm"] = np.float64(gn.item())
+        out[f"{name}_clipped_d_logstd"] = agent.actor_logstd.grad.view(-1).numpy().copy()
+        out[f"{name}_logstd_after"] = agent.actor_logstd.detach().view(-1).numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "ppo_update.npz"), **out)
+    print("ppo_update.npz", len(out), "arrays")
+
+
+
 def gen_ppo_defaults():
     """Defaults of every CLI flag: the reference's parse_args (ppo…:48-118) executed with no argv."""
     import argparse
@@ -362,3 +432,4 @@ if __name__ == "__main__":
     gen_gae()
     gen_wrappers()
     gen_agent()
+    gen_ppo_update()

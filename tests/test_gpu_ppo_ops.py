@@ -2,9 +2,13 @@
 expressions — the reference's own formulas (ppo_continuous_action_isaacgym.py:155-164, 314-354)
 evaluated with torch autograd / torch.optim.Adam. Tolerances are fp32 rounding (1e-5 relative)."""
 import math
+import os
 import types
 
+import numpy as np
 import pytest
+
+from oracle import ppo_oracle as po
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -182,3 +186,72 @@ def test_explicit_mlp_training_path_matches_the_autograd_function():
     for (k, pa), (_, pb) in zip(a.actor_mean.named_parameters(), b.actor_mean.named_parameters()):
         assert (2 * pa.grad - pb.grad).norm().item() <= 2e-4 * pa.grad.norm().item() + 1e-12, k
     assert math.isfinite(flat_grad.norm().item())
+
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ppo_update.npz")
+
+
+@pytest.mark.parametrize("name,clip_vloss", [("a2", False), ("a6v", True)])
+def test_ppo_loss_kernel_against_the_reference_update_golden(name, clip_vloss):
+    """vss_ppo_loss on the inputs / fresh network outputs recorded while executing the reference's own
+    minibatch code (ppo…:314-352): statistics and d loss / d (mean, value, logstd)."""
+    from rsoccer_isaac_cleanrl_b200.engine import ppo_loss
+    g = np.load(GOLD)
+    k = lambda s_: torch.from_numpy(g[f"{name}_{s_}"]).cuda()
+    A = k("logstd").numel()
+    d_logstd = torch.zeros(A, device="cuda")
+    d_mean, d_value, st = ppo_loss(k("mean").contiguous(), k("value").contiguous(), k("logstd"), k("b_actions"),
+                                   k("b_logprobs"), k("b_advantages"), k("b_returns"), k("b_values"), k("mb_inds"),
+                                   0.2, 0.005, 4.0, True, clip_vloss, d_logstd)
+    ref = [g[f"{name}_{s_}"] for s_ in ("pg_loss", "v_loss", "entropy_loss", "old_approx_kl", "approx_kl", "clipfrac", "loss")]
+    for i, r in enumerate(ref):
+        assert abs(st[i].item() - float(r)) <= 3e-6 + 3e-5 * abs(float(r)), (i, st[i].item(), float(r))
+    _close(d_mean, k("d_mean"), rtol=1e-4, atol=1e-9)
+    _close(d_value, k("d_value"), rtol=1e-4, atol=1e-9)
+    _close(d_logstd, k("d_logstd"), rtol=2e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("A,norm_adv,clip_vloss", [(2, True, False), (6, False, True)])
+def test_ppo_loss_kernel_against_the_numpy_oracle_at_minibatch_size(A, norm_adv, clip_vloss):
+    from rsoccer_isaac_cleanrl_b200.engine import PPO_STATS, ppo_loss
+    R, B = 524_288, 131_072
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    rn = lambda *s_: torch.randn(*s_, device="cuda", generator=gen)
+    b_act, b_adv, b_ret, b_val = rn(R, A), rn(R) * 3 - 1, rn(R), rn(R)
+    inds = torch.randperm(R, device="cuda", generator=gen)[:B]
+    mean, value = b_act[inds] + 0.4 * rn(B, A), (b_val[inds] + 0.5 * rn(B)).view(B, 1).contiguous()
+    logstd = torch.linspace(-0.6, 0.3, A, device="cuda")
+    b_lp = rn(R)
+    lp, _ = po.log_prob_and_entropy(mean.cpu().numpy(), logstd.cpu().numpy(), b_act[inds].cpu().numpy())
+    b_lp[inds] = torch.from_numpy(lp).float().cuda() + 0.2 * rn(B)
+    d_logstd = torch.zeros(A, device="cuda")
+    d_mean, d_value, st = ppo_loss(mean, value, logstd, b_act, b_lp, b_adv, b_ret, b_val, inds, 0.2, 0.005, 4.0,
+                                   norm_adv, clip_vloss, d_logstd)
+    c = lambda t: t.cpu().numpy()
+    r = po.ppo_loss(c(mean), c(value), c(logstd), c(b_act), c(b_lp), c(b_adv), c(b_ret), c(b_val), c(inds), 0.2, 0.005,
+                    4.0, norm_adv, clip_vloss)
+    for i, nm in enumerate(PPO_STATS):
+        tol = 8.0 / B if nm == "clipfrac" else 3e-6 + 5e-5 * abs(r[nm])
+        assert abs(st[i].item() - r[nm]) <= tol, (nm, st[i].item(), r[nm])
+    # element-wise: a ratio within fp32 rounding of the clip boundary may take the other branch
+    bad = (np.abs(c(d_mean) - r["d_mean"]) > 1e-9 + 2e-4 * np.abs(r["d_mean"])).any(1)
+    assert bad.mean() < 2e-5, bad.sum()
+    np.testing.assert_allclose(c(d_value).reshape(-1), r["d_value"], rtol=2e-4, atol=1e-10)
+    np.testing.assert_allclose(c(d_logstd), r["d_logstd"], rtol=5e-4, atol=1e-6)
+
+
+def test_clip_adam_kernel_against_the_numpy_oracle():
+    from rsoccer_isaac_cleanrl_b200.ppo import FlatAdam
+    n = 200_003
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    p = torch.randn(n, device="cuda", generator=gen)
+    grad = torch.zeros(n, device="cuda")
+    opt = FlatAdam(p.clone(), grad, lr=3e-4, eps=1e-5)
+    P, M, V, t = p.cpu().numpy().astype(np.float64), np.zeros(n), np.zeros(n), 0
+    for it in range(4):
+        g = torch.randn(n, device="cuda", generator=gen) * (3.0 if it < 2 else 1e-3)
+        grad.copy_(g)
+        opt.clip_and_step_fused(1.5, 0.25)
+        P, gc, M, V, t = po.clip_adam(P, g.cpu().numpy(), M, V, t, 3e-4, 1.5, grad_scale=0.25)
+        np.testing.assert_allclose(grad.cpu().numpy(), gc, rtol=2e-5, atol=1e-12)
+        np.testing.assert_allclose(opt.flat.cpu().numpy(), P, rtol=0, atol=3e-6)
