@@ -114,10 +114,14 @@ VSS_HD float bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 // Quick division / reciprocal square root for the contact code (2 ulp on the device; the physics is
 // compared with the fp64 oracle under a tolerance, unlike the rewards, which use the _rn forms above).
+// Without -ftz the CUDA intrinsics wrap every MUFU in denormal scaling (9 instructions per
+// division); the flush-to-zero forms are one MUFU (+ one FMUL), and no contact quantity is denormal.
 #if defined(__CUDA_ARCH__)
-VSS_HD float qdiv(float a, float b) { return __fdividef(a, b); }
-VSS_HD float qrsqrt(float a) { return rsqrtf(a); }
+VSS_HD float qrcp(float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
+VSS_HD float qdiv(float a, float b) { return a * qrcp(b); }
+VSS_HD float qrsqrt(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 #else
+VSS_HD float qrcp(float b) { return 1.0f / b; }
 VSS_HD float qdiv(float a, float b) { return a / b; }
 VSS_HD float qrsqrt(float a) { return 1.0f / sqrtf(a); }
 #endif
@@ -233,6 +237,30 @@ VSS_HD void resolve(Body& P, Body& Q, float nx, float ny, float depth, float cpx
     const float kt = wsum + rtp * rtp * P.invi + rtq * rtq * Q.invi + kt_extra;
     const float jt = clampf(qdiv(-vt, kt), -mu * jn, mu * jn);
     P.vx -= jt * tx * P.invm; P.vy -= jt * ty * P.invm; P.w -= jt * rtp * P.invi;
+    Q.vx += jt * tx * Q.invm; Q.vy += jt * ty * Q.invm; Q.w += jt * rtq * Q.invi;
+  }
+}
+
+// resolve() against a static body (walls, goal posts): Q is the dynamic body and the unit normal n
+// points from the wall into Q. Same impulse model with the wall's inverse mass and inertia taken
+// as the zeros they are (one division less and none of the dead arithmetic on the wall side; a
+// contact `resolve(R, wall, n)` with the robot on the P side is `resolve_static(R, -n)`).
+VSS_HD void resolve_static(Body& Q, float nx, float ny, float depth, float cpx, float cpy, float e1, float mu,
+                           float kt_extra) {
+  const float rqx = cpx - Q.x, rqy = cpy - Q.y;
+  Q.x += nx * depth; Q.y += ny * depth;
+  float vrx = Q.vx - Q.w * rqy, vry = Q.vy + Q.w * rqx;
+  const float vn = vrx * nx + vry * ny;
+  if (vn >= 0.0f) return;
+  const float rnq = rqx * ny - rqy * nx;
+  const float jn = qdiv(-e1 * vn, Q.invm + rnq * rnq * Q.invi);
+  Q.vx += jn * nx * Q.invm; Q.vy += jn * ny * Q.invm; Q.w += jn * rnq * Q.invi;
+  if (mu > 0.0f) {
+    const float tx = -ny, ty = nx;
+    vrx = Q.vx - Q.w * rqy; vry = Q.vy + Q.w * rqx;
+    const float vt = vrx * tx + vry * ty;
+    const float rtq = rqx * ty - rqy * tx;
+    const float jt = clampf(qdiv(-vt, Q.invm + rtq * rtq * Q.invi + kt_extra), -mu * jn, mu * jn);
     Q.vx += jt * tx * Q.invm; Q.vy += jt * ty * Q.invm; Q.w += jt * rtq * Q.invi;
   }
 }
@@ -353,14 +381,13 @@ VSS_HD void robot_robot(float* S, int i, int j, const DevParams& P) {
   store_robot(S, j, B);
 }
 
-// Point (rho = 0) or circle of body Q at local offset (lx,ly) against the static walls.
+// Circle of radius rho at the centre of body Q (the ball) against the static walls.
 // Three wall families, each resolved at once with the position re-evaluated.
-VSS_HD bool point_vs_walls(Body& Q, float lx, float ly, float rho, float mu, float kt_extra,
-                           const DevParams& P) {
+VSS_HD bool circle_vs_walls(Body& Q, float rho, float mu, float kt_extra, const DevParams& P) {
   bool any = false;
 #pragma unroll 1
   for (int pass = 0; pass < 3; ++pass) {
-    const float px = Q.x + lx * Q.c - ly * Q.s, py = Q.y + lx * Q.s + ly * Q.c;
+    const float px = Q.x, py = Q.y;
     const float ax = fabsf(px), ay = fabsf(py), sx = sgnf(px), sy = sgnf(py);
     float nx = 0.0f, ny = 0.0f, depth = 0.0f;
     bool hit = false;
@@ -387,8 +414,7 @@ VSS_HD bool point_vs_walls(Body& Q, float lx, float ly, float rho, float mu, flo
       if (ax > P.HL + P.GD - rho) { nx = -sx; ny = 0.0f; depth = ax - (P.HL + P.GD - rho); hit = true; }
     }
     if (hit) {
-      Body wall = static_body();
-      resolve(wall, Q, nx, ny, depth, px - nx * rho, py - ny * rho, P.e1, mu, kt_extra);
+      resolve_static(Q, nx, ny, depth, px - nx * rho, py - ny * rho, P.e1, mu, kt_extra);
       any = true;
     }
   }
@@ -404,23 +430,61 @@ VSS_HD bool robot_near_walls(const float* S, int r, const DevParams& P) {
 
 // Wall contacts of robot r of the field whose column starts at S. Touches only that robot, so
 // tasks of different (field, robot) pairs are independent and can run on any lane.
+// The four box corners are points (radius 0) tested against the same three wall families as the
+// ball, in the same order, each hit resolved at once and the corner re-evaluated: a point can only
+// touch the end-wall blocks or the goal back wall from |x| >= HL, so those two passes are skipped
+// for corners that are not there. Then the goal posts (+-HL, +-GH) against the box faces: a post
+// can only be inside the box if it is the one in the robot's own quadrant (the others are at
+// least 2 GH = 0.4 m away, the box's circumradius is 0.05 m).
 VSS_HD void robot_walls_task(float* S, int r, const DevParams& P) {
   Body R = load_robot(S, r, P);
   bool dirty = false;
+  // corner offsets in the world frame; contacts do not change the heading. Corners in the order
+  // (+,+) (-,+) (-,-) (+,-): each is the previous one rotated by 90 degrees.
+  float ox = P.H * R.c - P.H * R.s, oy = P.H * R.s + P.H * R.c;
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
-    float lx, ly;
-    corner_xy(k, P.H, lx, ly);
-    dirty |= point_vs_walls(R, lx, ly, 0.0f, P.mu_rw, 0.0f, P);
-  }
 #pragma unroll 1
-  for (int k = 0; k < 4; ++k) {  // goal-post corners (+-HL, +-GH) against the box faces
-    float cx, cy;
-    corner_xy(k, 1.0f, cx, cy);
-    const Hit h = circle_vs_box(R, P.H, cx * P.HL, cy * P.GH, 0.0f);
-    if (h.hit) {
-      Body wall = static_body();
-      resolve(R, wall, h.nx, h.ny, h.depth, h.cpx, h.cpy, P.e1, P.mu_rw, 0.0f);
+    for (int pass = 0; pass < 3; ++pass) {
+      const float px = R.x + ox, py = R.y + oy;
+      const float ax = fabsf(px), ay = fabsf(py);
+      float nx = 0.0f, ny = 0.0f, depth = 0.0f;
+      bool hit = false;
+      if (pass == 0) {  // side walls y = +-HW
+        if (ay > P.HW) { ny = -sgnf(py); depth = ay - P.HW; hit = true; }
+        else if (ax < P.HL) break;  // (side-wall hits never move the corner in x)
+      } else if (pass == 1) {  // end-wall blocks
+        if (ax >= P.HL && ay >= P.GH) {
+          const float dx = ax - P.HL, dy = ay - P.GH;
+          if (dx < dy) { nx = -sgnf(px); depth = dx; }
+          else { ny = -sgnf(py); depth = dy; }
+          hit = true;
+        }
+      } else {  // goal back wall
+        if (ax > P.HL + P.GD) { nx = -sgnf(px); depth = ax - (P.HL + P.GD); hit = true; }
+      }
+      if (hit) {
+        resolve_static(R, nx, ny, depth, px, py, P.e1, P.mu_rw, 0.0f);
+        dirty = true;
+      }
+    }
+    const float t = ox; ox = -oy; oy = t;
+  }
+  {  // the goal post of the robot's quadrant against the box faces
+    const float gx = R.x < 0.0f ? -P.HL : P.HL, gy = R.y < 0.0f ? -P.GH : P.GH;
+    const float dx = gx - R.x, dy = gy - R.y;
+    const float lx = dx * R.c + dy * R.s, ly = -dx * R.s + dy * R.c;
+    if (fabsf(lx) <= P.H && fabsf(ly) <= P.H) {  // face of least penetration
+      const float pxd = P.H - fabsf(lx), pyd = P.H - fabsf(ly);
+      float nlx, nly, depth;
+      if (pxd < pyd) { nlx = sgnf(lx); nly = 0.0f; depth = pxd; }
+      else { nlx = 0.0f; nly = sgnf(ly); depth = pyd; }
+      // the normal points out of the box towards the post: the robot is pushed the other way
+      const float nx = nlx * R.c - nly * R.s, ny = nlx * R.s + nly * R.c;
+      // contact point on the box face, as circle_vs_box reports it
+      const float clx = pxd < pyd ? sgnf(lx) * P.H : lx, cly = pxd < pyd ? ly : sgnf(ly) * P.H;
+      resolve_static(R, -nx, -ny, depth, R.x + clx * R.c - cly * R.s, R.y + clx * R.s + cly * R.c, P.e1, P.mu_rw,
+                     0.0f);
       dirty = true;
     }
   }
@@ -441,14 +505,6 @@ VSS_HD void sincos_small(float a, float& sa, float& ca) {
   sa = sinf(a); ca = cosf(a);
 #endif
 }
-VSS_HD float rsqrt_fast(float x) {
-#if defined(__CUDA_ARCH__)
-  return rsqrtf(x);
-#else
-  return 1.0f / sqrtf(x);
-#endif
-}
-
 // Phases A-B of a substep for one field plus the broadphase of phase C. Returns the 21-bit
 // candidate mask: bits 0-5 ball-robot r, bits 6-20 robot pairs in lexicographic order.
 VSS_HD uint32_t substep_integrate_lane(float* S, const DevParams& P) {
@@ -471,7 +527,7 @@ VSS_HD uint32_t substep_integrate_lane(float* S, const DevParams& P) {
     float sa, ca;
     sincos_small(w * P.h, sa, ca);
     const float c2 = c * ca - s * sa, s2 = s * ca + c * sa;
-    const float inv = rsqrt_fast(c2 * c2 + s2 * s2);
+    const float inv = qrsqrt(c2 * c2 + s2 * s2);
     b[0] = x; b[LDS] = y; b[2 * LDS] = vx; b[3 * LDS] = vy; b[4 * LDS] = c2 * inv; b[5 * LDS] = s2 * inv;
     b[6 * LDS] = w;
   }
@@ -542,7 +598,7 @@ VSS_HD bool ball_near_walls(const float* S, const DevParams& P) {
 }
 VSS_HD void ball_walls_task(float* S, const DevParams& P) {
   Body ball = load_ball(S, P);
-  if (point_vs_walls(ball, 0.0f, 0.0f, P.rb, P.mu_bw, 2.5f * P.inv_mb, P)) store_ball(S, ball);
+  if (circle_vs_walls(ball, P.rb, P.mu_bw, 2.5f * P.inv_mb, P)) store_ball(S, ball);
 }
 
 // Phases A-C of a substep for one field. Returns the 6-bit mask of robots that need the wall
@@ -880,41 +936,53 @@ VSS_HD void write_obs_tile(const float* T, const uint32_t* tab, int lane, int va
 }
 
 // Same result as write_obs_tile for layouts with at least 32 float4 per field (full contract: 78,
-// dma: 39), organised the other way round: lane l owns the float4 slots j = l, l+32, l+64 of EVERY
+// dma: 39), organised the other way round: lane l owns the float4 slots j = l, l+32 of EVERY
 // field, so its gather offsets and sign masks are loop-invariant registers and the loop over the
 // fields of the tile needs no index arithmetic or table look-ups (3x fewer instructions; the
 // observation write is the largest single consumer of issue slots in the step kernel). Each
-// warp-wide store still covers 512 contiguous bytes.
+// warp-wide store of a full slot covers 512 contiguous bytes. The slots left over after the full
+// ones (78 = 2 x 32 + 14, 39 = 32 + 7) are packed G fields to a store instruction: lane group g
+// (16 or 8 lanes wide) writes the tail of field e + g.
 template <int PER_FIELD>
 VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, int valid, float* tob, float* ob,
                                 uint32_t skip_mask) {
-  constexpr int SLOTS = (PER_FIELD + 31) / 32;
+  constexpr int FULL = PER_FIELD / 32, TAIL = PER_FIELD - 32 * FULL;
+  constexpr int TW = TAIL <= 1 ? 1 : TAIL <= 2 ? 2 : TAIL <= 4 ? 4 : TAIL <= 8 ? 8 : TAIL <= 16 ? 16 : 32;
+  constexpr int G = 32 / TW, SLOTS = FULL + (TAIL ? 1 : 0);
   int off[SLOTS][4];
   uint32_t sgn[SLOTS][4];
+  const int sub = lane / TW, jt = 32 * FULL + (lane % TW);
+  const bool tail_lane = TAIL && (lane % TW) < TAIL;
 #pragma unroll
   for (int sl = 0; sl < SLOTS; ++sl) {
-    const int j = lane + 32 * sl;
+    const int j = sl < FULL ? lane + 32 * sl : jt;
     const uint32_t entry = j < PER_FIELD ? tab[j] : 0u;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const uint32_t by = (entry >> (8 * c)) & 0xFFu;
-      off[sl][c] = (int)(by & 0x7Fu) * LDS;
+      off[sl][c] = (int)(by & 0x7Fu) * LDS + (sl < FULL ? 0 : sub);
       sgn[sl][c] = (by >> 7) << 31;
     }
   }
+  static_assert(G <= 4 && 4 % G == 0, "the tail packing assumes the field loop is unrolled by a multiple of G");
 #pragma unroll 4
   for (int e = 0; e < valid; ++e) {
     const bool keep = !((skip_mask >> e) & 1u);
 #pragma unroll
-    for (int sl = 0; sl < SLOTS; ++sl) {
-      const int j = lane + 32 * sl;
-      if (j < PER_FIELD) {
-        const F4 v{bitsf(fbits(T[off[sl][0] + e]) ^ sgn[sl][0]), bitsf(fbits(T[off[sl][1] + e]) ^ sgn[sl][1]),
-                   bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
-        const int idx = 4 * (e * PER_FIELD + j);
-        if (tob) st4_stream(tob + idx, v);
-        if (keep) st4_stream(ob + idx, v);
-      }
+    for (int sl = 0; sl < FULL; ++sl) {
+      const F4 v{bitsf(fbits(T[off[sl][0] + e]) ^ sgn[sl][0]), bitsf(fbits(T[off[sl][1] + e]) ^ sgn[sl][1]),
+                 bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
+      const int idx = 4 * (e * PER_FIELD + lane + 32 * sl);
+      if (tob) st4_stream(tob + idx, v);
+      if (keep) st4_stream(ob + idx, v);
+    }
+    if (TAIL && (e % G) == 0 && tail_lane && e + sub < valid) {  // fields e .. e+G-1, one lane group each
+      constexpr int sl = SLOTS - 1;
+      const F4 v{bitsf(fbits(T[off[sl][0] + e]) ^ sgn[sl][0]), bitsf(fbits(T[off[sl][1] + e]) ^ sgn[sl][1]),
+                 bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
+      const int idx = 4 * ((e + sub) * PER_FIELD + jt);
+      if (tob) st4_stream(tob + idx, v);
+      if (!((skip_mask >> (e + sub)) & 1u)) st4_stream(ob + idx, v);
     }
   }
 }

@@ -360,6 +360,51 @@ def check_chase_stress(Backend, n=2048, steps=150, seed=7):
     assert np.abs(st[0]).max() <= 0.85 + 1e-5 and np.abs(st[1]).max() <= 0.65 + 1e-5
 
 
+def check_wall_stress(Backend, n=4096, steps=6, seed=11):
+    """Every robot and the ball start within reach of a wall family (side walls, end-wall blocks,
+    goal side walls, goal back wall, goal posts), moving into it: exercises the specialised
+    point-vs-wall and post-vs-box code against the oracle's generic version, one control step at a
+    time from identical states."""
+    be, p = make_backend_pair(Backend, n, seed, 0)
+    rng = np.random.default_rng(seed)
+    rb = np.ones(n, np.int64)
+    be.reset_dones(rb)
+    rb[:] = 0
+    s = be.get_state()
+    kind = np.arange(n) % 4
+    sx = rng.choice([-1.0, 1.0], (7, n)); sy = rng.choice([-1.0, 1.0], (7, n))
+    for e in range(7):  # entity 0 = ball, 1..6 = robots
+        b = 0 if e == 0 else 4 + 9 * (e - 1)
+        reach = 0.03 if e == 0 else 0.06
+        # 0: side wall; 1: end wall outside the goal mouth; 2: goal mouth / posts / goal side walls; 3: inside the goal
+        x = np.select([kind == 0, kind == 1, kind == 2, kind == 3],
+                      [rng.uniform(-0.7, 0.7, n), 0.75 - rng.uniform(0, reach, n), 0.75 + rng.uniform(-reach, 0.02, n),
+                       0.85 - rng.uniform(0, reach, n)])
+        y = np.select([kind == 0, kind == 1, kind == 2, kind == 3],
+                      [0.65 - rng.uniform(0, reach, n), rng.uniform(0.25, 0.6, n), 0.2 + rng.uniform(-reach, reach, n),
+                       rng.uniform(0.0, 0.19 - 0.04, n)])
+        s[b, :n] = sx[e] * x; s[b + 1, :n] = sy[e] * y
+        s[b + 2, :n] = sx[e] * rng.uniform(-0.2, 1.2, n); s[b + 3, :n] = sy[e] * rng.uniform(-0.2, 1.2, n)
+        if e:
+            yaw = rng.uniform(-np.pi, np.pi, n)
+            s[b + 4, :n] = np.cos(yaw); s[b + 5, :n] = np.sin(yaw); s[b + 6, :n] = rng.uniform(-20, 20, n)
+    # keep the robots of one field apart (different wall stretches) so that this check is about walls:
+    # robots 1..6 of a field get distinct signs / offsets along the wall where possible
+    be.set_state(s)
+    flips = 0
+    for t in range(steps):
+        st = oracle_from_backend(be)
+        rb_ref = rb.copy()
+        actions = rng.uniform(-1.0, 1.0, (n, 2, 3, 2)).astype(np.float32)
+        out = be.step(actions, rb)
+        ref = orc.step(p, seed, 0, st, actions, rb_ref)
+        flips += compare_full_step(out, ref, rb, rb_ref, n, f"wall stress step {t}", exact_physics=False)
+        got = oracle_from_backend(be)
+        assert np.abs(got.ball_pos[:, 0]).max() <= 0.85 + 1e-5 and np.abs(got.ball_pos[:, 1]).max() <= 0.65 + 1e-5
+    assert flips <= max(2, 2 * FLIP_FRACTION * n * steps), f"{flips} field-steps outside the physics tolerance"
+    return flips
+
+
 def check_nonfinite_guard(Backend, n=96):
     """Safety net: a field whose state is not finite is re-randomised on the spot, reported done with
     zero reward and no timeout; its neighbours are untouched; backend and oracle agree."""

@@ -45,3 +45,7 @@ def test_nonfinite_state_guard():
 
 def test_contact_heavy_rollout_stays_finite():
     pc.check_chase_stress(EmuBackend)
+
+
+def test_wall_and_goal_post_contacts_track_oracle():
+    print("flips", pc.check_wall_stress(EmuBackend))

@@ -148,3 +148,7 @@ def test_nonfinite_state_guard(Gpu):
 
 def test_contact_heavy_rollout_stays_finite(Gpu):
     pc.check_chase_stress(Gpu, n=65536, steps=300)
+
+
+def test_wall_and_goal_post_contacts_track_oracle(Gpu):
+    pc.check_wall_stress(Gpu, n=8192, steps=6)
