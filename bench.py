@@ -237,7 +237,7 @@ def run_native(args):
                 "traffic": traffic, "kernel": "k_step<full>", "algorithmic_bytes_per_launch": BYTES_PER_FIELD_STEP * n,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"}
 
-    launches = 2 * args.steps  # timed region: K x (k_step + the 1-thread k_bump that advances the step index)
+    launches = args.steps  # timed region: K x k_step (its last CTA advances the device-resident step index)
 
     # ---- GAE reverse scan (BASELINE roofline row: 28 B per (t, env)), T = 128, N = 65536
     gae_res = None

@@ -29,8 +29,13 @@
 #define VSS_HD_COLD inline
 #endif
 
+#ifndef VSS_INTEG_UNROLL
+#define VSS_INTEG_UNROLL 2  // robots integrated side by side per lane (instruction-level parallelism vs code size)
+#endif
+
 namespace vss {
 
+constexpr int INTEG_UNROLL = VSS_INTEG_UNROLL;
 constexpr int LDS = 33;       // shared-memory column stride in words
 constexpr int W_PREV = 60;    // 7 words of pre-physics reward terms: ball potential, 6 robot-ball distances
 constexpr int SM_WORDS = 67;  // words per field staged in shared memory
@@ -267,13 +272,12 @@ VSS_HD void resolve_static(Body& Q, float nx, float ny, float depth, float cpx, 
 
 struct Hit { bool hit; float nx, ny, depth, cpx, cpy; };
 
-// Circle (centre px,py, radius rho; rho = 0 -> point) against the oriented box of B.
-// Normal points out of B towards the circle.
-VSS_HD Hit circle_vs_box(const Body& B, float H, float px, float py, float rho) {
+// Circle (centre (lx,ly) in the frame of box B, radius rho; rho = 0 -> point) against the oriented
+// box of B. Normal (world frame) points out of B towards the circle.
+struct Pose { float x, y, c, s; };
+VSS_HD Hit circle_vs_box_local(const Pose& B, float H, float lx, float ly, float rho) {
   Hit r;
   r.hit = false; r.nx = r.ny = r.depth = r.cpx = r.cpy = 0.0f;
-  const float dx = px - B.x, dy = py - B.y;
-  const float lx = dx * B.c + dy * B.s, ly = -dx * B.s + dy * B.c;
   float nlx, nly, clx, cly;
   bool face = fabsf(lx) <= H && fabsf(ly) <= H;  // centre inside (or exactly on) the box
   if (!face) {
@@ -297,6 +301,11 @@ VSS_HD Hit circle_vs_box(const Body& B, float H, float px, float py, float rho) 
   r.nx = nlx * B.c - nly * B.s; r.ny = nlx * B.s + nly * B.c;
   r.cpx = B.x + clx * B.c - cly * B.s; r.cpy = B.y + clx * B.s + cly * B.c;
   return r;
+}
+// The same with the circle's centre (px,py) given in the world frame.
+VSS_HD Hit circle_vs_box(const Body& B, float H, float px, float py, float rho) {
+  const float dx = px - B.x, dy = py - B.y;
+  return circle_vs_box_local(Pose{B.x, B.y, B.c, B.s}, H, dx * B.c + dy * B.s, -dx * B.s + dy * B.c, rho);
 }
 
 VSS_HD void corner_xy(int k, float H, float& lx, float& ly) {
@@ -337,6 +346,27 @@ VSS_HD uint32_t features_in_box(float lx, float ly, float cr, float sr, const De
   return hits;
 }
 
+// Hits of the features of F flagged in `mask` (4 corners, or 2 wheel circles if `wheels`) against
+// the box of G. (lx,ly) = F's centre and (cr,sr) = F's rotation in G's frame at entry, (f0x,f0y) and
+// (g0x,g0y) the entry positions; the penetration of each hit is reduced by the separation already
+// gained along its normal.
+VSS_HD void rr_hits(Body& F, Body& G, float f0x, float f0y, float g0x, float g0y, float lx, float ly, float cr,
+                    float sr, uint32_t mask, bool wheels, const DevParams& P) {
+  const Pose G0{g0x, g0y, G.c, G.s};  // (contacts move a body but do not turn it)
+  while (mask) {
+    const int q = ffs32(mask) - 1;
+    mask &= mask - 1;
+    float fx, fy, rho;  // the feature in F's own frame
+    if (wheels) { fx = 0.0f; fy = q ? -P.b : P.b; rho = P.rwc; }
+    else { corner_xy(q, P.H, fx, fy); rho = 0.0f; }
+    const Hit h = circle_vs_box_local(G0, P.H, lx + (fx * cr - fy * sr), ly + (fx * sr + fy * cr), rho);
+    if (h.hit) {
+      const float gained = ((F.x - f0x) - (G.x - g0x)) * h.nx + ((F.y - f0y) - (G.y - g0y)) * h.ny;
+      resolve(G, F, h.nx, h.ny, fmaxf(h.depth - gained, 0.0f), h.cpx, h.cpy, P.e1, 0.0f, 0.0f);
+    }
+  }
+}
+
 // Robot-robot contact. The 12 features — corners of A in B, corners of B in A,
 // wheels of A, wheels of B — are all tested against the poses at entry (one snapshot); the hits
 // are then resolved in that order, each penetration reduced by the separation already gained
@@ -356,26 +386,14 @@ VSS_HD void robot_robot(float* S, int i, int j, const DevParams& P) {
   }
   const uint32_t ha = features_in_box(lxb, lyb, cd, sd, P);   // features of A against box B
   const uint32_t hb = features_in_box(lxa, lya, cd, -sd, P);  // features of B against box A
-  // order: A corners (0-3), B corners (4-7), A wheels (8,9), B wheels (10,11)
-  uint32_t hits = (ha & 15u) | ((hb & 15u) << 4) | ((ha >> 4) << 8) | ((hb >> 4) << 10);
-  if (!hits) return;
-  const Body A0 = A, B0 = B;
-  while (hits) {
-    const int k = ffs32(hits) - 1;
-    hits &= hits - 1;
-    const bool a_owns = (k < 8) ? (k < 4) : (k < 10);
-    float lx, ly, rho;
-    if (k < 8) { corner_xy(k & 3, P.H, lx, ly); rho = 0.0f; }
-    else { lx = 0.0f; ly = (k & 1) ? -P.b : P.b; rho = P.rwc; }
-    const Body F0 = a_owns ? A0 : B0, G0 = a_owns ? B0 : A0;
-    const float px = F0.x + lx * F0.c - ly * F0.s, py = F0.y + lx * F0.s + ly * F0.c;
-    const Hit h = circle_vs_box(G0, P.H, px, py, rho);
-    if (h.hit) {
-      Body F = a_owns ? A : B, G = a_owns ? B : A;
-      const float gained = ((F.x - F0.x) - (G.x - G0.x)) * h.nx + ((F.y - F0.y) - (G.y - G0.y)) * h.ny;
-      resolve(G, F, h.nx, h.ny, fmaxf(h.depth - gained, 0.0f), h.cpx, h.cpy, P.e1, 0.0f, 0.0f);
-      if (a_owns) { A = F; B = G; } else { B = F; A = G; }
-    }
+  if (!(ha | hb)) return;
+  // resolution order: A corners, B corners, A wheels, B wheels. Feature positions are taken in the
+  // box's frame straight from the relative pose of the entry snapshot (as features_in_box did).
+  const float a0x = A.x, a0y = A.y, b0x = B.x, b0y = B.y;
+#pragma unroll 1
+  for (int w = 0; w < 2; ++w) {
+    rr_hits(A, B, a0x, a0y, b0x, b0y, lxb, lyb, cd, sd, w ? ha >> 4 : ha & 15u, w != 0, P);
+    rr_hits(B, A, b0x, b0y, a0x, a0y, lxa, lya, cd, -sd, w ? hb >> 4 : hb & 15u, w != 0, P);
   }
   store_robot(S, i, A);
   store_robot(S, j, B);
@@ -444,28 +462,31 @@ VSS_HD void robot_walls_task(float* S, int r, const DevParams& P) {
   float ox = P.H * R.c - P.H * R.s, oy = P.H * R.s + P.H * R.c;
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
+    // a corner inside |x| < HL, |y| <= HW touches nothing (most corners of most tasks); hits only push
+    // it further inside, so the test need not be repeated between the passes
+    if (fabsf(R.y + oy) > P.HW || fabsf(R.x + ox) >= P.HL) {
 #pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-      const float px = R.x + ox, py = R.y + oy;
-      const float ax = fabsf(px), ay = fabsf(py);
-      float nx = 0.0f, ny = 0.0f, depth = 0.0f;
-      bool hit = false;
-      if (pass == 0) {  // side walls y = +-HW
-        if (ay > P.HW) { ny = -sgnf(py); depth = ay - P.HW; hit = true; }
-        else if (ax < P.HL) break;  // (side-wall hits never move the corner in x)
-      } else if (pass == 1) {  // end-wall blocks
-        if (ax >= P.HL && ay >= P.GH) {
-          const float dx = ax - P.HL, dy = ay - P.GH;
-          if (dx < dy) { nx = -sgnf(px); depth = dx; }
-          else { ny = -sgnf(py); depth = dy; }
-          hit = true;
+      for (int pass = 0; pass < 3; ++pass) {  // uniform trip count: the lanes of a warp stay together
+        const float px = R.x + ox, py = R.y + oy;
+        const float ax = fabsf(px), ay = fabsf(py);
+        float nx = 0.0f, ny = 0.0f, depth = 0.0f;
+        bool hit = false;
+        if (pass == 0) {  // side walls y = +-HW
+          if (ay > P.HW) { ny = -sgnf(py); depth = ay - P.HW; hit = true; }
+        } else if (pass == 1) {  // end-wall blocks [HL,inf) x [GH,inf) per quadrant
+          if (ax >= P.HL && ay >= P.GH) {
+            const float dx = ax - P.HL, dy = ay - P.GH;
+            if (dx < dy) { nx = -sgnf(px); depth = dx; }
+            else { ny = -sgnf(py); depth = dy; }
+            hit = true;
+          }
+        } else {  // goal back wall x = +-(HL+GD)
+          if (ax > P.HL + P.GD) { nx = -sgnf(px); depth = ax - (P.HL + P.GD); hit = true; }
         }
-      } else {  // goal back wall
-        if (ax > P.HL + P.GD) { nx = -sgnf(px); depth = ax - (P.HL + P.GD); hit = true; }
-      }
-      if (hit) {
-        resolve_static(R, nx, ny, depth, px, py, P.e1, P.mu_rw, 0.0f);
-        dirty = true;
+        if (hit) {
+          resolve_static(R, nx, ny, depth, px, py, P.e1, P.mu_rw, 0.0f);
+          dirty = true;
+        }
       }
     }
     const float t = ox; ox = -oy; oy = t;
@@ -509,7 +530,7 @@ VSS_HD void sincos_small(float a, float& sa, float& ca) {
 // candidate mask: bits 0-5 ball-robot r, bits 6-20 robot pairs in lexicographic order.
 VSS_HD uint32_t substep_integrate_lane(float* S, const DevParams& P) {
   // A. wheel drive + integration
-#pragma unroll 2
+#pragma unroll(INTEG_UNROLL)
   for (int r = 0; r < 6; ++r) {
     float* b = S + (4 + 9 * r) * LDS;
     float x = b[0], y = b[LDS], vx = b[2 * LDS], vy = b[3 * LDS], c = b[4 * LDS], s = b[5 * LDS];
@@ -743,8 +764,13 @@ constexpr int VIEW_FULL = -1;
 struct StepArgs {
   float* state; long long n, ld; unsigned long long goff;
   uint32_t seed_lo, seed_hi;
-  const uint32_t* step_ptr;    // device-resident step index (keys the OU stream); bumped after every step so
-                               // that a CUDA graph replaying the launch still advances it
+  // Device-resident step index (keys the OU stream), kept as the number of step-kernel CTAs that have
+  // finished over the engine's life: every launch of an engine has the same grid, launches are
+  // stream-ordered, so at any time inside launch k the counter is in [k grid, (k+1) grid) and
+  // step = counter / grid. Every CTA adds 1 when it is done (fire-and-forget), so a CUDA graph that
+  // replays the launch still advances the index and no second kernel is needed.
+  unsigned long long* step_ctr;
+  uint32_t grid;
   const float* actions;        // full: (N,2,3,2)
   const float* inject;         // injected post-physics state (58 x ld) or null
   long long* reset_buf;        // (N) io
@@ -764,6 +790,14 @@ struct ViewShape {
   static constexpr int F4_PER = VIEW == VIEW_FULL ? F4_PER_FIELD : (VIEW == VSS_VIEW_DMA ? 3 * F4_PER_ROW : F4_PER_ROW);
   static constexpr int AGENTS = VIEW == VSS_VIEW_DMA ? 3 : 1;  // view "envs" per field
 };
+
+VSS_HD uint32_t step_index(const StepArgs& a) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)(__ldcg(a.step_ctr) / a.grid);  // read at L2, where the other CTAs' adds land
+#else
+  return (uint32_t)(*a.step_ctr / a.grid);
+#endif
+}
 
 VSS_HD RngKey make_key(const StepArgs& a, long long env) {
   const unsigned long long gid = a.goff + (unsigned long long)env;
@@ -797,7 +831,7 @@ VSS_HD void lane_phase1a(float* S, long long env, const StepArgs& a, const DevPa
     }
   }
   if (VIEW != VIEW_FULL) {
-    ou_lane(act, P, key, *a.step_ptr);  // action_buf = random_ou(action_buf)
+    ou_lane(act, P, key, step_index(a));  // action_buf = random_ou(action_buf)
     if (VIEW == VSS_VIEW_SA) {     // act_view[:] = action
       act[0] = a.policy_action[2 * env]; act[1] = a.policy_action[2 * env + 1];
     } else {  // cma (N,6) and dma (3N,2): the same 6 contiguous floats per field

@@ -162,21 +162,35 @@ __device__ __forceinline__ void physics_cta(float* tiles, uint32_t* queue, uint3
   }
 }
 
-template <int VIEW, bool INJECT, bool SYNC>
+// The last warp of a CTA to finish counts the CTA as done (StepArgs::step_ctr): every warp of the CTA
+// has read the step index (phase 1a) by then. No return value is used, so the add is fire-and-forget.
+__device__ __forceinline__ void step_done(const StepArgs& a, uint32_t* ctr) {
+#ifdef VSS_NO_STEP_DONE  // timing experiment only: the step index does not advance
+  return;
+#endif
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0 && atomicAdd(&ctr[3], 1u) == (blockDim.x >> 5) - 1u) atomicAdd(a.step_ctr, 1ull);
+}
+
+// SYNC: 0 = warps run free; 1 = CTA-wide barriers at substep / phase boundaries; 2 = 1 + the
+// contact phases as CTA-wide task queues (physics_cta). Separate instantiations so that the default
+// kernel does not carry the queue variant's copy of the contact code.
+template <int VIEW, bool INJECT, int SYNC>
 __global__ void __launch_bounds__(384)
 k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) {
   extern __shared__ __align__(16) float smem[];
   uint32_t* tab = reinterpret_cast<uint32_t*>(smem);
   for (int i = threadIdx.x; i < F4_PER_FIELD; i += blockDim.x) tab[i] = c_obs_table.v[i];
+  float* tiles = smem + TAB_WORDS;
+  uint32_t* queue = reinterpret_cast<uint32_t*>(tiles + (blockDim.x >> 5) * TILE_STATE_WORDS);
+  uint32_t* ctr = queue + (blockDim.x >> 5) * QUEUE_WORDS;
+  if (threadIdx.x == 0) ctr[3] = 0u;  // warps of this CTA that have finished
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long env0 = tile * 32;
-  if (!SYNC && env0 >= a.n) return;  // (with block-level syncs every warp must stay until the end)
-  float* tiles = smem + TAB_WORDS;
+  if (!SYNC && env0 >= a.n) { step_done(a, ctr); return; }  // (with block-level syncs every warp stays until the end)
   float* T = tiles + warp * TILE_STATE_WORDS;
-  uint32_t* queue = reinterpret_cast<uint32_t*>(tiles + (blockDim.x >> 5) * TILE_STATE_WORDS);
-  uint32_t* ctr = queue + (blockDim.x >> 5) * QUEUE_WORDS;
   float* S = T + lane;
   const long long env = env0 + lane;
   const bool active = env < a.n;
@@ -186,8 +200,8 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   // 1. per lane: load, actions, physics, rewards, dones
   if (active) lane_phase1a<VIEW>(S, env, a, P, key);
   if (INJECT) { if (active) lane_inject(S, env, a); }
-  else if (SYNC && a.sync_level >= 4) physics_cta(tiles, queue, ctr, active, P);
-  else physics_tile<SYNC>(T, reinterpret_cast<uint8_t*>(queue + warp * QUEUE_WORDS), lane, active, P, a.sync_level);
+  else if (SYNC == 2) physics_cta(tiles, queue, ctr, active, P);
+  else physics_tile<SYNC != 0>(T, reinterpret_cast<uint8_t*>(queue + warp * QUEUE_WORDS), lane, active, P, a.sync_level);
   if (SYNC) __syncthreads();
   int code = LANE_RUNNING;
   if (active) code = lane_phase1d<VIEW>(S, env, a, P, key);
@@ -209,10 +223,8 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   // 5. state out
   if (SYNC && a.sync_level >= 2) __syncthreads();
   if (active) lane_phase5<VIEW>(S, env, a, code != LANE_RUNNING);
+  step_done(a, ctr);
 }
-
-// Advances the device-resident step index after a step (stream-ordered, so graph replays see it).
-__global__ void k_bump(uint32_t* ctr) { *ctr += 1u; }
 
 // reset_dones() + compute_observations(): vss.py:72-73, 267-333, 205-216
 __global__ void __launch_bounds__(384)
@@ -300,7 +312,7 @@ struct vss_engine {
   int device;
   int64_t n, ld, goff;
   uint64_t seed;
-  uint32_t* d_step;  // device-resident step index
+  unsigned long long* d_step;  // device-resident step index, as finished step-kernel CTAs (StepArgs::step_ctr)
   vss_params params;
   DevParams dp;
   float* state;
@@ -358,7 +370,7 @@ static StepArgs base_args(vss_handle h) {
   StepArgs a;
   memset(&a, 0, sizeof(a));
   a.state = h->state; a.n = h->n; a.ld = h->ld; a.goff = (unsigned long long)h->goff;
-  a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.step_ptr = h->d_step;
+  a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.step_ctr = h->d_step;
   return a;
 }
 
@@ -367,16 +379,17 @@ static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
   int wpb, sync_phases; unsigned grid; size_t smem;
   launch_cfg(h->n, &wpb, &grid, &smem, &sync_phases);
   const_cast<StepArgs&>(a).sync_level = sync_phases;
+  const_cast<StepArgs&>(a).grid = grid;
   static bool big_smem_ok = false;
   if (smem > 48 * 1024 && !big_smem_ok) {
-    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     big_smem_ok = true;
   }
-  if (sync_phases && wpb > 1) k_step<VIEW, INJECT, true><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
-  else k_step<VIEW, INJECT, false><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
-  VSS_CUDA(cudaGetLastError());
-  k_bump<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_step);
+  if (sync_phases >= 4 && wpb > 1 && !INJECT) k_step<VIEW, INJECT, 2><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
+  else if (sync_phases && wpb > 1) k_step<VIEW, INJECT, 1><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
+  else k_step<VIEW, INJECT, 0><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
   VSS_CUDA(cudaGetLastError());
   return VSS_OK;
 }
@@ -431,8 +444,8 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
   e = cudaMalloc(&h->state, bytes);
   if (e != cudaSuccess) { delete h; return fail(VSS_E_NOMEM, "vss_create: cudaMalloc(state)", e); }
   e = cudaMemset(h->state, 0, bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_step, sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemset(h->d_step, 0, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_step, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_step, 0, sizeof(unsigned long long));
   if (e != cudaSuccess) { cudaFree(h->state); cudaFree(h->d_step); delete h; return fail(VSS_E_CUDA, "vss_create: cudaMemset", e); }
   *out = h;
   return VSS_OK;
@@ -451,15 +464,19 @@ VSS_API int64_t vss_state_ld(vss_handle h) { return h ? h->ld : 0; }
 // The counter lives on the device; these two synchronise (tests / checkpointing only).
 VSS_API uint64_t vss_step_count(vss_handle h) {
   if (!h) return 0;
-  uint32_t v = 0;
+  unsigned long long v = 0;
   if (use_device(h) != VSS_OK) return 0;
   if (cudaMemcpy(&v, h->d_step, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-  return v;
+  int wpb; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem);
+  return v / grid;
 }
 VSS_API int vss_set_step_count(vss_handle h, uint64_t n) {
   if (!h) return fail(VSS_E_INVALID, "null handle");
   if (int rc = use_device(h)) return rc;
-  const uint32_t v = (uint32_t)n;
+  int wpb; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem);
+  const unsigned long long v = (unsigned long long)(uint32_t)n * grid;
   VSS_CUDA(cudaMemcpy(h->d_step, &v, sizeof(v), cudaMemcpyHostToDevice));
   return VSS_OK;
 }

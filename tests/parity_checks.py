@@ -405,6 +405,50 @@ def check_wall_stress(Backend, n=4096, steps=6, seed=11):
     return flips
 
 
+def check_pair_stress(Backend, n=4096, steps=6, seed=13):
+    """Robots start in touching / overlapping pairs and triples (corner-in-box, wheel-in-box, box
+    on box at every relative heading) with the ball wedged between some of them: exercises the
+    robot-robot feature code and the ball-robot code against the oracle from identical states."""
+    be, p = make_backend_pair(Backend, n, seed, 0)
+    rng = np.random.default_rng(seed)
+    rb = np.ones(n, np.int64)
+    be.reset_dones(rb)
+    rb[:] = 0
+    s = be.get_state()
+    cx = rng.uniform(-0.5, 0.5, (3, n)); cy = rng.uniform(-0.45, 0.45, (3, n))   # three cluster centres per field
+    for r in range(6):
+        b = 4 + 9 * r
+        g = r // 2 if True else 0
+        d = rng.uniform(0.02, 0.06, n) * np.where(np.arange(n) % 3 == 0, 1.0, 0.75)
+        ang = rng.uniform(-np.pi, np.pi, n)
+        s[b, :n] = cx[g] + (d * np.cos(ang) if r % 2 else 0.0)
+        s[b + 1, :n] = cy[g] + (d * np.sin(ang) if r % 2 else 0.0)
+        s[b + 2, :n] = rng.uniform(-1.0, 1.0, n); s[b + 3, :n] = rng.uniform(-1.0, 1.0, n)
+        yaw = rng.uniform(-np.pi, np.pi, n)
+        s[b + 4, :n] = np.cos(yaw); s[b + 5, :n] = np.sin(yaw); s[b + 6, :n] = rng.uniform(-25, 25, n)
+    # every fourth field: robots 4 and 5 join cluster 0 (triple contact)
+    t3 = np.arange(n) % 4 == 0
+    for r in (4, 5):
+        b = 4 + 9 * r
+        s[b, :n] = np.where(t3, cx[0] + rng.uniform(-0.08, 0.08, n), s[b, :n])
+        s[b + 1, :n] = np.where(t3, cy[0] + rng.uniform(-0.08, 0.08, n), s[b + 1, :n])
+    # the ball next to cluster 1
+    s[0, :n] = cx[1] + rng.uniform(-0.07, 0.07, n); s[1, :n] = cy[1] + rng.uniform(-0.07, 0.07, n)
+    s[2, :n] = rng.uniform(-1.5, 1.5, n); s[3, :n] = rng.uniform(-1.5, 1.5, n)
+    be.set_state(s)
+    flips = 0
+    for t in range(steps):
+        st = oracle_from_backend(be)
+        rb_ref = rb.copy()
+        actions = rng.uniform(-1.0, 1.0, (n, 2, 3, 2)).astype(np.float32)
+        out = be.step(actions, rb)
+        ref = orc.step(p, seed, 0, st, actions, rb_ref)
+        flips += compare_full_step(out, ref, rb, rb_ref, n, f"pair stress step {t}", exact_physics=False)
+    # deep initial overlaps are resolved through many near-degenerate branches: a looser flip budget
+    assert flips <= max(2, 4 * FLIP_FRACTION * n * steps), f"{flips} field-steps outside the physics tolerance"
+    return flips
+
+
 def check_nonfinite_guard(Backend, n=96):
     """Safety net: a field whose state is not finite is re-randomised on the spot, reported done with
     zero reward and no timeout; its neighbours are untouched; backend and oracle agree."""

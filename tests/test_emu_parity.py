@@ -49,3 +49,7 @@ def test_contact_heavy_rollout_stays_finite():
 
 def test_wall_and_goal_post_contacts_track_oracle():
     print("flips", pc.check_wall_stress(EmuBackend))
+
+
+def test_robot_pair_contacts_track_oracle():
+    print("flips", pc.check_pair_stress(EmuBackend))

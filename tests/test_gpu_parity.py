@@ -152,3 +152,7 @@ def test_contact_heavy_rollout_stays_finite(Gpu):
 
 def test_wall_and_goal_post_contacts_track_oracle(Gpu):
     pc.check_wall_stress(Gpu, n=8192, steps=6)
+
+
+def test_robot_pair_contacts_track_oracle(Gpu):
+    pc.check_pair_stress(Gpu, n=8192, steps=6)
