@@ -243,16 +243,20 @@ def run_native(args):
     gae_res = None
     if world == 1:
         from rsoccer_isaac_cleanrl_b200.engine import gae as gae_kernel
-        Tn, Nn = 128, 65536
-        gin = [torch.randn((Tn, Nn), device="cuda") for _ in range(3)]
-        gd = (torch.rand((Tn, Nn), device="cuda") < 0.01).float()
-        gto = gd * (torch.rand((Tn, Nn), device="cuda") < 0.5).float()
-        adv, ret = torch.empty_like(gd), torch.empty_like(gd)
-        # 7 x 33.5 MB per call = 235 MB: larger than L2, so consecutive calls do not hit in cache
-        ms_g = time_steps(torch, dist, 1, lambda i: gae_kernel(*gin, gd, gto, 0.99, 0.95, adv, ret), 50, 5)
-        gbs = 28.0 * Tn * Nn / (ms_g * 1e-3 / 50) / 1e9
-        gae_res = {"elements_per_s": Tn * Nn * 50 / (ms_g * 1e-3), "us_per_call": ms_g * 1e3 / 50, "achieved_gbs": gbs,
-                   "frac": gbs / peak, "workload": f"vss_gae T={Tn} N={Nn}, 28 B per (t, env)"}
+        # two sizes: T=128 x 65536 columns (configs[3] read as 65 536 agents: 235 MB per call, latency and
+        # launch ramp still visible) and T=128 x 196608 (65 536 dma fields = 196 608 agents: 705 MB per call)
+        gae_res = []
+        for Tn, Nn in ((128, 65536), (128, 196608)):
+            gin = [torch.randn((Tn, Nn), device="cuda") for _ in range(3)]
+            gd = (torch.rand((Tn, Nn), device="cuda") < 0.01).float()
+            gto = gd * (torch.rand((Tn, Nn), device="cuda") < 0.5).float()
+            adv, ret = torch.empty_like(gd), torch.empty_like(gd)
+            # >= 235 MB per call: larger than L2, so consecutive calls do not hit in cache
+            ms_g = time_steps(torch, dist, 1, lambda i: gae_kernel(*gin, gd, gto, 0.99, 0.95, adv, ret), 50, 5)
+            gbs = 28.0 * Tn * Nn / (ms_g * 1e-3 / 50) / 1e9
+            gae_res.append({"elements_per_s": Tn * Nn * 50 / (ms_g * 1e-3), "us_per_call": ms_g * 1e3 / 50,
+                            "achieved_gbs": gbs, "frac": gbs / peak,
+                            "workload": f"vss_gae T={Tn} N={Nn}, 28 B per (t, env)"})
         del gin, gd, gto, adv, ret
     # ---- e2e: the user-facing call with HOST buffers (SingleAgent view): pinned policy action ->
     #      device, fused view step, view obs/reward/done -> pinned host, every step.

@@ -188,9 +188,10 @@ VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, fl
  * (VSS_STATE_WORDS x ld 32-bit words) device->device. */
 VSS_API int vss_get_state(vss_handle h, float* state_out, void* stream);
 VSS_API int vss_set_state(vss_handle h, const float* state_in, void* stream);
-/* number of steps executed so far (keys the OU-noise RNG). The counter is device-resident and
- * advanced by a stream-ordered kernel after every step, so CUDA-graph replays of a captured
- * vss_step / vss_step_view launch advance it too; these two calls synchronise with the device. */
+/* number of vss_step_view launches executed so far (keys the OU-noise RNG of the views; vss_step
+ * draws no noise and does not advance it). The counter is device-resident and advanced by the step
+ * kernel itself, so CUDA-graph replays of a captured vss_step_view launch advance it too; these two
+ * calls synchronise with the device. */
 VSS_API uint64_t vss_step_count(vss_handle h);
 VSS_API int vss_set_step_count(vss_handle h, uint64_t n);
 
