@@ -68,9 +68,12 @@ __device__ __forceinline__ void physics_tile(float* T, uint8_t* queue, int lane,
       queue[pos++] = (uint8_t)((lane << 3) | r);
     }
     if (SYNC && sync_level >= 3) __syncthreads(); else __syncwarp();
-    for (int t = lane; t < total; t += 32) {
-      const int q = queue[t];
-      robot_walls_task(T + (q >> 3), q & 7, P);
+#pragma unroll 1
+    for (int t0 = 0; t0 < total; t0 += 32) {  // warp-uniform trip count: usually one pass, rarely more
+      if (t0 + lane < total) {
+        const int q = queue[t0 + lane];
+        robot_walls_task(T + (q >> 3), q & 7, P);
+      }
     }
     if (SYNC && sync_level >= 3) __syncthreads(); else __syncwarp();
     if (active) substep_ball_walls_lane(S, P);
