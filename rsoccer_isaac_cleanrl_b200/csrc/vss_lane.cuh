@@ -790,6 +790,7 @@ struct StepArgs {
   // view mode only
   const float* policy_action; float* action_buf; float* reward_v; long long* done_v;
   float* ep_ret; int* ep_len; float* ret_ret; int* ret_len;
+  int stagger_ns;              // first-wave CTAs start (blockIdx % 6) * stagger_ns late (0 = off)
   int sync_level;              // 0: warps run free; >= 1: CTA-wide barriers keep them in the same code region
 };
 

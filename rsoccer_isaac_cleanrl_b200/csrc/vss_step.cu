@@ -166,6 +166,12 @@ __device__ __forceinline__ void physics_cta(float* tiles, uint32_t* queue, uint3
   }
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 // The last warp of a CTA to finish counts the CTA as done (StepArgs::step_ctr): every warp of the CTA
 // has read the step index (phase 1a) by then. No return value is used, so the add is fire-and-forget.
 __device__ __forceinline__ void step_done(const StepArgs& a, uint32_t* ctr) {
@@ -186,6 +192,15 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   uint32_t* queue = reinterpret_cast<uint32_t*>(tiles + (blockDim.x >> 5) * TILE_STATE_WORDS);
   uint32_t* ctr = queue + (blockDim.x >> 5) * QUEUE_WORDS;
   if (threadIdx.x == 0) ctr[3] = 0u;  // warps of this CTA that have finished
+  // The CTAs of the first wave all start at once and would run their load / compute / store phases in
+  // lock-step (memory idle while they all compute, then all storing); the CTAs that take their slots
+  // later inherit the rhythm. Start the co-resident CTAs of an SM a little apart.
+  if (SYNC && a.stagger_ns > 0 && blockIdx.x < 148u * 6u) {
+    // CTAs are handed out round-robin over the 148 SMs: the k-th CTA of an SM is blockIdx / 148
+    const unsigned wait_ns = ((blockIdx.x / 148u) % 6u) * (unsigned)a.stagger_ns;
+    const unsigned long long t0 = globaltimer_ns();
+    while (globaltimer_ns() - t0 < wait_ns) __nanosleep(1000);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -382,6 +397,10 @@ static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
   int wpb, sync_phases; unsigned grid; size_t smem;
   launch_cfg(h->n, &wpb, &grid, &smem, &sync_phases);
   const_cast<StepArgs&>(a).sync_level = sync_phases;
+  // First-wave stagger (profiles/r01_g_*.md): 5 us per resident CTA of an SM, measured best of 0-12 us
+  // at 2^20 fields (675 -> 652 us per step); only when the launch is longer than one wave.
+  static const int stagger = env_int("VSS_STAGGER_NS", -1);
+  const_cast<StepArgs&>(a).stagger_ns = stagger >= 0 ? stagger : (grid > 148u * 6u ? 5000 : 0);
   const_cast<StepArgs&>(a).grid = grid;
   static bool big_smem_ok = false;
   if (smem > 48 * 1024 && !big_smem_ok) {
