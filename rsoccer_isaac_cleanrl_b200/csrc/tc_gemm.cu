@@ -762,20 +762,31 @@ k_head_fwd(const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict
   for (int j = 0; j < NO; ++j)
 #pragma unroll
     for (int c = 0; c < 8; ++c) w[j][c] = __ldg(W + j * 256 + 8 * lane + c);
-  for (int m = warp; m < M; m += nwarps) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(h + (size_t)m * ldh + 8 * lane);
-    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-    float x[8];
+  constexpr int U = 4;  // rows in flight per warp (each row is one 16-byte load per lane)
+  for (int m0 = warp; m0 < M; m0 += U * nwarps) {
+    uint4 raws[U];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { x[2 * c] = __bfloat162float(h2[c].x); x[2 * c + 1] = __bfloat162float(h2[c].y); }
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + u * nwarps;
+      if (m < M) raws[u] = *reinterpret_cast<const uint4*>(h + (size_t)m * ldh + 8 * lane);
+    }
 #pragma unroll
-    for (int j = 0; j < NO; ++j) {
-      float acc = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + u * nwarps;
+      if (m >= M) break;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raws[u]);
+      float x[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc = fmaf(x[c], w[j][c], acc);
+      for (int c = 0; c < 4; ++c) { x[2 * c] = __bfloat162float(h2[c].x); x[2 * c + 1] = __bfloat162float(h2[c].y); }
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-      if (lane == 0) out[(size_t)m * NO + j] = acc + __ldg(b + j);
+      for (int j = 0; j < NO; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc = fmaf(x[c], w[j][c], acc);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) out[(size_t)m * NO + j] = acc + __ldg(b + j);
+      }
     }
   }
 }
@@ -800,31 +811,50 @@ k_head_bwd(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ h, 
 #pragma unroll
     for (int c = 0; c < 8; ++c) { w[j][c] = __ldg(W + j * 256 + 8 * lane + c); gw[j][c] = 0.f; }
   }
-  for (int m = warp; m < M; m += nwarps) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(h + (size_t)m * ldh + 8 * lane);
-    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-    float x[8], g[8], d[NO];
+  // U rows per warp in flight: with one row per iteration every row was a DRAM round trip on the warp's
+  // critical path (55 rows x ~1.5 us = 98 us for 134 MB of traffic). Rows are consumed in the same
+  // ascending order as before, so the accumulated sums are unchanged.
+  constexpr int U = NO >= 6 ? 2 : 4;  // (NO = 6 at U = 4 needs 192 registers: one CTA per SM)
+  for (int m0 = warp; m0 < M; m0 += U * nwarps) {
+    uint4 raws[U];
+    float ds[U][NO];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { x[2 * c] = __bfloat162float(h2[c].x); x[2 * c + 1] = __bfloat162float(h2[c].y); }
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + u * nwarps;
+      if (m < M) {
+        raws[u] = *reinterpret_cast<const uint4*>(h + (size_t)m * ldh + 8 * lane);
 #pragma unroll
-    for (int j = 0; j < NO; ++j) { d[j] = __ldg(dout + (size_t)m * NO + j); gb[j] += d[j]; }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float acc = 0.f;
-#pragma unroll
-      for (int j = 0; j < NO; ++j) { acc = fmaf(d[j], w[j][c], acc); gw[j][c] = fmaf(d[j], x[c], gw[j][c]); }
-      g[c] = acc * (1.0f - x[c] * x[c]);
+        for (int j = 0; j < NO; ++j) ds[u][j] = __ldg(dout + (size_t)m * NO + j);
+      }
     }
-    uint4 o;
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(g[0], g[1]), p1 = __floats2bfloat162_rn(g[2], g[3]);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(g[4], g[5]), p3 = __floats2bfloat162_rn(g[6], g[7]);
-    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-    *reinterpret_cast<uint4*>(dz + (size_t)m * ldz + 8 * lane) = o;
-    // bias gradient of the last hidden layer = column sums of dz as stored (bf16-rounded)
-    gz[0] += __bfloat162float(p0.x); gz[1] += __bfloat162float(p0.y); gz[2] += __bfloat162float(p1.x);
-    gz[3] += __bfloat162float(p1.y); gz[4] += __bfloat162float(p2.x); gz[5] += __bfloat162float(p2.y);
-    gz[6] += __bfloat162float(p3.x); gz[7] += __bfloat162float(p3.y);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + u * nwarps;
+      if (m >= M) break;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raws[u]);
+      float x[8], g[8], d[NO];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { x[2 * c] = __bfloat162float(h2[c].x); x[2 * c + 1] = __bfloat162float(h2[c].y); }
+#pragma unroll
+      for (int j = 0; j < NO; ++j) { d[j] = ds[u][j]; gb[j] += d[j]; }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < NO; ++j) { acc = fmaf(d[j], w[j][c], acc); gw[j][c] = fmaf(d[j], x[c], gw[j][c]); }
+        g[c] = acc * (1.0f - x[c] * x[c]);
+      }
+      uint4 o;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(g[0], g[1]), p1 = __floats2bfloat162_rn(g[2], g[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(g[4], g[5]), p3 = __floats2bfloat162_rn(g[6], g[7]);
+      o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+      o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(dz + (size_t)m * ldz + 8 * lane) = o;
+      // bias gradient of the last hidden layer = column sums of dz as stored (bf16-rounded)
+      gz[0] += __bfloat162float(p0.x); gz[1] += __bfloat162float(p0.y); gz[2] += __bfloat162float(p1.x);
+      gz[3] += __bfloat162float(p1.y); gz[4] += __bfloat162float(p2.x); gz[5] += __bfloat162float(p2.y);
+      gz[6] += __bfloat162float(p3.x); gz[7] += __bfloat162float(p3.y);
+    }
   }
 #pragma unroll
   for (int j = 0; j < NO; ++j)

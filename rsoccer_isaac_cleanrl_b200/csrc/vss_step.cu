@@ -280,6 +280,33 @@ k_reset_dones(float* state, long long n, long long ld, unsigned long long goff, 
 // coalesced across envs, the T loop in registers, loads unrolled 8 deep ahead of the
 // (serial) recurrence. 28 B of HBM traffic per (t, env).
 // ----------------------------------------------------------------------------------------
+struct GaeRows { float r, v, nv, d, to; };
+
+__device__ __forceinline__ GaeRows gae_load(const float* __restrict__ rewards, const float* __restrict__ values,
+                                            const float* __restrict__ next_values, const float* __restrict__ next_dones,
+                                            const float* __restrict__ next_timeouts, long long i) {
+  return GaeRows{__ldg(rewards + i), __ldg(values + i), __ldg(next_values + i), __ldg(next_dones + i),
+                 __ldg(next_timeouts + i)};
+}
+
+// One step of the recurrence (ppo…:284-296), in the oracle's operation order.
+__device__ __forceinline__ float gae_step(const GaeRows& x, float last, float gamma, float gamma_lambda,
+                                          float* __restrict__ advantages, float* __restrict__ returns, long long i) {
+  const float nnt = (x.d != 0.0f && !(x.to != 0.0f)) ? 0.0f : 1.0f;
+  const float delta = fsub(fadd(x.r, fmul(fmul(gamma, x.nv), nnt)), x.v);
+  last = fadd(delta, fmul(fmul(gamma_lambda, fsub(1.0f, x.d)), last));
+  advantages[i] = last;
+  returns[i] = fadd(last, x.v);
+  return last;
+}
+
+// The recurrence is serial in t, the loads are not: the rows of the NEXT group of U time steps are
+// requested before the current group is consumed (two register buffers), so a thread always has
+// 5 U loads in flight. Without this the kernel is bound by T / U DRAM round trips (52 us at
+// T = 128, N = 65536, whatever the CTA size).
+// PREFETCH = false (many columns: enough warps per SM to cover the round trips, and 80 loads in
+// flight per thread then only thrash DRAM pages): the next group is requested after the current one.
+template <bool PREFETCH>
 __global__ void __launch_bounds__(128)
 k_gae(const float* __restrict__ rewards, const float* __restrict__ values, const float* __restrict__ next_values,
       const float* __restrict__ next_dones, const float* __restrict__ next_timeouts,
@@ -290,32 +317,34 @@ k_gae(const float* __restrict__ rewards, const float* __restrict__ values, const
   float last = 0.0f;
   constexpr int U = 8;
   int t = T - 1;
-  for (; t >= U - 1; t -= U) {
-    float r[U], v[U], nv[U], d[U], to[U];
+  if (t >= U - 1) {
+    GaeRows cur[U], nxt[U];
 #pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const long long i = (long long)(t - k) * N + n;
-      r[k] = __ldg(rewards + i); v[k] = __ldg(values + i); nv[k] = __ldg(next_values + i);
-      d[k] = __ldg(next_dones + i); to[k] = __ldg(next_timeouts + i);
-    }
+    for (int k = 0; k < U; ++k)
+      cur[k] = gae_load(rewards, values, next_values, next_dones, next_timeouts, (long long)(t - k) * N + n);
+    for (; t >= U - 1; t -= U) {
+      const bool more = t - U >= U - 1;  // another full group follows: request it now (or after this one)
+      if (PREFETCH && more) {
 #pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const long long i = (long long)(t - k) * N + n;
-      const float nnt = (d[k] != 0.0f && !(to[k] != 0.0f)) ? 0.0f : 1.0f;
-      const float delta = fsub(fadd(r[k], fmul(fmul(gamma, nv[k]), nnt)), v[k]);
-      last = fadd(delta, fmul(fmul(gamma_lambda, fsub(1.0f, d[k])), last));
-      advantages[i] = last;
-      returns[i] = fadd(last, v[k]);
+        for (int k = 0; k < U; ++k)
+          nxt[k] = gae_load(rewards, values, next_values, next_dones, next_timeouts, (long long)(t - U - k) * N + n);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        last = gae_step(cur[k], last, gamma, gamma_lambda, advantages, returns, (long long)(t - k) * N + n);
+      if (more) {
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+          cur[k] = PREFETCH ? nxt[k]
+                            : gae_load(rewards, values, next_values, next_dones, next_timeouts,
+                                       (long long)(t - U - k) * N + n);
+      }
     }
   }
   for (; t >= 0; --t) {
     const long long i = (long long)t * N + n;
-    const float d = next_dones[i], v = values[i];
-    const float nnt = (d != 0.0f && !(next_timeouts[i] != 0.0f)) ? 0.0f : 1.0f;
-    const float delta = fsub(fadd(rewards[i], fmul(fmul(gamma, next_values[i]), nnt)), v);
-    last = fadd(delta, fmul(fmul(gamma_lambda, fsub(1.0f, d)), last));
-    advantages[i] = last;
-    returns[i] = fadd(last, v);
+    last = gae_step(gae_load(rewards, values, next_values, next_dones, next_timeouts, i), last, gamma, gamma_lambda,
+                    advantages, returns, i);
   }
 }
 
@@ -402,12 +431,12 @@ static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
   static const int stagger = env_int("VSS_STAGGER_NS", -1);
   const_cast<StepArgs&>(a).stagger_ns = stagger >= 0 ? stagger : (grid > 148u * 6u ? 5000 : 0);
   const_cast<StepArgs&>(a).grid = grid;
-  static bool big_smem_ok = false;
-  if (smem > 48 * 1024 && !big_smem_ok) {
+  static bool big_smem_ok[64] = {};  // per device: the attribute belongs to the function in one context
+  if (smem > 48 * 1024 && !big_smem_ok[h->device & 63]) {
     VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    big_smem_ok = true;
+    big_smem_ok[h->device & 63] = true;
   }
   if (sync_phases >= 4 && wpb > 1 && !INJECT) k_step<VIEW, INJECT, 2><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
   else if (sync_phases && wpb > 1) k_step<VIEW, INJECT, 1><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
@@ -515,10 +544,10 @@ VSS_API int vss_reset_dones(vss_handle h, const int64_t* reset_buf, float* obs, 
   if (int rc = use_device(h)) return rc;
   int wpb; unsigned grid; size_t smem;
   launch_cfg(h->n, &wpb, &grid, &smem);
-  static bool big_smem_ok = false;
-  if (smem > 48 * 1024 && !big_smem_ok) {
+  static bool big_smem_ok[64] = {};
+  if (smem > 48 * 1024 && !big_smem_ok[h->device & 63]) {
     VSS_CUDA(cudaFuncSetAttribute(k_reset_dones, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    big_smem_ok = true;
+    big_smem_ok[h->device & 63] = true;
   }
   k_reset_dones<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(
       h->state, h->n, h->ld, (unsigned long long)h->goff, (uint32_t)h->seed, (uint32_t)(h->seed >> 32),
@@ -594,10 +623,22 @@ VSS_API int vss_gae(const float* rewards, const float* values, const float* next
   if (!rewards || !values || !next_values || !next_dones || !next_timeouts || !advantages || !returns)
     return fail(VSS_E_INVALID, "vss_gae: null argument");
   if (T <= 0 || N <= 0) return fail(VSS_E_INVALID, "vss_gae: T and N must be > 0");
-  const unsigned grid = (unsigned)((N + 127) / 128);
-  k_gae<<<grid, 128, 0, (cudaStream_t)stream>>>(rewards, values, next_values, next_dones, next_timeouts,
-                                                advantages, returns, T, N, (float)gamma,
-                                                (float)(gamma * gae_lambda));
+  // 64 columns per CTA: at N = 65536 that is 1024 CTAs = 6.9 per SM (128 per CTA: 3.46 per SM, i.e. a
+  // quarter of the SMs carry a third more columns than the rest)
+  static const int gae_block = env_int("VSS_GAE_BLOCK", 64);
+  const unsigned grid = (unsigned)((N + gae_block - 1) / gae_block);
+  // prefetch while the batch has fewer than ~28 warps per SM (measured: N = 65536 51.7 -> 39.8 us with it,
+  // N = 196608 112.8 -> 122.9 us)
+  static const int pf_knob = env_int("VSS_GAE_PREFETCH", -1);
+  const bool prefetch = pf_knob >= 0 ? pf_knob != 0 : N <= 131072;
+  if (prefetch)
+    k_gae<true><<<grid, gae_block, 0, (cudaStream_t)stream>>>(rewards, values, next_values, next_dones, next_timeouts,
+                                                            advantages, returns, T, N, (float)gamma,
+                                                            (float)(gamma * gae_lambda));
+  else
+    k_gae<false><<<grid, gae_block, 0, (cudaStream_t)stream>>>(rewards, values, next_values, next_dones, next_timeouts,
+                                                             advantages, returns, T, N, (float)gamma,
+                                                             (float)(gamma * gae_lambda));
   VSS_CUDA(cudaGetLastError());
   return VSS_OK;
 }
