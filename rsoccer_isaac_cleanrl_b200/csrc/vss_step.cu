@@ -393,7 +393,9 @@ static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* s
   int wpb = 4, sync = 2;  // 6 CTAs of 4 warps per SM (measured at 2^20 fields: 4 / 6 / 8 / 12 warps per CTA ->
                           // 0.672 / 0.671 / 0.652 / 0.592 of the HBM roofline; at 2^16 fields 0.405 / 0.366 / 0.377)
   if (tiles < 148 * 2) { wpb = 1; sync = 0; }
-  else if (tiles < 148 * 8) { wpb = 2; sync = 0; }
+  else if (tiles < 148 * 20) { wpb = 2; sync = 0; }  // up to ~3 resident warps per scheduler the barriers only add
+                                                     // latency (2^16 fields: 61.5 us vs 68.0 us with 4 warps + barriers;
+                                                     // 2^17 fields: 117 vs 109 us, so the switch sits between them)
   static const int forced_wpb = env_int("VSS_WPB", 0), forced_sync = env_int("VSS_SYNC", -1);
   if (forced_wpb >= 1 && forced_wpb <= 12) wpb = forced_wpb;
   if (forced_sync >= 0) sync = forced_sync;
