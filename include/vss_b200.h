@@ -184,6 +184,16 @@ VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, fl
                           float* ep_ret, int32_t* ep_len, float* ret_ret, int32_t* ret_len,
                           void* stream);
 
+/* Optional side outputs of the following vss_step_view launches (each may be NULL = off), for a
+ * caller that feeds the observation straight into a bf16 tensor-core MLP and the flags into a float
+ * GAE (the PPO loop, ppo_continuous_action_isaacgym.py:258-272, 282-296):
+ *   obs_bf16     (N',64) bf16: the view observation rounded to nearest even; columns 52..63 are
+ *                never written (zero the buffer once);
+ *   done_f32     (N') f32: done_v as 0.0f / 1.0f;   timeout_f32 (N') f32: timeout_v as 0.0f / 1.0f.
+ * Host-side state of the handle (no device work, no synchronisation); the pointers are read when
+ * vss_step_view is called, so they may change from step to step. */
+VSS_API int vss_set_step_aux(vss_handle h, void* obs_bf16, float* done_f32, float* timeout_f32);
+
 /* State access for parity tests and checkpointing: copies the SoA state
  * (VSS_STATE_WORDS x ld 32-bit words) device->device. */
 VSS_API int vss_get_state(vss_handle h, float* state_out, void* stream);

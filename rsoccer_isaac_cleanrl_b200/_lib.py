@@ -65,6 +65,7 @@ _SYMBOLS = {
     "vss_step": (C.c_int, [_VP] * 9),
     "vss_step_injected": (C.c_int, [_VP] * 10),
     "vss_step_view": (C.c_int, [_VP, C.c_int] + [_VP] * 15),
+    "vss_set_step_aux": (C.c_int, [_VP, _VP, _VP, _VP]),
     "vss_get_state": (C.c_int, [_VP, _VP, _VP]),
     "vss_set_state": (C.c_int, [_VP, _VP, _VP]),
     "vss_step_count": (C.c_uint64, [_VP]),

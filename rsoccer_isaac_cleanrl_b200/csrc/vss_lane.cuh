@@ -18,6 +18,9 @@
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
+#if defined(__CUDACC__)
+#include <cuda_bf16.h>
+#endif
 
 #include "../../include/vss_b200.h"
 
@@ -760,11 +763,20 @@ VSS_HD void st4(float* p, const F4& v) { *reinterpret_cast<float4*>(p) = make_fl
 // streaming store (evict-first): observations are written once and never re-read by this kernel
 VSS_HD void st4_stream(float* p, const F4& v) { __stcs(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, v.w)); }
 VSS_HD float ldg(const float* p) { return __ldg(p); }
+// four floats -> four bf16 (round to nearest even), one 8-byte store at element offset `off` of `base`
+VSS_HD void st_bf16x4(void* base, long long off, const F4& v) {
+  const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.x)) |
+                      ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.y)) << 16);
+  const uint32_t hi = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.z)) |
+                      ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.w)) << 16);
+  *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(base) + off) = make_uint2(lo, hi);
+}
 #else
 VSS_HD F4 ld4(const float* p) { return F4{p[0], p[1], p[2], p[3]}; }
 VSS_HD void st4(float* p, const F4& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
 VSS_HD void st4_stream(float* p, const F4& v) { st4(p, v); }
 VSS_HD float ldg(const float* p) { return *p; }
+VSS_HD void st_bf16x4(void*, long long, const F4&) {}  // (the host emulation has no bf16 side output)
 #endif
 
 constexpr int VIEW_FULL = -1;
@@ -790,6 +802,9 @@ struct StepArgs {
   // view mode only
   const float* policy_action; float* action_buf; float* reward_v; long long* done_v;
   float* ep_ret; int* ep_len; float* ret_ret; int* ret_len;
+  // optional side outputs of the views (vss_set_step_aux): the observation as bf16 rows padded to 64
+  // columns (what the tensor-core MLP reads), done / timeout as floats (what the GAE kernel reads)
+  void* obs_bf16; float* done_f; float* timeout_f;
   int stagger_ns;              // first-wave CTAs start (blockIdx % 6) * stagger_ns late (0 = off)
   int sync_level;              // 0: warps run free; >= 1: CTA-wide barriers keep them in the same code region
 };
@@ -933,6 +948,8 @@ VSS_HD int lane_phase1d(float* S, long long env, const StepArgs& a, const DevPar
       a.reward_v[v] = fadd(fadd(fadd(r4[0], r4[1]), r4[2]), r4[3]);
       a.done_v[v] = done ? 1 : 0;
       a.timeout[v] = tmo ? 1 : 0;
+      if (a.done_f) a.done_f[v] = done ? 1.0f : 0.0f;
+      if (a.timeout_f) a.timeout_f[v] = tmo ? 1.0f : 0.0f;
       if (a.progress_f) a.progress_f[v] = (float)progress;
       if (a.ep_ret) {  // RecordEpisodeStatisticsTorch.step, wrappers.py:68-75
         const float keep = done ? 0.0f : 1.0f;
@@ -966,15 +983,21 @@ VSS_HD void lane_phase5(const float* S, long long env, const StepArgs& a, bool d
 // Cooperative, coalesced observation write of one tile (all 32 lanes call it).
 //   per_field = float4 per field in this layout (78 full, 13 sa/cma, 39 dma)
 //   skip_mask = fields whose `ob` row is NOT written now (they are reset first)
+// Element offset, in a (rows, 64) bf16 matrix, of float4 slot f of a (rows, 52) f32 matrix.
+VSS_HD int bf16_pad_offset(int f) { const int row = f / F4_PER_ROW; return row * 64 + (f - row * F4_PER_ROW) * 4; }
+
 VSS_HD void write_obs_tile(const float* T, const uint32_t* tab, int lane, int valid, int per_field, float* tob,
-                           float* ob, uint32_t skip_mask) {
+                           float* ob, uint32_t skip_mask, void* obh = nullptr) {
   const int total = valid * per_field;
 #pragma unroll 4
   for (int f = lane; f < total; f += 32) {
     const int e = f / per_field, j = f - e * per_field;
     const F4 v = obs_gather(T, tab[j], e);
     if (tob) st4(tob + 4 * f, v);
-    if (!((skip_mask >> e) & 1u)) st4(ob + 4 * f, v);
+    if (!((skip_mask >> e) & 1u)) {
+      st4(ob + 4 * f, v);
+      if (obh) st_bf16x4(obh, bf16_pad_offset(f), v);
+    }
   }
 }
 
@@ -988,7 +1011,7 @@ VSS_HD void write_obs_tile(const float* T, const uint32_t* tab, int lane, int va
 // (16 or 8 lanes wide) writes the tail of field e + g.
 template <int PER_FIELD>
 VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, int valid, float* tob, float* ob,
-                                uint32_t skip_mask) {
+                                uint32_t skip_mask, void* obh = nullptr) {
   constexpr int FULL = PER_FIELD / 32, TAIL = PER_FIELD - 32 * FULL;
   constexpr int TW = TAIL <= 1 ? 1 : TAIL <= 2 ? 2 : TAIL <= 4 ? 4 : TAIL <= 8 ? 8 : TAIL <= 16 ? 16 : 32;
   constexpr int G = 32 / TW, SLOTS = FULL + (TAIL ? 1 : 0);
@@ -1017,7 +1040,10 @@ VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, i
                  bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
       const int idx = 4 * (e * PER_FIELD + lane + 32 * sl);
       if (tob) st4_stream(tob + idx, v);
-      if (keep) st4_stream(ob + idx, v);
+      if (keep) {
+        st4_stream(ob + idx, v);
+        if (obh) st_bf16x4(obh, bf16_pad_offset(idx >> 2), v);
+      }
     }
     if (TAIL && (e % G) == 0 && tail_lane && e + sub < valid) {  // fields e .. e+G-1, one lane group each
       constexpr int sl = SLOTS - 1;
@@ -1025,17 +1051,24 @@ VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, i
                  bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
       const int idx = 4 * ((e + sub) * PER_FIELD + jt);
       if (tob) st4_stream(tob + idx, v);
-      if (!((skip_mask >> (e + sub)) & 1u)) st4_stream(ob + idx, v);
+      if (!((skip_mask >> (e + sub)) & 1u)) {
+        st4_stream(ob + idx, v);
+        if (obh) st_bf16x4(obh, bf16_pad_offset(idx >> 2), v);
+      }
     }
   }
 }
 
 VSS_HD void write_obs_fields(const float* T, const uint32_t* tab, int lane, int per_field, float* ob,
-                             uint32_t field_mask) {
+                             uint32_t field_mask, void* obh = nullptr) {
   while (field_mask) {
     const int e = ffs32(field_mask) - 1;
     field_mask &= field_mask - 1;
-    for (int j = lane; j < per_field; j += 32) st4(ob + 4 * (e * per_field + j), obs_gather(T, tab[j], e));
+    for (int j = lane; j < per_field; j += 32) {
+      const F4 v = obs_gather(T, tab[j], e);
+      st4(ob + 4 * (e * per_field + j), v);
+      if (obh) st_bf16x4(obh, bf16_pad_offset(e * per_field + j), v);
+    }
   }
 }
 

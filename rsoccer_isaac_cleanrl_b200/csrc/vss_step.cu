@@ -228,14 +228,18 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
   float* ob = a.obs + env0 * (PER_FIELD * 4);
   float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
-  if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD>(T, tab, lane, valid, tob, ob, done_mask);
-  else write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, done_mask);
+  // (views only) the same rows as bf16, padded to 64 columns: the tile's first view row is env0 * AGENTS
+  void* obh = (VIEW != VIEW_FULL && a.obs_bf16)
+                  ? static_cast<void*>(static_cast<unsigned short*>(a.obs_bf16) + env0 * (ViewShape<VIEW>::AGENTS * 64))
+                  : nullptr;
+  if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD>(T, tab, lane, valid, tob, ob, done_mask, obh);
+  else write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, done_mask, obh);
   __syncwarp();
   // 3. masked reset (vss.py:202, 267-333)
   if (done) reset_lane(S, P, key);
   __syncwarp();
   // 4. observation of the fields that were reset (vss.py:203)
-  write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask);
+  write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask, obh);
   // 5. state out
   if (SYNC && a.sync_level >= 2) __syncthreads();
   if (active) lane_phase5<VIEW>(S, env, a, code != LANE_RUNNING);
@@ -363,6 +367,7 @@ struct vss_engine {
   vss_params params;
   DevParams dp;
   float* state;
+  void* aux_obs_bf16; float* aux_done_f; float* aux_timeout_f;  // vss_set_step_aux
 };
 
 static thread_local std::string g_last_error;
@@ -492,6 +497,7 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
   vss_engine* h = new (std::nothrow) vss_engine();
   if (!h) return fail(VSS_E_NOMEM, "vss_create: host allocation failed");
   h->device = device; h->n = num_envs; h->ld = (num_envs + 31) / 32 * 32; h->goff = global_env_offset;
+  h->aux_obs_bf16 = nullptr; h->aux_done_f = nullptr; h->aux_timeout_f = nullptr;
   h->seed = seed; h->d_step = nullptr; h->params = *p; h->dp = derive_params(*p); h->state = nullptr;
   const size_t bytes = sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld;
   e = cudaMalloc(&h->state, bytes);
@@ -595,12 +601,19 @@ VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, fl
   a.obs = obs_v; a.term_obs = term_obs_v; a.rew = rews_v; a.reward_v = reward_v;
   a.done_v = reinterpret_cast<long long*>(done_v); a.timeout = timeout_v; a.progress_f = progress_v;
   a.ep_ret = ep_ret; a.ep_len = ep_len; a.ret_ret = ret_ret; a.ret_len = ret_len;
+  a.obs_bf16 = h->aux_obs_bf16; a.done_f = h->aux_done_f; a.timeout_f = h->aux_timeout_f;
   switch (view) {
     case VSS_VIEW_SA: return launch_step<VSS_VIEW_SA, false>(h, a, stream);
     case VSS_VIEW_CMA: return launch_step<VSS_VIEW_CMA, false>(h, a, stream);
     case VSS_VIEW_DMA: return launch_step<VSS_VIEW_DMA, false>(h, a, stream);
     default: return fail(VSS_E_INVALID, "vss_step_view: unknown view");
   }
+}
+
+VSS_API int vss_set_step_aux(vss_handle h, void* obs_bf16, float* done_f32, float* timeout_f32) {
+  if (!h) return fail(VSS_E_INVALID, "vss_set_step_aux: null handle");
+  h->aux_obs_bf16 = obs_bf16; h->aux_done_f = done_f32; h->aux_timeout_f = timeout_f32;
+  return VSS_OK;
 }
 
 VSS_API int vss_get_state(vss_handle h, float* state_out, void* stream) {

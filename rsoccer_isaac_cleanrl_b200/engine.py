@@ -37,6 +37,7 @@ class Engine:
         check(self.lib.vss_create(C.byref(self._h), C.byref(self.params), self.num_envs, int(global_env_offset),
                                   idx, int(seed) & 0xFFFFFFFFFFFFFFFF))
         self.ld = int(self.lib.vss_state_ld(self._h))
+        self._aux_set = False
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -96,10 +97,19 @@ class Engine:
         check(fn(self._h, *args))
 
     def step_view(self, view, policy_action, action_buf, reset_buf, obs_v, term_obs_v, rews_v, reward_v, done_v,
-                  timeout_v, progress_v, ep_ret=None, ep_len=None, ret_ret=None, ret_len=None):
+                  timeout_v, progress_v, ep_ret=None, ep_len=None, ret_ret=None, ret_len=None, obs_bf16=None,
+                  done_f=None, timeout_f=None):
+        """`obs_bf16 (N',64) bf16`, `done_f (N') f32`, `timeout_f (N') f32`: optional side outputs
+        (vss_set_step_aux) — the observation as the tensor-core MLP reads it, the flags as the GAE
+        kernel reads them."""
         n = self.num_envs
         nv = n * 3 if view == VIEW_DMA else n
         adim = 6 if view == VIEW_CMA else 2
+        if obs_bf16 is not None or done_f is not None or timeout_f is not None or self._aux_set:
+            check(self.lib.vss_set_step_aux(self._h, _ptr(obs_bf16, torch.bfloat16, nv * 64, "obs_bf16"),
+                                            _ptr(done_f, torch.float32, nv, "done_f"),
+                                            _ptr(timeout_f, torch.float32, nv, "timeout_f")))
+            self._aux_set = obs_bf16 is not None or done_f is not None or timeout_f is not None
         check(self.lib.vss_step_view(
             self._h, int(view), _ptr(policy_action, torch.float32, nv * adim, "policy_action"),
             _ptr(action_buf, torch.float32, n * 12, "action_buf"), _ptr(reset_buf, torch.int64, n, "reset_buf"),

@@ -88,10 +88,13 @@ class _FusedView(Wrapper):
         observations = self.env.reset(**kwargs)
         return {"obs": self._slice_obs(observations["obs"])}
 
-    def step(self, action, obs_out=None, term_obs_out=None, reward_out=None):
+    def step(self, action, obs_out=None, term_obs_out=None, reward_out=None, obs_bf16_out=None, done_f_out=None,
+             timeout_f_out=None):
         """One fused step. The optional `*_out` tensors (contiguous, right shape) make the kernel write
         the observation / terminal observation / scalar reward straight into caller storage — e.g. the
-        `(T, N, …)` rollout slabs of the PPO loop (ppo…:258-272) — instead of the view's own buffers."""
+        `(T, N, …)` rollout slabs of the PPO loop (ppo…:258-272) — instead of the view's own buffers.
+        `obs_bf16_out (N',64) bf16`, `done_f_out`, `timeout_f_out (N') f32` are extra copies in the form the
+        tensor-core MLP and the GAE kernel read (no conversion launches between the steps)."""
         task = self.task
         if action.device != task.device or action.dtype != torch.float32 or not action.is_contiguous():
             action = action.to(task.device, torch.float32).contiguous()
@@ -101,7 +104,8 @@ class _FusedView(Wrapper):
         task.engine.step_view(self.VIEW, action, self.action_buf, task.reset_buf, obs, term_obs,
                               self._rews, reward, self._done, self._timeout_u8, self._progress,
                               self.episode_returns, self.episode_lengths, self.returned_episode_returns,
-                              self.returned_episode_lengths)
+                              self.returned_episode_lengths, obs_bf16=obs_bf16_out, done_f=done_f_out,
+                              timeout_f=timeout_f_out)
         task._obs_stale = True
         infos = task.extras
         infos["rews"] = self._rews

@@ -255,22 +255,29 @@ def train(args, log=print, hook=None):
         if side is not None:
             torch.cuda.current_stream(device).wait_stream(side)
 
+    if fused:
+        # the env step writes the next observation a second time as bf16 rows padded to k0 = 64 columns
+        # (what the first tcgen05 GEMM reads) and done / timeout as floats (what the GAE kernel reads):
+        # no conversion launches between the steps. Two buffers: step t reads one, writes the other.
+        assert k0 == 64, k0
+        x16_buf = [torch.zeros((N, k0), device=device, dtype=torch.bfloat16) for _ in range(2)]
+
     def rollout_fused(first_obs):
-        """rollout() with every per-step piece as one launch: pad/convert the observation once for
-        both networks, 2 x (4 tcgen05 GEMMs + head), the sampling kernel writing action and log-prob
-        into the rollout slabs, the critic head writing values[step], the env step."""
+        """rollout() with every per-step piece as one launch: 2 x (4 tcgen05 GEMMs + head), the sampling
+        kernel writing action and log-prob into the rollout slabs, the critic head writing values[step],
+        the env step writing obs / reward / done / timeout slabs and the next bf16 MLP input."""
         with torch.no_grad():
             obs_all[0] = first_obs
+            x16_buf[0].copy_(gather_pad_bf16(obs_all[0], None, k0))
             mw_actor.refresh(); mw_critic.refresh()
             for step in range(T):
-                x16 = gather_pad_bf16(obs_all[step], None, k0)
+                x16 = x16_buf[step & 1]
                 critic_out = on_side(lambda: forward_explicit(mw_critic, x16, out=values[step]))
                 mean, _ = forward_explicit(mw_actor, x16)
                 policy_sample(mean, logstd_flat, sample_seed, sample_ctr, action=actions[step], logprob=logprobs[step])
-                _, _, next_done, info = envs.step(actions[step], obs_out=obs_all[step + 1],
-                                                  term_obs_out=term_obs_all[step], reward_out=rewards[step])
-                next_dones[step] = next_done
-                next_timeouts[step] = info["time_outs"]
+                envs.step(actions[step], obs_out=obs_all[step + 1], term_obs_out=term_obs_all[step],
+                          reward_out=rewards[step], obs_bf16_out=x16_buf[(step + 1) & 1],
+                          done_f_out=next_dones[step], timeout_f_out=next_timeouts[step])
                 join_side()
                 del critic_out
             forward_explicit(mw_critic, gather_pad_bf16(term_obs_all.view(T * N, -1), None, k0), out=next_values)

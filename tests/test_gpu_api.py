@@ -174,3 +174,36 @@ def test_cuda_graph_replay_advances_the_ou_stream():
     torch.cuda.synchronize()
     assert torch.equal(view2.action_buf, bufs[2])
     assert torch.equal(envs2.engine.get_state(), envs.engine.get_state())
+
+
+@pytest.mark.parametrize("env_id,n", [("sa", 333), ("cma", 97), ("dma", 1000)])
+def test_view_side_outputs_bf16_obs_and_float_flags(env_id, n):
+    """vss_set_step_aux: the bf16 / padded copy of the view observation and the float copies of done and
+    timeout equal what the conversion launches they replace would produce, for kept and reset fields."""
+    from rsoccer_isaac_cleanrl_b200.envs import CMA, DMA, VSS, SingleAgent
+    envs = VSS(_cfg(n), "cuda:0", "cuda:0", 0, True, seed=21)
+    view = {"sa": SingleAgent, "cma": CMA, "dma": DMA}[env_id](envs)
+    nv = view.num_view_envs
+    # push many fields to the end of their episodes so that resets happen within the few steps
+    st = envs.engine.get_state()
+    st[58, :n] = torch.randint(394, 399, (n,), device="cuda", dtype=torch.int32).view(torch.float32)
+    envs.engine.set_state(st)
+    x16 = torch.full((nv, 64), 7.0, device="cuda", dtype=torch.bfloat16)
+    done_f = torch.full((nv,), -1.0, device="cuda")
+    tmo_f = torch.full((nv,), -1.0, device="cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    seen_done = 0
+    for t in range(8):
+        act = torch.rand((nv, view.ACT_DIM), device="cuda", generator=g) * 2 - 1
+        obs, reward, done, info = view.step(act, obs_bf16_out=x16, done_f_out=done_f, timeout_f_out=tmo_f)
+        torch.cuda.synchronize()
+        assert torch.equal(x16[:, :52], obs["obs"].to(torch.bfloat16))
+        assert torch.all(x16[:, 52:] == 7.0)          # the padding columns are never written
+        assert torch.equal(done_f, done.float()) and torch.equal(tmo_f, info["time_outs"].float())
+        seen_done += int(done.sum())
+    assert seen_done > 0
+    # and switching the side outputs off again leaves the buffers alone
+    x16.fill_(3.0)
+    view.step(act)
+    torch.cuda.synchronize()
+    assert torch.all(x16 == 3.0)

@@ -109,6 +109,24 @@ def test_gae_matches_reference_loop_and_oracle():
     assert np.array_equal(pc.bits(ret.cpu().numpy()), pc.bits(oret))
 
 
+@pytest.mark.parametrize("T,N", [(1, 5), (7, 33), (8, 129), (9, 1000), (23, 4097), (128, 150000), (40, 262144)])
+def test_gae_ragged_shapes_bit_exact(T, N):
+    """T below / equal to / not a multiple of the 8-step load group (remainder loop), both load
+    schedules (prefetching below 131072 columns, plain above): bit-exact against the oracle."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rsoccer_isaac_cleanrl_b200.engine import gae
+    rng = np.random.default_rng(T * 1000 + N)
+    a = [rng.normal(size=(T, N)).astype(np.float32) for _ in range(3)]
+    d = (rng.uniform(size=(T, N)) < 0.05).astype(np.float32)
+    to = ((rng.uniform(size=(T, N)) < 0.5) * d).astype(np.float32)
+    adv, ret = gae(*[torch.from_numpy(x).cuda() for x in (*a, d, to)], 0.99, 0.95)
+    oadv, oret = orc.gae(*a, d, to, 0.99, 0.95)
+    assert np.array_equal(pc.bits(adv.cpu().numpy()), pc.bits(oadv))
+    assert np.array_equal(pc.bits(ret.cpu().numpy()), pc.bits(oret))
+
+
 def test_full_size_properties(Gpu):
     """N = 1,048,576 fields (top of the BASELINE sweep): size-independent properties."""
     n = 1 << 20
