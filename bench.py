@@ -271,8 +271,10 @@ def run_native(args):
                "h2d_bytes_per_step": view.h2d_bytes_per_step, "d2h_bytes_per_step": view.d2h_bytes_per_step,
                "steps": k_e2e, "ms_per_step": ms_e / k_e2e,
                "api": "SingleAgent.step_host(pinned policy action (N,2)) -> pinned obs (N,52), reward (N), "
-                      "done (N); one fused vss_step_view launch, host sync every step"}
-        launches += k_e2e + 3
+                      f"done (N); the step runs as {view.HOST_CHUNKS if n >= view.HOST_CHUNK_MIN_FIELDS else 1} field "
+                      "ranges (vss_set_step_range) on two streams so that the D2H copy of one range overlaps the "
+                      "kernel of the next; host sync every step"}
+        launches += (k_e2e + 3) * (view.HOST_CHUNKS if n >= view.HOST_CHUNK_MIN_FIELDS else 1)
 
     sweep = None
     if not args.no_sweep:

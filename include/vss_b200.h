@@ -194,6 +194,17 @@ VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, fl
  * vss_step_view is called, so they may change from step to step. */
 VSS_API int vss_set_step_aux(vss_handle h, void* obs_bf16, float* done_f32, float* timeout_f32);
 
+/* Restricts the following vss_step / vss_step_view launches to the fields [first_field, first_field +
+ * num_fields) (num_fields = 0: the whole engine again). Buffers keep their whole-engine shapes and base
+ * pointers; only the rows of the range are read and written. For a caller that pipelines one step over
+ * several streams (host copies of chunk c overlapping the kernel of chunk c+1): the chunks of ONE step
+ * may run concurrently, every field must be covered exactly once per step, and the next step's launches
+ * must be ordered after all of them (the OU-noise step index is counted over the whole engine).
+ * first_field and num_fields must be multiples of vss_step_granularity(h), except that the last range
+ * may end at num_envs. Host-side state of the handle, like vss_set_step_aux. */
+VSS_API int64_t vss_step_granularity(vss_handle h);
+VSS_API int vss_set_step_range(vss_handle h, int64_t first_field, int64_t num_fields);
+
 /* State access for parity tests and checkpointing: copies the SoA state
  * (VSS_STATE_WORDS x ld 32-bit words) device->device. */
 VSS_API int vss_get_state(vss_handle h, float* state_out, void* stream);

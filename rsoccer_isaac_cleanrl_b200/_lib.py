@@ -66,6 +66,8 @@ _SYMBOLS = {
     "vss_step_injected": (C.c_int, [_VP] * 10),
     "vss_step_view": (C.c_int, [_VP, C.c_int] + [_VP] * 15),
     "vss_set_step_aux": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "vss_step_granularity": (C.c_int64, [_VP]),
+    "vss_set_step_range": (C.c_int, [_VP, C.c_int64, C.c_int64]),
     "vss_get_state": (C.c_int, [_VP, _VP, _VP]),
     "vss_set_state": (C.c_int, [_VP, _VP, _VP]),
     "vss_step_count": (C.c_uint64, [_VP]),

@@ -782,7 +782,8 @@ VSS_HD void st_bf16x4(void*, long long, const F4&) {}  // (the host emulation ha
 constexpr int VIEW_FULL = -1;
 
 struct StepArgs {
-  float* state; long long n, ld; unsigned long long goff;
+  float* state; long long n, ld; unsigned long long goff;  // n = end of the field range of this launch
+  long long env_begin;         // first field of this launch (0 unless vss_set_step_range restricts it)
   uint32_t seed_lo, seed_hi;
   // Device-resident step index (keys the OU stream), kept as the number of step-kernel CTAs that have
   // finished over the engine's life: every launch of an engine has the same grid, launches are

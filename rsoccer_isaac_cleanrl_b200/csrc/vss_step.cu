@@ -67,7 +67,7 @@ __device__ __forceinline__ void physics_tile(float* T, uint8_t* queue, int lane,
       m &= m - 1;
       queue[pos++] = (uint8_t)((lane << 3) | r);
     }
-    if (SYNC && sync_level >= 3) __syncthreads(); else __syncwarp();
+    if (SYNC && (sync_level & 7) >= 3) __syncthreads(); else __syncwarp();
 #pragma unroll 1
     for (int t0 = 0; t0 < total; t0 += 32) {  // warp-uniform trip count: usually one pass, rarely more
       if (t0 + lane < total) {
@@ -75,7 +75,7 @@ __device__ __forceinline__ void physics_tile(float* T, uint8_t* queue, int lane,
         robot_walls_task(T + (q >> 3), q & 7, P);
       }
     }
-    if (SYNC && sync_level >= 3) __syncthreads(); else __syncwarp();
+    if (SYNC && (sync_level & 7) >= 3) __syncthreads(); else __syncwarp();
     if (active) substep_ball_walls_lane(S, P);
   }
 }
@@ -204,7 +204,7 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  const long long env0 = tile * 32;
+  const long long env0 = a.env_begin + tile * 32;
   if (!SYNC && env0 >= a.n) { if (VIEW != VIEW_FULL) step_done(a, ctr); return; }  // (with block-level syncs every warp stays until the end)
   float* T = tiles + warp * TILE_STATE_WORDS;
   float* S = T + lane;
@@ -223,7 +223,7 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   if (active) code = lane_phase1d<VIEW>(S, env, a, P, key);
   const bool done = code == LANE_DONE;   // needs the masked reset of phase 3
   __syncwarp();
-  if (SYNC && a.sync_level >= 2) __syncthreads();
+  if (SYNC && (a.sync_level & 7) >= 2 && !(a.sync_level & 16)) __syncthreads();
   // 2. terminal observation + observation of the fields that keep their state (vss.py:195-196)
   const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
   float* ob = a.obs + env0 * (PER_FIELD * 4);
@@ -241,7 +241,7 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   // 4. observation of the fields that were reset (vss.py:203)
   write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask, obh);
   // 5. state out
-  if (SYNC && a.sync_level >= 2) __syncthreads();
+  if (SYNC && (a.sync_level & 7) >= 2 && !(a.sync_level & 8)) __syncthreads();
   if (active) lane_phase5<VIEW>(S, env, a, code != LANE_RUNNING);
   // only the views draw OU noise: the full-contract step neither reads nor advances the index (the
   // extra memory operation at the end of every CTA costs 1 % of the launch at 2^20 fields)
@@ -368,6 +368,7 @@ struct vss_engine {
   DevParams dp;
   float* state;
   void* aux_obs_bf16; float* aux_done_f; float* aux_timeout_f;  // vss_set_step_aux
+  int64_t range_first, range_count;                             // vss_set_step_range (count 0 = all fields)
 };
 
 static thread_local std::string g_last_error;
@@ -405,7 +406,7 @@ static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* s
   if (forced_wpb >= 1 && forced_wpb <= 12) wpb = forced_wpb;
   if (forced_sync >= 0) sync = forced_sync;
   if (wpb == 1) sync = 0;
-  if (sync >= 4 && wpb > 8) sync = 2;  // the CTA-wide task queues index fields with 8 bits
+  if ((sync & 7) >= 4 && wpb > 8) sync = 2;  // the CTA-wide task queues index fields with 8 bits
   *warps_per_block = wpb;
   *grid = (unsigned)((tiles + wpb - 1) / wpb);
   *smem = sizeof(float) * smem_words(wpb);
@@ -437,7 +438,15 @@ static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
   // at 2^20 fields (675 -> 652 us per step); only when the launch is longer than one wave.
   static const int stagger = env_int("VSS_STAGGER_NS", -1);
   const_cast<StepArgs&>(a).stagger_ns = stagger >= 0 ? stagger : (grid > 148u * 6u ? 5000 : 0);
-  const_cast<StepArgs&>(a).grid = grid;
+  const_cast<StepArgs&>(a).grid = grid;  // the step index is counted in CTAs of the WHOLE engine
+  if (h->range_count > 0) {  // vss_set_step_range: this launch covers [first, first + count) — same CTA shape, fewer CTAs
+    const int64_t per_cta = (int64_t)wpb * 32;
+    if (h->range_first % per_cta != 0 || (h->range_count % per_cta != 0 && h->range_first + h->range_count != h->n))
+      return fail(VSS_E_INVALID, "step range: first / count must be multiples of vss_step_granularity()");
+    const_cast<StepArgs&>(a).env_begin = h->range_first;
+    const_cast<StepArgs&>(a).n = h->range_first + h->range_count;
+    grid = (unsigned)((h->range_count + per_cta - 1) / per_cta);
+  }
   static bool big_smem_ok[64] = {};  // per device: the attribute belongs to the function in one context
   if (smem > 48 * 1024 && !big_smem_ok[h->device & 63]) {
     VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -445,7 +454,7 @@ static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
     VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     big_smem_ok[h->device & 63] = true;
   }
-  if (sync_phases >= 4 && wpb > 1 && !INJECT) k_step<VIEW, INJECT, 2><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
+  if ((sync_phases & 7) >= 4 && wpb > 1 && !INJECT) k_step<VIEW, INJECT, 2><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
   else if (sync_phases && wpb > 1) k_step<VIEW, INJECT, 1><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
   else k_step<VIEW, INJECT, 0><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
   VSS_CUDA(cudaGetLastError());
@@ -498,6 +507,7 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
   if (!h) return fail(VSS_E_NOMEM, "vss_create: host allocation failed");
   h->device = device; h->n = num_envs; h->ld = (num_envs + 31) / 32 * 32; h->goff = global_env_offset;
   h->aux_obs_bf16 = nullptr; h->aux_done_f = nullptr; h->aux_timeout_f = nullptr;
+  h->range_first = 0; h->range_count = 0;
   h->seed = seed; h->d_step = nullptr; h->params = *p; h->dp = derive_params(*p); h->state = nullptr;
   const size_t bytes = sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld;
   e = cudaMalloc(&h->state, bytes);
@@ -613,6 +623,21 @@ VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, fl
 VSS_API int vss_set_step_aux(vss_handle h, void* obs_bf16, float* done_f32, float* timeout_f32) {
   if (!h) return fail(VSS_E_INVALID, "vss_set_step_aux: null handle");
   h->aux_obs_bf16 = obs_bf16; h->aux_done_f = done_f32; h->aux_timeout_f = timeout_f32;
+  return VSS_OK;
+}
+
+VSS_API int64_t vss_step_granularity(vss_handle h) {
+  if (!h) return 0;
+  int wpb; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem);
+  return (int64_t)wpb * 32;
+}
+
+VSS_API int vss_set_step_range(vss_handle h, int64_t first_field, int64_t num_fields) {
+  if (!h) return fail(VSS_E_INVALID, "vss_set_step_range: null handle");
+  if (first_field < 0 || num_fields < 0 || first_field + num_fields > h->n)
+    return fail(VSS_E_INVALID, "vss_set_step_range: range outside [0, num_envs)");
+  h->range_first = num_fields ? first_field : 0; h->range_count = num_fields;
   return VSS_OK;
 }
 

@@ -76,6 +76,14 @@ class Engine:
     def step_count(self, n):
         check(self.lib.vss_set_step_count(self._h, int(n)))
 
+    # ---- pipelining one step over several streams (include/vss_b200.h: vss_set_step_range)
+    @property
+    def step_granularity(self):
+        return int(self.lib.vss_step_granularity(self._h))
+
+    def set_step_range(self, first_field=0, num_fields=0):
+        check(self.lib.vss_set_step_range(self._h, int(first_field), int(num_fields)))
+
     # ---- hot path
     def reset_dones(self, reset_buf, obs):
         n = self.num_envs

@@ -115,21 +115,60 @@ class _FusedView(Wrapper):
         return {"obs": obs}, reward, self._done, infos
 
     # ---- the same call with HOST buffers (pinned): action in, (obs, reward, done) out
+    HOST_CHUNKS = 8            # large batches are stepped in this many field ranges ...
+    HOST_CHUNK_MIN_FIELDS = 1 << 17   # ... when there are at least this many fields
+
     def step_host(self, action_host):
+        """One step with host buffers. Large batches are pipelined: the fields are split into ranges
+        (`vss_set_step_range`), each with its own H2D copy -> kernel -> D2H copies on one of two side
+        streams, so the device-to-host copy of one range (PCIe-bound, 220 B per field) overlaps the
+        kernel of the next. Same kernels, same RNG keys: the results are bit-identical to `step()`."""
+        task, nv = self.task, self.num_view_envs
         if self._host is None:
-            nv = self.num_view_envs
             self._host = dict(
-                act=torch.empty((nv, self.ACT_DIM), device=self.task.device, dtype=torch.float32),
-                obs=torch.empty((nv, self.task.num_obs), dtype=torch.float32).pin_memory(),
+                act=torch.empty((nv, self.ACT_DIM), device=task.device, dtype=torch.float32),
+                obs=torch.empty((nv, task.num_obs), dtype=torch.float32).pin_memory(),
                 reward=torch.empty(nv, dtype=torch.float32).pin_memory(),
-                done=torch.empty(nv, dtype=torch.long).pin_memory())
+                done=torch.empty(nv, dtype=torch.long).pin_memory(),
+                streams=[torch.cuda.Stream(device=task.device) for _ in range(2)])
         h = self._host
-        h["act"].copy_(action_host.view(h["act"].shape), non_blocking=True)
-        obs, reward, done, _ = self.step(h["act"])
-        h["obs"].copy_(obs["obs"], non_blocking=True)
-        h["reward"].copy_(reward, non_blocking=True)
-        h["done"].copy_(done, non_blocking=True)
-        torch.cuda.current_stream(self.task.device).synchronize()
+        act_host = action_host.view(h["act"].shape)
+        n, agents = task.num_fields, nv // task.num_fields
+        chunks = self.HOST_CHUNKS if n >= self.HOST_CHUNK_MIN_FIELDS else 1
+        cur = torch.cuda.current_stream(task.device)
+        if chunks == 1:
+            h["act"].copy_(act_host, non_blocking=True)
+            obs, reward, done, _ = self.step(h["act"])
+            h["obs"].copy_(obs["obs"], non_blocking=True)
+            h["reward"].copy_(reward, non_blocking=True)
+            h["done"].copy_(done, non_blocking=True)
+            cur.synchronize()
+            return h["obs"], h["reward"], h["done"]
+        g = task.engine.step_granularity
+        per = -(-n // (chunks * g)) * g
+        start = torch.cuda.Event()
+        start.record(cur)
+        try:
+            for c in range(chunks):
+                f0 = c * per
+                cnt = min(per, n - f0)
+                if cnt <= 0:
+                    break
+                v0, v1 = f0 * agents, (f0 + cnt) * agents
+                s = h["streams"][c & 1]
+                with torch.cuda.stream(s):
+                    s.wait_event(start)
+                    h["act"][v0:v1].copy_(act_host[v0:v1], non_blocking=True)
+                    task.engine.set_step_range(f0, cnt)
+                    obs, reward, done, _ = self.step(h["act"])
+                    h["obs"][v0:v1].copy_(obs["obs"][v0:v1], non_blocking=True)
+                    h["reward"][v0:v1].copy_(reward[v0:v1], non_blocking=True)
+                    h["done"][v0:v1].copy_(done[v0:v1], non_blocking=True)
+        finally:
+            task.engine.set_step_range(0, 0)
+        for s in h["streams"]:
+            cur.wait_stream(s)
+        cur.synchronize()
         return h["obs"], h["reward"], h["done"]
 
     @property

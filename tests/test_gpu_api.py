@@ -207,3 +207,34 @@ def test_view_side_outputs_bf16_obs_and_float_flags(env_id, n):
     view.step(act)
     torch.cuda.synchronize()
     assert torch.all(x16 == 3.0)
+
+
+@pytest.mark.parametrize("env_id", ["sa", "dma"])
+def test_step_host_pipelined_over_field_ranges_is_bit_identical(env_id):
+    """`step_host` splits a large batch into field ranges (vss_set_step_range) on two streams; the
+    results and the engine state must equal the single-launch step bit for bit (same kernels, RNG
+    keyed by global field id and by the whole-engine step index)."""
+    from rsoccer_isaac_cleanrl_b200.envs import DMA, VSS, SingleAgent
+    n = 5000                                   # ragged: the last range ends at num_envs
+    cls = {"sa": SingleAgent, "dma": DMA}[env_id]
+    a, b = (cls(VSS(_cfg(n), "cuda:0", "cuda:0", 0, True, seed=31)) for _ in range(2))
+    a.HOST_CHUNKS, a.HOST_CHUNK_MIN_FIELDS = 5, 1          # force the pipelined path on the small batch
+    b.HOST_CHUNK_MIN_FIELDS = 1 << 30                      # single launch
+    for v in (a, b):                                       # some episodes end within the test
+        st = v.task.engine.get_state()
+        st[58, :n] = (torch.arange(n, device="cuda", dtype=torch.int32) % 7 + 392).view(torch.float32)
+        v.task.engine.set_state(st)
+    g = torch.Generator(); g.manual_seed(5)
+    for t in range(10):
+        act = (torch.rand((a.num_view_envs, a.ACT_DIM), generator=g) * 2 - 1).pin_memory()
+        oa, ra, da = a.step_host(act)
+        ob, rb, db = b.step_host(act)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), t
+    assert int(da.sum()) >= 0 and torch.equal(a.task.engine.get_state(), b.task.engine.get_state())
+    assert torch.equal(a.action_buf, b.action_buf)
+    assert a.task.engine.step_count == b.task.engine.step_count == 10
+    # a misaligned range is refused
+    with pytest.raises(RuntimeError):
+        a.task.engine.set_step_range(1, a.task.engine.step_granularity)
+        a.step(torch.zeros((a.num_view_envs, a.ACT_DIM), device="cuda"))
+    a.task.engine.set_step_range(0, 0)
