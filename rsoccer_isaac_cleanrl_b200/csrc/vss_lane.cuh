@@ -806,6 +806,7 @@ struct StepArgs {
   // optional side outputs of the views (vss_set_step_aux): the observation as bf16 rows padded to 64
   // columns (what the tensor-core MLP reads), done / timeout as floats (what the GAE kernel reads)
   void* obs_bf16; float* done_f; float* timeout_f;
+  int fpw;                     // fields per warp: 32, or 16 / 8 for small batches (idle lanes, shorter critical path)
   int stagger_ns;              // first-wave CTAs start (blockIdx % 6) * stagger_ns late (0 = off)
   int sync_level;              // 0: warps run free; >= 1: CTA-wide barriers keep them in the same code region
 };

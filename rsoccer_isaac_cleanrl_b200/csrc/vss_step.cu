@@ -204,13 +204,13 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  const long long env0 = a.env_begin + tile * 32;
+  const long long env0 = a.env_begin + tile * a.fpw;
   if (!SYNC && env0 >= a.n) { if (VIEW != VIEW_FULL) step_done(a, ctr); return; }  // (with block-level syncs every warp stays until the end)
   float* T = tiles + warp * TILE_STATE_WORDS;
   float* S = T + lane;
   const long long env = env0 + lane;
-  const bool active = env < a.n;
-  const int valid = (int)max(0LL, min(32LL, a.n - env0));
+  const bool active = lane < a.fpw && env < a.n;
+  const int valid = (int)max(0LL, min((long long)a.fpw, a.n - env0));
   constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
   const RngKey key = make_key(a, env);
   // 1. per lane: load, actions, physics, rewards, dones
@@ -394,8 +394,22 @@ static int env_int(const char* name, int dflt) {
 // region at the same time share its lines in the instruction caches (+25 % measured). Small
 // batches: 1-2 warps per CTA so that at least 148 CTAs exist; no barriers (latency matters there).
 // VSS_WPB / VSS_SYNC environment variables override (tuning).
-static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* smem, int* sync_level = nullptr) {
-  const int64_t tiles = (n + 31) / 32;
+// `fpw` (fields per warp, step kernels only): small batches leave most SMs empty and are bound by one
+// warp's critical path, which grows with the number of fields it owns (every contact of any of its fields
+// is serialised): 16 or 8 fields per warp (the other lanes idle in the per-field phases and help in the
+// cooperative observation writes).
+static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* smem, int* sync_level = nullptr,
+                      int* fields_per_warp = nullptr) {
+  int fpw = 32;
+  if (fields_per_warp) {
+    static const int forced_fpw = env_int("VSS_FPW", 0);
+    // measured (k_step<sa>, CUDA-graph timed, us per step at 32 / 16 / 8 fields per warp): 1024 fields 43.7 /
+    // 35.7 / 33.8; 4096: 46.4 / 40.0 / 36.2; 8192: 47.7 / 40.2 / 40.3; 16384: 48.7 / 44.4 / 47.5; 21845: 51.2 /
+    // 47.4 / 53.7; 32768: 53.9 / 53.8 / 84.2
+    fpw = n < 148 * 40 ? 8 : (n < 148 * 192 ? 16 : 32);
+    if (forced_fpw == 8 || forced_fpw == 16 || forced_fpw == 32) fpw = forced_fpw;
+  }
+  const int64_t tiles = (n + fpw - 1) / fpw;
   int wpb = 4, sync = 2;  // 6 CTAs of 4 warps per SM (measured at 2^20 fields: 4 / 6 / 8 / 12 warps per CTA ->
                           // 0.672 / 0.671 / 0.652 / 0.592 of the HBM roofline; at 2^16 fields 0.405 / 0.366 / 0.377)
   if (tiles < 148 * 2) { wpb = 1; sync = 0; }
@@ -407,10 +421,12 @@ static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* s
   if (forced_sync >= 0) sync = forced_sync;
   if (wpb == 1) sync = 0;
   if ((sync & 7) >= 4 && wpb > 8) sync = 2;  // the CTA-wide task queues index fields with 8 bits
+  if ((sync & 7) >= 4 && fpw != 32) sync = 2;  // (and assume thread t owns field t of the CTA)
   *warps_per_block = wpb;
   *grid = (unsigned)((tiles + wpb - 1) / wpb);
   *smem = sizeof(float) * smem_words(wpb);
   if (sync_level) *sync_level = sync;
+  if (fields_per_warp) *fields_per_warp = fpw;
   return 0;
 }
 
@@ -431,16 +447,17 @@ static StepArgs base_args(vss_handle h) {
 
 template <int VIEW, bool INJECT>
 static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
-  int wpb, sync_phases; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem, &sync_phases);
+  int wpb, sync_phases, fpw; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem, &sync_phases, &fpw);
   const_cast<StepArgs&>(a).sync_level = sync_phases;
+  const_cast<StepArgs&>(a).fpw = fpw;
   // First-wave stagger (profiles/r01_g_*.md): 5 us per resident CTA of an SM, measured best of 0-12 us
   // at 2^20 fields (675 -> 652 us per step); only when the launch is longer than one wave.
   static const int stagger = env_int("VSS_STAGGER_NS", -1);
   const_cast<StepArgs&>(a).stagger_ns = stagger >= 0 ? stagger : (grid > 148u * 6u ? 5000 : 0);
   const_cast<StepArgs&>(a).grid = grid;  // the step index is counted in CTAs of the WHOLE engine
   if (h->range_count > 0) {  // vss_set_step_range: this launch covers [first, first + count) — same CTA shape, fewer CTAs
-    const int64_t per_cta = (int64_t)wpb * 32;
+    const int64_t per_cta = (int64_t)wpb * fpw;
     if (h->range_first % per_cta != 0 || (h->range_count % per_cta != 0 && h->range_first + h->range_count != h->n))
       return fail(VSS_E_INVALID, "step range: first / count must be multiples of vss_step_granularity()");
     const_cast<StepArgs&>(a).env_begin = h->range_first;
@@ -536,15 +553,15 @@ VSS_API uint64_t vss_step_count(vss_handle h) {
   unsigned long long v = 0;
   if (use_device(h) != VSS_OK) return 0;
   if (cudaMemcpy(&v, h->d_step, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-  int wpb; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem);
+  int wpb, sync, fpw; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem, &sync, &fpw);
   return v / grid;
 }
 VSS_API int vss_set_step_count(vss_handle h, uint64_t n) {
   if (!h) return fail(VSS_E_INVALID, "null handle");
   if (int rc = use_device(h)) return rc;
-  int wpb; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem);
+  int wpb, sync, fpw; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem, &sync, &fpw);
   const unsigned long long v = (unsigned long long)(uint32_t)n * grid;
   VSS_CUDA(cudaMemcpy(h->d_step, &v, sizeof(v), cudaMemcpyHostToDevice));
   return VSS_OK;
@@ -628,9 +645,9 @@ VSS_API int vss_set_step_aux(vss_handle h, void* obs_bf16, float* done_f32, floa
 
 VSS_API int64_t vss_step_granularity(vss_handle h) {
   if (!h) return 0;
-  int wpb; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem);
-  return (int64_t)wpb * 32;
+  int wpb, sync, fpw; unsigned grid; size_t smem;
+  launch_cfg(h->n, &wpb, &grid, &smem, &sync, &fpw);
+  return (int64_t)wpb * fpw;
 }
 
 VSS_API int vss_set_step_range(vss_handle h, int64_t first_field, int64_t num_fields) {
