@@ -238,3 +238,32 @@ def test_step_host_pipelined_over_field_ranges_is_bit_identical(env_id):
         a.task.engine.set_step_range(1, a.task.engine.step_granularity)
         a.step(torch.zeros((a.num_view_envs, a.ACT_DIM), device="cuda"))
     a.task.engine.set_step_range(0, 0)
+
+
+@pytest.mark.parametrize("n", [100, 3000, 9000, 40000])
+def test_outputs_stay_inside_their_buffers(n):
+    """Every output of the view step (incl. the side outputs) is a slice of a larger buffer filled with a
+    sentinel: the kernel must write every row of the slice and nothing outside it. Sizes cover 8 / 16 /
+    32 fields per warp and ragged last tiles."""
+    from rsoccer_isaac_cleanrl_b200.envs import DMA, VSS, SingleAgent
+    PAD, SENT = 300, -12345.0
+    for cls in (SingleAgent, DMA):
+        view = cls(VSS(_cfg(n), "cuda:0", "cuda:0", 0, True, seed=n))
+        nv = view.num_view_envs
+
+        def guarded(cols, dtype=torch.float32, sent=SENT):
+            big = torch.full(((nv + 2 * PAD) * cols,), sent, device="cuda", dtype=dtype)
+            return big, big[PAD * cols:(PAD + nv) * cols].view((nv, cols) if cols > 1 else (nv,))
+
+        bufs = {k: guarded(c) for k, c in (("obs", 52), ("term", 52), ("rew", 1), ("done_f", 1), ("tmo_f", 1))}
+        bufs["x16"] = guarded(64, torch.bfloat16)
+        act = torch.rand((nv, view.ACT_DIM), device="cuda") * 2 - 1
+        view.step(act, obs_out=bufs["obs"][1], term_obs_out=bufs["term"][1], reward_out=bufs["rew"][1],
+                  obs_bf16_out=bufs["x16"][1], done_f_out=bufs["done_f"][1], timeout_f_out=bufs["tmo_f"][1])
+        torch.cuda.synchronize()
+        for k, (big, sl) in bufs.items():
+            cols = sl.shape[1] if sl.dim() == 2 else 1
+            assert torch.all(big[:PAD * cols] == SENT) and torch.all(big[(PAD + nv) * cols:] == SENT), (k, "outside")
+            inner = sl[:, :52] if k == "x16" else sl
+            assert not torch.any(inner == SENT), (k, "unwritten rows")
+        assert torch.all(bufs["x16"][1][:, 52:] == SENT)
