@@ -8,6 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rsoccer_isaac_cleanrl_b200.engine import (EPI_ATOMIC_F32, EPI_BIAS_TANH_BF16, EPI_DTANH_BF16,  # noqa: E402
                                                gemm_bf16)
+from rsoccer_isaac_cleanrl_b200.tc_mlp import _splits  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 M = 131072
@@ -46,8 +47,7 @@ for (n_out, k_in) in [(256, 64), (512, 256), (512, 512), (256, 512)]:   # wgrad:
     dz = torch.randn(M, n_out, device=dev).to(torch.bfloat16)
     x = torch.randn(M, k_in, device=dev).to(torch.bfloat16)
     dw = torch.zeros(n_out, k_in, device=dev)
-    tiles = (n_out // 128) * max(1, k_in // (128 if k_in % 128 == 0 else 64))
-    splits = max(1, 296 // tiles)
+    splits = _splits(n_out, k_in, M)   # the PPO loop's own choice (tc_mlp.py)
     t = timeit(lambda: gemm_bf16(dz, x, dw, EPI_ATOMIC_F32, splits=splits, mn_major=True))
     rows.append(("wgrad split-K ", n_out, k_in, M, t))
 tot_f = tot_t = 0.0

@@ -22,7 +22,16 @@ def _splits(n_out, k_in, batch):
     tiles = (n_out // 128) * max(1, k_in // (128 if k_in % 128 == 0 else 64))
     # floor, not ceil: with more tiles than resident CTAs (2 per SM) a few CTAs would run a second tile
     # alone and the launch would take two tile-times
-    return max(1, min((batch + 63) // 64, _SM_TARGET // tiles))
+    target = _SM_TARGET // tiles
+    # Every split adds n_out x k_in fp32 atomics on the same addresses; with few output tiles the atomics,
+    # not the operand stream, bound the launch. Measured at batch 131072 (profiles/wgrad_splits_bench.py, us):
+    # 256x64: 148 splits 37.3, 49 splits 25.0; 512x256: 37 -> 67.5, 27 -> 60.2; 256x512: 37 -> 67.6, 27 -> 61.9;
+    # 512x512: 18 -> 80.0 (best).
+    if tiles <= 2:
+        target //= 3
+    elif tiles <= 8:
+        target = target * 3 // 4
+    return max(1, min((batch + 63) // 64, target))
 
 
 class TCMlp(torch.autograd.Function):
