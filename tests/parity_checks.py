@@ -449,6 +449,95 @@ def check_pair_stress(Backend, n=4096, steps=6, seed=13):
     return flips
 
 
+def _place(be, mutate):
+    """Reset everything, then overwrite the state through `mutate(State)` (robots parked far apart)."""
+    n = be.n
+    rb = np.ones(n, np.int64)
+    be.reset_dones(rb)
+    st = oracle_from_backend(be)
+    st.ball_pos[:] = (0.0, 0.55); st.ball_vel[:] = 0
+    park = np.array([[-0.6, -0.5], [-0.3, -0.5], [0.0, -0.5], [0.3, -0.5], [0.6, -0.5], [0.6, 0.5]], np.float32)
+    st.r_pos[:] = park.reshape(1, 2, 3, 2); st.r_vel[:] = 0; st.r_w[:] = 0; st.r_act[:] = 0
+    st.r_rot[:] = (1.0, 0.0)
+    st.progress[:] = 0
+    mutate(st)
+    be.set_state(st.to_soa(be.ld))
+    return np.zeros(n, np.int64)
+
+
+def check_physics_spec(Backend):
+    """The new 2-D model against the numbers the reference's scene description implies (SURVEY App. B;
+    vss_robot.urdf, vss.py:427-434): these are properties of the SPEC, not of PhysX's solver."""
+    p = orc.default_params()
+    r_w, track, wmax = 0.024, 0.0675, 42.0
+    v_max, yaw_max = r_w * wmax, r_w * 2 * wmax / track          # 1.008 m/s, 29.87 rad/s
+    # 1. straight drive: terminal speed r_w * 42 rad/s, reached within a few control steps, and the
+    #    traction limit mu m g caps the acceleration (0.7 * 9.81 * 0.05 = 0.343 m/s per control step)
+    def lane(st):
+        st.r_pos[:, 0, 0] = (-0.6, 0.0)                          # a free lane along y = 0
+
+    be = Backend(4, seed=1, goff=0, params=p)
+    rb = _place(be, lane)
+    act = np.zeros((4, 2, 3, 2), np.float32); act[:, 0, 0] = (1.0, 1.0)
+    speeds = []
+    for t in range(12):
+        be.step(act, rb); rb[:] = 0
+        speeds.append(float(np.linalg.norm(oracle_from_backend(be).r_vel[0, 0, 0])))
+    assert abs(speeds[-1] - v_max) < 0.01 * v_max, speeds
+    assert speeds[3] > 0.9 * v_max, speeds                       # "0 -> 1 m/s takes about 3 control steps"
+    assert max(np.diff([0.0] + speeds)) <= 0.7 * 9.81 * 0.05 * 1.001, speeds
+    st = oracle_from_backend(be)
+    assert abs(st.r_vel[0, 0, 0, 1]) < 1e-6 and abs(st.r_w[0, 0, 0]) < 1e-6   # straight: no drift, no spin
+    assert np.allclose(st.r_vel[0, 0, 1:], 0, atol=1e-7) and np.allclose(st.r_vel[0, 1], 0, atol=1e-7)
+    # 2. spin in place: yaw rate r_w (w_r - w_l) / track; DOF 0 is the left wheel (vss.py / urdf)
+    be = Backend(4, seed=1, goff=0, params=p)
+    rb = _place(be, lane)
+    act = np.zeros((4, 2, 3, 2), np.float32); act[:, 0, 0] = (-1.0, 1.0)
+    for t in range(12):
+        be.step(act, rb); rb[:] = 0
+    st = oracle_from_backend(be)
+    assert abs(st.r_w[0, 0, 0] - yaw_max) < 0.01 * yaw_max, st.r_w[0, 0, 0]
+    assert np.linalg.norm(st.r_pos[0, 0, 0] - np.array([-0.6, 0.0])) < 1e-3            # turns on the spot
+    assert abs(np.linalg.norm(st.r_rot[0, 0, 0]) - 1.0) < 1e-6
+    # 3. free rolling ball: exponential decay with the rolling-sphere share (2/7) of PhysX's angular damping 0.5
+    be = Backend(4, seed=1, goff=0, params=p)
+    def roll(st):
+        st.ball_pos[:] = (-0.5, 0.0); st.ball_vel[:] = (0.5, 0.0)
+    rb = _place(be, roll)
+    act = np.zeros((4, 2, 3, 2), np.float32)
+    for t in range(20):                                          # 1 s
+        be.step(act, rb); rb[:] = 0
+    st = oracle_from_backend(be)
+    assert abs(st.ball_vel[0, 0] - 0.5 * np.exp(-0.5 * 2 / 7)) < 1e-4 and abs(st.ball_vel[0, 1]) < 1e-7
+    # 4. walls: restitution 0 (the ball keeps no normal velocity), nothing leaves the field, and the ball
+    #    only passes the end line through the goal mouth |y| < 0.2 (vss.py:342-345) — which ends the episode
+    be = Backend(4, seed=1, goff=0, params=p)
+    def shoot(st):
+        st.ball_pos[0] = (0.0, 0.6); st.ball_vel[0] = (0.0, 2.0)          # into the side wall
+        st.ball_pos[1] = (0.7, 0.4); st.ball_vel[1] = (2.0, 0.0)          # into the end wall beside the goal
+        st.ball_pos[2] = (0.7, 0.1); st.ball_vel[2] = (2.0, 0.0)          # into the yellow goal
+        st.ball_pos[3] = (-0.7, -0.1); st.ball_vel[3] = (-2.0, 0.0)       # into the blue goal
+    rb = _place(be, shoot)
+    out = be.step(act, rb)
+    st = oracle_from_backend(be)
+    assert abs(st.ball_pos[0, 1]) <= 0.65 - 0.02134 + 1e-5 and abs(st.ball_vel[0, 1]) < 1e-6
+    assert abs(st.ball_pos[1, 0]) <= 0.75 - 0.02134 + 1e-5 and abs(st.ball_vel[1, 0]) < 1e-6
+    assert rb.tolist() == [0, 0, 1, 1]
+    assert out["rew"][2, 0, 0, 0] == 10.0 and out["rew"][2, 1, 0, 0] == -10.0     # blue attacks +x (vss.py:589-594)
+    assert out["rew"][3, 0, 0, 0] == -10.0 and out["rew"][3, 1, 0, 0] == 10.0
+    # 5. a robot driving into the ball pushes it ahead (contact + Coulomb friction 0.5), without tunnelling
+    be = Backend(4, seed=1, goff=0, params=p)
+    def push(st):
+        st.r_pos[:, 0, 0] = (-0.2, 0.0); st.ball_pos[:] = (-0.12, 0.0)
+    rb = _place(be, push)
+    act = np.zeros((4, 2, 3, 2), np.float32); act[:, 0, 0] = (1.0, 1.0)
+    for t in range(10):
+        be.step(act, rb); rb[:] = 0
+        st = oracle_from_backend(be)
+        assert st.ball_pos[0, 0] - st.r_pos[0, 0, 0, 0] >= 0.035 + 0.02134 - 1e-4, t   # ball stays in front of the face
+    assert st.ball_vel[0, 0] > 0.8 and abs(st.ball_pos[0, 1]) < 1e-3
+
+
 def check_nonfinite_guard(Backend, n=96):
     """Safety net: a field whose state is not finite is re-randomised on the spot, reported done with
     zero reward and no timeout; its neighbours are untouched; backend and oracle agree."""

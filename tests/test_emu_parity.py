@@ -53,3 +53,7 @@ def test_wall_and_goal_post_contacts_track_oracle():
 
 def test_robot_pair_contacts_track_oracle():
     print("flips", pc.check_pair_stress(EmuBackend))
+
+
+def test_physics_model_embodies_the_scene_spec():
+    pc.check_physics_spec(EmuBackend)

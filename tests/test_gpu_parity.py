@@ -174,3 +174,7 @@ def test_wall_and_goal_post_contacts_track_oracle(Gpu):
 
 def test_robot_pair_contacts_track_oracle(Gpu):
     pc.check_pair_stress(Gpu, n=8192, steps=6)
+
+
+def test_physics_model_embodies_the_scene_spec(Gpu):
+    pc.check_physics_spec(Gpu)
