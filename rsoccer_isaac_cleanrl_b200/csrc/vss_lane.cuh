@@ -42,6 +42,10 @@
 namespace vss {
 
 constexpr int INTEG_UNROLL = VSS_INTEG_UNROLL;
+#ifndef VSS_OBS_UNROLL
+#define VSS_OBS_UNROLL 4  // fields per iteration of the row-owner observation writer (multiple of the tail packing G)
+#endif
+constexpr int OBS_UNROLL = VSS_OBS_UNROLL;
 constexpr int LDS = 33;       // shared-memory column stride in words
 constexpr int W_PREV = 60;    // 7 words of pre-physics reward terms: ball potential, 6 robot-ball distances
 constexpr int SM_WORDS = 67;  // words per field staged in shared memory
@@ -1036,7 +1040,7 @@ VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, i
     }
   }
   static_assert(G <= 4 && 4 % G == 0, "the tail packing assumes the field loop is unrolled by a multiple of G");
-#pragma unroll 4
+#pragma unroll(OBS_UNROLL)
   for (int e = 0; e < valid; ++e) {
     const bool keep = !((skip_mask >> e) & 1u);
 #pragma unroll
