@@ -43,7 +43,8 @@ namespace vss {
 
 constexpr int INTEG_UNROLL = VSS_INTEG_UNROLL;
 #ifndef VSS_OBS_UNROLL
-#define VSS_OBS_UNROLL 4  // fields per iteration of the row-owner observation writer (multiple of the tail packing G)
+#define VSS_OBS_UNROLL 1  // fields per iteration of the row-owner observation writer: 8 / 4 / 2 / 1 -> 657.3 / 644.5 / 640.2 /
+                          // 636.5 us per step at 2^20 fields (code size beats loop overhead: the kernel is fetch-bound)
 #endif
 constexpr int OBS_UNROLL = VSS_OBS_UNROLL;
 constexpr int LDS = 33;       // shared-memory column stride in words
@@ -1039,7 +1040,6 @@ VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, i
       sgn[sl][c] = (by >> 7) << 31;
     }
   }
-  static_assert(G <= 4 && 4 % G == 0, "the tail packing assumes the field loop is unrolled by a multiple of G");
 #pragma unroll(OBS_UNROLL)
   for (int e = 0; e < valid; ++e) {
     const bool keep = !((skip_mask >> e) & 1u);
