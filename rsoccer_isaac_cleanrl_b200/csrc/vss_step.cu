@@ -195,7 +195,7 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   // The CTAs of the first wave all start at once and would run their load / compute / store phases in
   // lock-step (memory idle while they all compute, then all storing); the CTAs that take their slots
   // later inherit the rhythm. Start the co-resident CTAs of an SM a little apart.
-  if (SYNC && a.stagger_ns > 0 && blockIdx.x < 148u * 6u) {
+  if (a.stagger_ns > 0 && blockIdx.x < 148u * 6u) {
     // CTAs are handed out round-robin over the 148 SMs: the k-th CTA of an SM is blockIdx / 148
     const unsigned wait_ns = ((blockIdx.x / 148u) % 6u) * (unsigned)a.stagger_ns;
     const unsigned long long t0 = globaltimer_ns();
@@ -454,7 +454,8 @@ static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
   // First-wave stagger (profiles/r01_g_*.md): 5 us per resident CTA of an SM, measured best of 0-12 us
   // at 2^20 fields (675 -> 652 us per step); only when the launch is longer than one wave.
   static const int stagger = env_int("VSS_STAGGER_NS", -1);
-  const_cast<StepArgs&>(a).stagger_ns = stagger >= 0 ? stagger : (grid > 148u * 6u ? 5000 : 0);
+  static const int stagger_min_grid = env_int("VSS_STAGGER_MIN_GRID", 148 * 6 + 1);
+  const_cast<StepArgs&>(a).stagger_ns = (int)grid >= stagger_min_grid ? (stagger >= 0 ? stagger : 5000) : 0;
   const_cast<StepArgs&>(a).grid = grid;  // the step index is counted in CTAs of the WHOLE engine
   if (h->range_count > 0) {  // vss_set_step_range: this launch covers [first, first + count) — same CTA shape, fewer CTAs
     const int64_t per_cta = (int64_t)wpb * fpw;
