@@ -455,7 +455,10 @@ static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
   // at 2^20 fields (675 -> 652 us per step); only when the launch is longer than one wave.
   static const int stagger = env_int("VSS_STAGGER_NS", -1);
   static const int stagger_min_grid = env_int("VSS_STAGGER_MIN_GRID", 148 * 6 + 1);
-  const_cast<StepArgs&>(a).stagger_ns = (int)grid >= stagger_min_grid ? (stagger >= 0 ? stagger : 5000) : 0;
+  // (only the barrier-synchronised shape of the large batches: the 2-warp shape used up to 2 960 tiles has
+  // more than 888 CTAs from 57 K fields on, but all of them are resident at once and the delay only hurts)
+  const_cast<StepArgs&>(a).stagger_ns =
+      ((int)grid >= stagger_min_grid && sync_phases && wpb > 1) ? (stagger >= 0 ? stagger : 5000) : 0;
   const_cast<StepArgs&>(a).grid = grid;  // the step index is counted in CTAs of the WHOLE engine
   if (h->range_count > 0) {  // vss_set_step_range: this launch covers [first, first + count) — same CTA shape, fewer CTAs
     const int64_t per_cta = (int64_t)wpb * fpw;
