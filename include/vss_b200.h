@@ -194,6 +194,20 @@ VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, fl
  * vss_step_view is called, so they may change from step to step. */
 VSS_API int vss_set_step_aux(vss_handle h, void* obs_bf16, float* done_f32, float* timeout_f32);
 
+/* Optional packed per-agent output of the following vss_step_view launches (NULL = off), for a caller
+ * on the HOST side of the PCIe link (what SingleAgent/CMA/DMA.step returns to the policy,
+ * envs/wrappers.py:108-115, in as few bytes as carry it): one row of VSS_PACKED_ROW_BYTES = 112 bytes
+ * per view env,
+ *   bytes   0..103  the 52 observation values as bf16 (round to nearest even)
+ *   bytes 104..107  the scalar reward, f32
+ *   byte  108       done (0 / 1)          byte 109  time-out (0 / 1)          bytes 110..111  zero
+ * `rows` is any pointer the device can write: device memory (staging for one cudaMemcpyAsync per field
+ * range) or pinned host memory (cudaHostAlloc is device-mapped under unified addressing: the kernel then
+ * stores straight across PCIe and no copy is issued at all). Host-side state of the handle, like
+ * vss_set_step_aux. */
+#define VSS_PACKED_ROW_BYTES 112
+VSS_API int vss_set_step_packed(vss_handle h, void* rows);
+
 /* Restricts the following vss_step / vss_step_view launches to the fields [first_field, first_field +
  * num_fields) (num_fields = 0: the whole engine again). Buffers keep their whole-engine shapes and base
  * pointers; only the rows of the range are read and written. For a caller that pipelines one step over
@@ -209,10 +223,13 @@ VSS_API int vss_set_step_range(vss_handle h, int64_t first_field, int64_t num_fi
  * (VSS_STATE_WORDS x ld 32-bit words) device->device. */
 VSS_API int vss_get_state(vss_handle h, float* state_out, void* stream);
 VSS_API int vss_set_state(vss_handle h, const float* state_in, void* stream);
-/* number of vss_step_view launches executed so far (keys the OU-noise RNG of the views; vss_step
- * draws no noise and does not advance it). The counter is device-resident and advanced by the step
- * kernel itself, so CUDA-graph replays of a captured vss_step_view launch advance it too; these two
- * calls synchronise with the device. */
+/* number of view steps executed so far (keys the OU-noise RNG of the views; vss_step draws no noise
+ * and does not advance it). The counter is device-resident and advanced by the step kernel itself — by
+ * the CTA that completes the step, counted over all the range launches of that step — so CUDA-graph
+ * replays of a captured vss_step_view launch advance it too; these two calls synchronise with the
+ * device. vss_set_step_count also forgets a partially issued step (a caller that abandons a step after
+ * some of its range launches must call it before the next step); values above UINT32_MAX are rejected
+ * (the index is one 32-bit word of the Philox counter). */
 VSS_API uint64_t vss_step_count(vss_handle h);
 VSS_API int vss_set_step_count(vss_handle h, uint64_t n);
 

@@ -16,6 +16,7 @@ CSRC = os.path.join(_PKG, "csrc")
 VIEW_SA, VIEW_CMA, VIEW_DMA = 0, 1, 2
 STATE_FLOATS, STATE_WORDS = 58, 60
 W_PROGRESS, W_EPISODE = 58, 59
+PACKED_ROW_BYTES = 112  # VSS_PACKED_ROW_BYTES: 52 bf16 obs | f32 reward | u8 done | u8 timeout | 2 zero bytes
 
 
 class VssParams(C.Structure):
@@ -66,6 +67,7 @@ _SYMBOLS = {
     "vss_step_injected": (C.c_int, [_VP] * 10),
     "vss_step_view": (C.c_int, [_VP, C.c_int] + [_VP] * 15),
     "vss_set_step_aux": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "vss_set_step_packed": (C.c_int, [_VP, _VP]),
     "vss_step_granularity": (C.c_int64, [_VP]),
     "vss_set_step_range": (C.c_int, [_VP, C.c_int64, C.c_int64]),
     "vss_get_state": (C.c_int, [_VP, _VP, _VP]),

@@ -784,7 +784,16 @@ VSS_HD F4 ld4(const float* p) { return F4{p[0], p[1], p[2], p[3]}; }
 VSS_HD void st4(float* p, const F4& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
 VSS_HD void st4_stream(float* p, const F4& v) { st4(p, v); }
 VSS_HD float ldg(const float* p) { return *p; }
-VSS_HD void st_bf16x4(void*, long long, const F4&) {}  // (the host emulation has no bf16 side output)
+VSS_HD uint32_t bf16_rne(float f) {  // round to nearest even, as __float2bfloat16_rn (NaN stays NaN)
+  const uint32_t u = fbits(f);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 0x7FFFu;
+  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
+VSS_HD void st_bf16x4(void* base, long long off, const F4& v) {
+  unsigned short* p = reinterpret_cast<unsigned short*>(base) + off;
+  p[0] = (unsigned short)bf16_rne(v.x); p[1] = (unsigned short)bf16_rne(v.y);
+  p[2] = (unsigned short)bf16_rne(v.z); p[3] = (unsigned short)bf16_rne(v.w);
+}
 #endif
 
 constexpr int VIEW_FULL = -1;
@@ -793,11 +802,10 @@ struct StepArgs {
   float* state; long long n, ld; unsigned long long goff;  // n = end of the field range of this launch
   long long env_begin;         // first field of this launch (0 unless vss_set_step_range restricts it)
   uint32_t seed_lo, seed_hi;
-  // Device-resident step index (keys the OU stream), kept as the number of step-kernel CTAs that have
-  // finished over the engine's life: every launch of an engine has the same grid, launches are
-  // stream-ordered, so at any time inside launch k the counter is in [k grid, (k+1) grid) and
-  // step = counter / grid. Every CTA adds 1 when it is done (fire-and-forget), so a CUDA graph that
-  // replays the launch still advances the index and no second kernel is needed.
+  // Device-resident step index (keys the OU stream): step_ctr[0] = index, step_ctr[1] = CTAs of the
+  // current step that have finished. The CTA that brings the count to `grid` (the CTAs of a whole-engine
+  // launch; a step issued as several range launches adds up to the same number) clears it and advances
+  // the index, so a CUDA graph that replays the launch advances the index without a second kernel.
   unsigned long long* step_ctr;
   uint32_t grid;
   const float* actions;        // full: (N,2,3,2)
@@ -814,9 +822,10 @@ struct StepArgs {
   // optional side outputs of the views (vss_set_step_aux): the observation as bf16 rows padded to 64
   // columns (what the tensor-core MLP reads), done / timeout as floats (what the GAE kernel reads)
   void* obs_bf16; float* done_f; float* timeout_f;
+  // optional packed per-agent rows (vss_set_step_packed): 52 bf16 obs | f32 reward | u8 done | u8 timeout | 0
+  void* packed;
   int fpw;                     // fields per warp: 32, or 16 / 8 for small batches (idle lanes, shorter critical path)
-  int stagger_ns;              // first-wave CTAs start (blockIdx % 6) * stagger_ns late (0 = off)
-  int sync_level;              // 0: warps run free; >= 1: CTA-wide barriers keep them in the same code region
+  int stagger_ns;              // first-wave CTAs start (blockIdx / 148 % 6) * stagger_ns late (0 = off)
 };
 
 template <int VIEW>
@@ -827,9 +836,9 @@ struct ViewShape {
 
 VSS_HD uint32_t step_index(const StepArgs& a) {
 #if defined(__CUDA_ARCH__)
-  return (uint32_t)(__ldcg(a.step_ctr) / a.grid);  // read at L2, where the other CTAs' adds land
+  return (uint32_t)__ldcg(a.step_ctr);  // read at L2, where the advancing CTA's add lands
 #else
-  return (uint32_t)(*a.step_ctr / a.grid);
+  return (uint32_t)*a.step_ctr;
 #endif
 }
 
@@ -961,6 +970,11 @@ VSS_HD int lane_phase1d(float* S, long long env, const StepArgs& a, const DevPar
       if (a.done_f) a.done_f[v] = done ? 1.0f : 0.0f;
       if (a.timeout_f) a.timeout_f[v] = tmo ? 1.0f : 0.0f;
       if (a.progress_f) a.progress_f[v] = (float)progress;
+      if (a.packed) {  // bytes 104..111 of the agent's packed row
+        uint32_t* tail = reinterpret_cast<uint32_t*>(static_cast<char*>(a.packed) + v * VSS_PACKED_ROW_BYTES + 104);
+        tail[0] = fbits(fadd(fadd(fadd(r4[0], r4[1]), r4[2]), r4[3]));
+        tail[1] = (done ? 1u : 0u) | (tmo ? 0x100u : 0u);
+      }
       if (a.ep_ret) {  // RecordEpisodeStatisticsTorch.step, wrappers.py:68-75
         const float keep = done ? 0.0f : 1.0f;
         F4 er = ld4(a.ep_ret + 4 * v);
@@ -995,9 +1009,12 @@ VSS_HD void lane_phase5(const float* S, long long env, const StepArgs& a, bool d
 //   skip_mask = fields whose `ob` row is NOT written now (they are reset first)
 // Element offset, in a (rows, 64) bf16 matrix, of float4 slot f of a (rows, 52) f32 matrix.
 VSS_HD int bf16_pad_offset(int f) { const int row = f / F4_PER_ROW; return row * 64 + (f - row * F4_PER_ROW) * 4; }
+// The same for the packed rows of vss_set_step_packed (112 bytes = 56 bf16 elements per row).
+constexpr int PACKED_ROW_ELEMS = VSS_PACKED_ROW_BYTES / 2;
+VSS_HD int packed_offset(int f) { const int row = f / F4_PER_ROW; return row * PACKED_ROW_ELEMS + (f - row * F4_PER_ROW) * 4; }
 
 VSS_HD void write_obs_tile(const float* T, const uint32_t* tab, int lane, int valid, int per_field, float* tob,
-                           float* ob, uint32_t skip_mask, void* obh = nullptr) {
+                           float* ob, uint32_t skip_mask, void* obh = nullptr, void* pk = nullptr) {
   const int total = valid * per_field;
 #pragma unroll 4
   for (int f = lane; f < total; f += 32) {
@@ -1007,6 +1024,7 @@ VSS_HD void write_obs_tile(const float* T, const uint32_t* tab, int lane, int va
     if (!((skip_mask >> e) & 1u)) {
       st4(ob + 4 * f, v);
       if (obh) st_bf16x4(obh, bf16_pad_offset(f), v);
+      if (pk) st_bf16x4(pk, packed_offset(f), v);
     }
   }
 }
@@ -1021,7 +1039,7 @@ VSS_HD void write_obs_tile(const float* T, const uint32_t* tab, int lane, int va
 // (16 or 8 lanes wide) writes the tail of field e + g.
 template <int PER_FIELD>
 VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, int valid, float* tob, float* ob,
-                                uint32_t skip_mask, void* obh = nullptr) {
+                                uint32_t skip_mask, void* obh = nullptr, void* pk = nullptr) {
   constexpr int FULL = PER_FIELD / 32, TAIL = PER_FIELD - 32 * FULL;
   constexpr int TW = TAIL <= 1 ? 1 : TAIL <= 2 ? 2 : TAIL <= 4 ? 4 : TAIL <= 8 ? 8 : TAIL <= 16 ? 16 : 32;
   constexpr int G = 32 / TW, SLOTS = FULL + (TAIL ? 1 : 0);
@@ -1052,6 +1070,7 @@ VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, i
       if (keep) {
         st4_stream(ob + idx, v);
         if (obh) st_bf16x4(obh, bf16_pad_offset(idx >> 2), v);
+        if (pk) st_bf16x4(pk, packed_offset(idx >> 2), v);
       }
     }
     if (TAIL && (e % G) == 0 && tail_lane && e + sub < valid) {  // fields e .. e+G-1, one lane group each
@@ -1063,13 +1082,14 @@ VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, i
       if (!((skip_mask >> (e + sub)) & 1u)) {
         st4_stream(ob + idx, v);
         if (obh) st_bf16x4(obh, bf16_pad_offset(idx >> 2), v);
+        if (pk) st_bf16x4(pk, packed_offset(idx >> 2), v);
       }
     }
   }
 }
 
 VSS_HD void write_obs_fields(const float* T, const uint32_t* tab, int lane, int per_field, float* ob,
-                             uint32_t field_mask, void* obh = nullptr) {
+                             uint32_t field_mask, void* obh = nullptr, void* pk = nullptr) {
   while (field_mask) {
     const int e = ffs32(field_mask) - 1;
     field_mask &= field_mask - 1;
@@ -1077,6 +1097,7 @@ VSS_HD void write_obs_fields(const float* T, const uint32_t* tab, int lane, int 
       const F4 v = obs_gather(T, tab[j], e);
       st4(ob + 4 * (e * per_field + j), v);
       if (obh) st_bf16x4(obh, bf16_pad_offset(e * per_field + j), v);
+      if (pk) st_bf16x4(pk, packed_offset(e * per_field + j), v);
     }
   }
 }

@@ -43,8 +43,7 @@ __host__ __device__ constexpr size_t smem_words(int wpb) {
 // on any field of the tile because the state columns live in shared memory — then the ball-wall
 // phase per lane.
 template <bool SYNC>
-__device__ __forceinline__ void physics_tile(float* T, uint8_t* queue, int lane, bool active, const DevParams& P,
-                                             int sync_level) {
+__device__ __forceinline__ void physics_tile(float* T, uint8_t* queue, int lane, bool active, const DevParams& P) {
   float* S = T + lane;
 #pragma unroll 1
   for (int it = 0; it < P.substeps; ++it) {
@@ -67,7 +66,7 @@ __device__ __forceinline__ void physics_tile(float* T, uint8_t* queue, int lane,
       m &= m - 1;
       queue[pos++] = (uint8_t)((lane << 3) | r);
     }
-    if (SYNC && (sync_level & 7) >= 3) __syncthreads(); else __syncwarp();
+    __syncwarp();
 #pragma unroll 1
     for (int t0 = 0; t0 < total; t0 += 32) {  // warp-uniform trip count: usually one pass, rarely more
       if (t0 + lane < total) {
@@ -75,94 +74,8 @@ __device__ __forceinline__ void physics_tile(float* T, uint8_t* queue, int lane,
         robot_walls_task(T + (q >> 3), q & 7, P);
       }
     }
-    if (SYNC && (sync_level & 7) >= 3) __syncthreads(); else __syncwarp();
+    __syncwarp();
     if (active) substep_ball_walls_lane(S, P);
-  }
-}
-
-// CTA-wide version. Contacts are rare per field (a few per cent of the fields per substep) but
-// almost certain per 32-field warp, so with one lane per field the contact code runs at 2-4
-// active lanes and takes 40 % of the issue slots. Here every phase that diverges is turned into
-// tasks that the whole CTA compacts into one queue; thread t runs task t, so the contact code
-// executes on one or two dense warps instead of on all of them. Tasks of one phase touch disjoint
-// state (different fields, or different bodies of a field), so the result does not depend on
-// which thread runs them; barriers separate the phases.
-//   queue (bytes, per CTA of W warps): contact tasks u32 [0, 128 W)  (field << 21 | pair mask);
-//   robot-wall tasks u16 [0, 384 W)  (field << 3 | robot);  ball-wall tasks u8 [384 W, 416 W).
-__device__ __forceinline__ float* field_column(float* tiles, int f) {
-  return tiles + (f >> 5) * TILE_STATE_WORDS + (f & 31);
-}
-__device__ __forceinline__ void physics_cta(float* tiles, uint32_t* queue, uint32_t* ctr, bool active,
-                                            const DevParams& P) {
-  const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31;
-  float* S = field_column(tiles, tid);
-  uint16_t* qrobot = reinterpret_cast<uint16_t*>(queue);
-  uint8_t* qball = reinterpret_cast<uint8_t*>(queue) + 12 * nthreads;
-  const uint32_t lt = (1u << lane) - 1u;
-  if (tid == 0) { ctr[0] = 0; ctr[1] = 0; ctr[2] = 0; }
-  __syncthreads();
-#pragma unroll 1
-  for (int it = 0; it < P.substeps; ++it) {
-    if (tid == 0) { ctr[1] = 0; ctr[2] = 0; }  // (their readers are behind the barrier that ended the last substep)
-    // A-B + broadphase, one lane per field
-    const uint32_t m = active ? substep_integrate_lane(S, P) : 0u;
-    {
-      const uint32_t has = __ballot_sync(0xffffffffu, m != 0u);
-      uint32_t base = 0;
-      if (lane == 0 && has) base = atomicAdd(&ctr[0], (uint32_t)__popc(has));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (m) queue[base + __popc(has & lt)] = ((uint32_t)tid << 21) | m;
-    }
-    __syncthreads();
-    // C. narrow phase + impulses, one thread per field that has candidates
-    {
-      const int n = (int)ctr[0];
-      for (int t = tid; t < n; t += nthreads) {
-        const uint32_t q = queue[t];
-        contacts_task(field_column(tiles, (int)(q >> 21)), q & 0x1fffffu, P);
-      }
-    }
-    __syncthreads();
-    if (tid == 0) ctr[0] = 0;
-    // D-E. wall candidates, one lane per field
-    {
-      uint32_t w = active ? robots_near_walls_lane(S, P) : 0u;
-      const bool bw = active && ball_near_walls(S, P);
-      const int cnt = __popc(w);
-      int incl = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      const uint32_t hasb = __ballot_sync(0xffffffffu, bw);
-      uint32_t base = 0, baseb = 0;
-      if (lane == 0) {
-        if (total) base = atomicAdd(&ctr[1], (uint32_t)total);
-        if (hasb) baseb = atomicAdd(&ctr[2], (uint32_t)__popc(hasb));
-      }
-      base = __shfl_sync(0xffffffffu, base, 0);
-      baseb = __shfl_sync(0xffffffffu, baseb, 0);
-      int pos = (int)base + incl - cnt;
-      while (w) {
-        const int r = __ffs((int)w) - 1;
-        w &= w - 1;
-        qrobot[pos++] = (uint16_t)((tid << 3) | r);
-      }
-      if (bw) qball[baseb + __popc(hasb & lt)] = (uint8_t)tid;
-    }
-    __syncthreads();
-    {
-      const int nr = (int)ctr[1], nb = (int)ctr[2];
-      for (int t = tid; t < nr; t += nthreads) {  // robot tasks from the first warps up ...
-        const int q = qrobot[t];
-        robot_walls_task(field_column(tiles, q >> 3), q & 7, P);
-      }
-      for (int t = nthreads - 1 - tid; t < nb; t += nthreads)  // ... ball tasks from the last warps down
-        ball_walls_task(field_column(tiles, (int)qball[t]), P);
-    }
-    __syncthreads();
   }
 }
 
@@ -172,17 +85,24 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// The last warp of a CTA to finish counts the CTA as done (StepArgs::step_ctr): every warp of the CTA
-// has read the step index (phase 1a) by then. No return value is used, so the add is fire-and-forget.
+// The last warp of a CTA to finish counts the CTA as done (StepArgs::step_ctr[1]): every warp of the CTA
+// has read the step index (phase 1a) by then. The CTA that completes the step — `a.grid` CTAs, over all
+// the range launches of one step — clears the count and advances the step index (step_ctr[0]); launches
+// of the next step are ordered after every launch of this one, so they read the new index.
 __device__ __forceinline__ void step_done(const StepArgs& a, uint32_t* ctr) {
   __syncwarp();
-  if ((threadIdx.x & 31) == 0 && atomicAdd(&ctr[3], 1u) == (blockDim.x >> 5) - 1u) atomicAdd(a.step_ctr, 1ull);
+  if ((threadIdx.x & 31) == 0 && atomicAdd(&ctr[3], 1u) == (blockDim.x >> 5) - 1u) {
+    unsigned long long* done_ctas = a.step_ctr + 1;
+    if (atomicAdd(done_ctas, 1ull) == (unsigned long long)a.grid - 1ull) {
+      atomicExch(done_ctas, 0ull);
+      atomicAdd(a.step_ctr, 1ull);
+    }
+  }
 }
 
-// SYNC: 0 = warps run free; 1 = CTA-wide barriers at substep / phase boundaries; 2 = 1 + the
-// contact phases as CTA-wide task queues (physics_cta). Separate instantiations so that the default
-// kernel does not carry the queue variant's copy of the contact code.
-template <int VIEW, bool INJECT, int SYNC>
+// SYNC: false = warps run free (small batches: 1-2 warps per CTA); true = CTA-wide barriers at substep
+// and phase boundaries (large batches: 4 warps per CTA kept in the same code region).
+template <int VIEW, bool INJECT, bool SYNC>
 __global__ void __launch_bounds__(384)
 k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) {
   extern __shared__ __align__(16) float smem[];
@@ -216,14 +136,13 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   // 1. per lane: load, actions, physics, rewards, dones
   if (active) lane_phase1a<VIEW>(S, env, a, P, key);
   if (INJECT) { if (active) lane_inject(S, env, a); }
-  else if (SYNC == 2) physics_cta(tiles, queue, ctr, active, P);
-  else physics_tile<SYNC != 0>(T, reinterpret_cast<uint8_t*>(queue + warp * QUEUE_WORDS), lane, active, P, a.sync_level);
+  else physics_tile<SYNC>(T, reinterpret_cast<uint8_t*>(queue + warp * QUEUE_WORDS), lane, active, P);
   if (SYNC) __syncthreads();
   int code = LANE_RUNNING;
   if (active) code = lane_phase1d<VIEW>(S, env, a, P, key);
   const bool done = code == LANE_DONE;   // needs the masked reset of phase 3
   __syncwarp();
-  if (SYNC && (a.sync_level & 7) >= 2 && !(a.sync_level & 16)) __syncthreads();
+  if (SYNC) __syncthreads();
   // 2. terminal observation + observation of the fields that keep their state (vss.py:195-196)
   const uint32_t done_mask = __ballot_sync(0xffffffffu, done);
   float* ob = a.obs + env0 * (PER_FIELD * 4);
@@ -232,16 +151,19 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   void* obh = (VIEW != VIEW_FULL && a.obs_bf16)
                   ? static_cast<void*>(static_cast<unsigned short*>(a.obs_bf16) + env0 * (ViewShape<VIEW>::AGENTS * 64))
                   : nullptr;
-  if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD>(T, tab, lane, valid, tob, ob, done_mask, obh);
-  else write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, done_mask, obh);
+  void* pk = (VIEW != VIEW_FULL && a.packed)
+                 ? static_cast<void*>(static_cast<char*>(a.packed) + env0 * (ViewShape<VIEW>::AGENTS * VSS_PACKED_ROW_BYTES))
+                 : nullptr;
+  if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD>(T, tab, lane, valid, tob, ob, done_mask, obh, pk);
+  else write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, done_mask, obh, pk);
   __syncwarp();
   // 3. masked reset (vss.py:202, 267-333)
   if (done) reset_lane(S, P, key);
   __syncwarp();
   // 4. observation of the fields that were reset (vss.py:203)
-  write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask, obh);
+  write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask, obh, pk);
   // 5. state out
-  if (SYNC && (a.sync_level & 7) >= 2 && !(a.sync_level & 8)) __syncthreads();
+  if (SYNC) __syncthreads();
   if (active) lane_phase5<VIEW>(S, env, a, code != LANE_RUNNING);
   // only the views draw OU noise: the full-contract step neither reads nor advances the index (the
   // extra memory operation at the end of every CTA costs 1 % of the launch at 2^20 fields)
@@ -363,11 +285,12 @@ struct vss_engine {
   int device;
   int64_t n, ld, goff;
   uint64_t seed;
-  unsigned long long* d_step;  // device-resident step index, as finished step-kernel CTAs (StepArgs::step_ctr)
+  unsigned long long* d_step;  // device words: [0] step index (keys the OU stream), [1] CTAs of the current step that finished
   vss_params params;
   DevParams dp;
   float* state;
   void* aux_obs_bf16; float* aux_done_f; float* aux_timeout_f;  // vss_set_step_aux
+  void* packed_rows;                                            // vss_set_step_packed
   int64_t range_first, range_count;                             // vss_set_step_range (count 0 = all fields)
 };
 
@@ -384,50 +307,41 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e_ != cudaSuccess) return fail(VSS_E_CUDA, #call, e_); \
   } while (0)
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
+// Launch shape of the step kernels (a function of the engine's field count only, so that every
+// launch of an engine — whole or one range of vss_set_step_range — uses the same CTA shape).
+// Large batches: 4 warps per CTA with CTA-wide barriers at phase boundaries — the step kernel is
+// instruction-fetch bound (profiles/r01_b_*.md), and warps that execute the same code region at the
+// same time share its lines in the instruction caches (+25 % measured); 6 CTAs of 4 warps per SM
+// (measured at 2^20 fields: 4 / 6 / 8 / 12 warps per CTA -> 0.672 / 0.671 / 0.652 / 0.592 of the HBM
+// roofline). Small batches: 1-2 warps per CTA so that at least 148 CTAs exist; no barriers (up to ~3
+// resident warps per scheduler the barriers only add latency: 2^16 fields 61.5 us vs 68.0 us with 4
+// warps + barriers; 2^17 fields 117 vs 109 us, so the switch sits between them).
+// `fpw` (fields per warp): small batches leave most SMs empty and are bound by one warp's critical
+// path, which grows with the number of fields it owns (every contact of any of its fields is
+// serialised): 16 or 8 fields per warp (the other lanes idle in the per-field phases and help in the
+// cooperative observation writes). Measured (k_step<sa>, us per step at 32 / 16 / 8 fields per warp):
+// 1024 fields 43.7 / 35.7 / 33.8; 4096: 46.4 / 40.0 / 36.2; 8192: 47.7 / 40.2 / 40.3; 16384: 48.7 /
+// 44.4 / 47.5; 21845: 51.2 / 47.4 / 53.7; 32768: 53.9 / 53.8 / 84.2.
+// First-wave stagger (profiles/r01_g_*.md): 5 us per resident CTA of an SM, measured best of 0-12 us
+// at 2^20 fields (675 -> 652 us per step); only for the barrier-synchronised shape and only when the
+// launch is longer than one wave of 148 x 6 CTAs.
+struct LaunchShape {
+  int wpb, fpw, stagger_ns;
+  bool sync;
+  unsigned grid;  // CTAs of a whole-engine launch
+  size_t smem;
+};
 
-// Launch shape. Large batches: 4 warps per CTA with CTA-wide barriers at phase boundaries — the step
-// kernel is instruction-fetch bound (profiles/r01_b_*.md), and warps that execute the same code
-// region at the same time share its lines in the instruction caches (+25 % measured). Small
-// batches: 1-2 warps per CTA so that at least 148 CTAs exist; no barriers (latency matters there).
-// VSS_WPB / VSS_SYNC environment variables override (tuning).
-// `fpw` (fields per warp, step kernels only): small batches leave most SMs empty and are bound by one
-// warp's critical path, which grows with the number of fields it owns (every contact of any of its fields
-// is serialised): 16 or 8 fields per warp (the other lanes idle in the per-field phases and help in the
-// cooperative observation writes).
-static int launch_cfg(int64_t n, int* warps_per_block, unsigned* grid, size_t* smem, int* sync_level = nullptr,
-                      int* fields_per_warp = nullptr) {
-  int fpw = 32;
-  if (fields_per_warp) {
-    static const int forced_fpw = env_int("VSS_FPW", 0);
-    // measured (k_step<sa>, CUDA-graph timed, us per step at 32 / 16 / 8 fields per warp): 1024 fields 43.7 /
-    // 35.7 / 33.8; 4096: 46.4 / 40.0 / 36.2; 8192: 47.7 / 40.2 / 40.3; 16384: 48.7 / 44.4 / 47.5; 21845: 51.2 /
-    // 47.4 / 53.7; 32768: 53.9 / 53.8 / 84.2
-    fpw = n < 148 * 40 ? 8 : (n < 148 * 192 ? 16 : 32);
-    if (forced_fpw == 8 || forced_fpw == 16 || forced_fpw == 32) fpw = forced_fpw;
-  }
-  const int64_t tiles = (n + fpw - 1) / fpw;
-  int wpb = 4, sync = 2;  // 6 CTAs of 4 warps per SM (measured at 2^20 fields: 4 / 6 / 8 / 12 warps per CTA ->
-                          // 0.672 / 0.671 / 0.652 / 0.592 of the HBM roofline; at 2^16 fields 0.405 / 0.366 / 0.377)
-  if (tiles < 148 * 2) { wpb = 1; sync = 0; }
-  else if (tiles < 148 * 20) { wpb = 2; sync = 0; }  // up to ~3 resident warps per scheduler the barriers only add
-                                                     // latency (2^16 fields: 61.5 us vs 68.0 us with 4 warps + barriers;
-                                                     // 2^17 fields: 117 vs 109 us, so the switch sits between them)
-  static const int forced_wpb = env_int("VSS_WPB", 0), forced_sync = env_int("VSS_SYNC", -1);
-  if (forced_wpb >= 1 && forced_wpb <= 12) wpb = forced_wpb;
-  if (forced_sync >= 0) sync = forced_sync;
-  if (wpb == 1) sync = 0;
-  if ((sync & 7) >= 4 && wpb > 8) sync = 2;  // the CTA-wide task queues index fields with 8 bits
-  if ((sync & 7) >= 4 && fpw != 32) sync = 2;  // (and assume thread t owns field t of the CTA)
-  *warps_per_block = wpb;
-  *grid = (unsigned)((tiles + wpb - 1) / wpb);
-  *smem = sizeof(float) * smem_words(wpb);
-  if (sync_level) *sync_level = sync;
-  if (fields_per_warp) *fields_per_warp = fpw;
-  return 0;
+static LaunchShape launch_shape(int64_t n, bool step_kernel = true) {
+  LaunchShape s;
+  s.fpw = !step_kernel ? 32 : (n < 148 * 40 ? 8 : (n < 148 * 192 ? 16 : 32));
+  const int64_t tiles = (n + s.fpw - 1) / s.fpw;
+  s.wpb = tiles < 148 * 2 ? 1 : (tiles < 148 * 20 ? 2 : 4);
+  s.sync = s.wpb == 4;
+  s.grid = (unsigned)((tiles + s.wpb - 1) / s.wpb);
+  s.smem = sizeof(float) * smem_words(s.wpb);
+  s.stagger_ns = (s.sync && s.grid > 148u * 6u) ? 5000 : 0;
+  return s;
 }
 
 static int use_device(vss_handle h) {
@@ -446,38 +360,21 @@ static StepArgs base_args(vss_handle h) {
 }
 
 template <int VIEW, bool INJECT>
-static int launch_step(vss_handle h, const StepArgs& a, void* stream) {
-  int wpb, sync_phases, fpw; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem, &sync_phases, &fpw);
-  const_cast<StepArgs&>(a).sync_level = sync_phases;
-  const_cast<StepArgs&>(a).fpw = fpw;
-  // First-wave stagger (profiles/r01_g_*.md): 5 us per resident CTA of an SM, measured best of 0-12 us
-  // at 2^20 fields (675 -> 652 us per step); only when the launch is longer than one wave.
-  static const int stagger = env_int("VSS_STAGGER_NS", -1);
-  static const int stagger_min_grid = env_int("VSS_STAGGER_MIN_GRID", 148 * 6 + 1);
-  // (only the barrier-synchronised shape of the large batches: the 2-warp shape used up to 2 960 tiles has
-  // more than 888 CTAs from 57 K fields on, but all of them are resident at once and the delay only hurts)
-  const_cast<StepArgs&>(a).stagger_ns =
-      ((int)grid >= stagger_min_grid && sync_phases && wpb > 1) ? (stagger >= 0 ? stagger : 5000) : 0;
-  const_cast<StepArgs&>(a).grid = grid;  // the step index is counted in CTAs of the WHOLE engine
+static int launch_step(vss_handle h, StepArgs a, void* stream) {
+  const LaunchShape ls = launch_shape(h->n);
+  a.fpw = ls.fpw; a.stagger_ns = ls.stagger_ns;
+  a.grid = ls.grid;  // a step is complete when this many CTAs have finished, over all its range launches
+  unsigned grid = ls.grid;
   if (h->range_count > 0) {  // vss_set_step_range: this launch covers [first, first + count) — same CTA shape, fewer CTAs
-    const int64_t per_cta = (int64_t)wpb * fpw;
+    const int64_t per_cta = (int64_t)ls.wpb * ls.fpw;
     if (h->range_first % per_cta != 0 || (h->range_count % per_cta != 0 && h->range_first + h->range_count != h->n))
       return fail(VSS_E_INVALID, "step range: first / count must be multiples of vss_step_granularity()");
-    const_cast<StepArgs&>(a).env_begin = h->range_first;
-    const_cast<StepArgs&>(a).n = h->range_first + h->range_count;
+    a.env_begin = h->range_first;
+    a.n = h->range_first + h->range_count;
     grid = (unsigned)((h->range_count + per_cta - 1) / per_cta);
   }
-  static bool big_smem_ok[64] = {};  // per device: the attribute belongs to the function in one context
-  if (smem > 48 * 1024 && !big_smem_ok[h->device & 63]) {
-    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    VSS_CUDA(cudaFuncSetAttribute(k_step<VIEW, INJECT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    big_smem_ok[h->device & 63] = true;
-  }
-  if ((sync_phases & 7) >= 4 && wpb > 1 && !INJECT) k_step<VIEW, INJECT, 2><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
-  else if (sync_phases && wpb > 1) k_step<VIEW, INJECT, 1><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
-  else k_step<VIEW, INJECT, 0><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a, h->dp);
+  if (ls.sync) k_step<VIEW, INJECT, true><<<grid, ls.wpb * 32, ls.smem, (cudaStream_t)stream>>>(a, h->dp);
+  else k_step<VIEW, INJECT, false><<<grid, ls.wpb * 32, ls.smem, (cudaStream_t)stream>>>(a, h->dp);
   VSS_CUDA(cudaGetLastError());
   return VSS_OK;
 }
@@ -527,15 +424,15 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
   vss_engine* h = new (std::nothrow) vss_engine();
   if (!h) return fail(VSS_E_NOMEM, "vss_create: host allocation failed");
   h->device = device; h->n = num_envs; h->ld = (num_envs + 31) / 32 * 32; h->goff = global_env_offset;
-  h->aux_obs_bf16 = nullptr; h->aux_done_f = nullptr; h->aux_timeout_f = nullptr;
+  h->aux_obs_bf16 = nullptr; h->aux_done_f = nullptr; h->aux_timeout_f = nullptr; h->packed_rows = nullptr;
   h->range_first = 0; h->range_count = 0;
   h->seed = seed; h->d_step = nullptr; h->params = *p; h->dp = derive_params(*p); h->state = nullptr;
   const size_t bytes = sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld;
   e = cudaMalloc(&h->state, bytes);
   if (e != cudaSuccess) { delete h; return fail(VSS_E_NOMEM, "vss_create: cudaMalloc(state)", e); }
   e = cudaMemset(h->state, 0, bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_step, sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(h->d_step, 0, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_step, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_step, 0, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) { cudaFree(h->state); cudaFree(h->d_step); delete h; return fail(VSS_E_CUDA, "vss_create: cudaMemset", e); }
   *out = h;
   return VSS_OK;
@@ -557,17 +454,15 @@ VSS_API uint64_t vss_step_count(vss_handle h) {
   unsigned long long v = 0;
   if (use_device(h) != VSS_OK) return 0;
   if (cudaMemcpy(&v, h->d_step, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-  int wpb, sync, fpw; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem, &sync, &fpw);
-  return v / grid;
+  return v;
 }
 VSS_API int vss_set_step_count(vss_handle h, uint64_t n) {
   if (!h) return fail(VSS_E_INVALID, "null handle");
   if (int rc = use_device(h)) return rc;
-  int wpb, sync, fpw; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem, &sync, &fpw);
-  const unsigned long long v = (unsigned long long)(uint32_t)n * grid;
-  VSS_CUDA(cudaMemcpy(h->d_step, &v, sizeof(v), cudaMemcpyHostToDevice));
+  // the index is one 32-bit word of the Philox counter of the OU stream
+  if (n > 0xFFFFFFFFull) return fail(VSS_E_INVALID, "vss_set_step_count: the step index is a 32-bit counter");
+  const unsigned long long v[2] = {(unsigned long long)n, 0ull};  // also forgets a partially issued step
+  VSS_CUDA(cudaMemcpy(h->d_step, v, sizeof(v), cudaMemcpyHostToDevice));
   return VSS_OK;
 }
 
@@ -581,14 +476,8 @@ VSS_API int vss_set_reward_weights(vss_handle h, const float w[4]) {
 VSS_API int vss_reset_dones(vss_handle h, const int64_t* reset_buf, float* obs, void* stream) {
   if (!h || !reset_buf) return fail(VSS_E_INVALID, "vss_reset_dones: null argument");
   if (int rc = use_device(h)) return rc;
-  int wpb; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem);
-  static bool big_smem_ok[64] = {};
-  if (smem > 48 * 1024 && !big_smem_ok[h->device & 63]) {
-    VSS_CUDA(cudaFuncSetAttribute(k_reset_dones, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    big_smem_ok[h->device & 63] = true;
-  }
-  k_reset_dones<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(
+  const LaunchShape ls = launch_shape(h->n, false);
+  k_reset_dones<<<ls.grid, ls.wpb * 32, ls.smem, (cudaStream_t)stream>>>(
       h->state, h->n, h->ld, (unsigned long long)h->goff, (uint32_t)h->seed, (uint32_t)(h->seed >> 32),
       reinterpret_cast<const long long*>(reset_buf), obs, h->dp);
   VSS_CUDA(cudaGetLastError());
@@ -633,6 +522,7 @@ VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, fl
   a.done_v = reinterpret_cast<long long*>(done_v); a.timeout = timeout_v; a.progress_f = progress_v;
   a.ep_ret = ep_ret; a.ep_len = ep_len; a.ret_ret = ret_ret; a.ret_len = ret_len;
   a.obs_bf16 = h->aux_obs_bf16; a.done_f = h->aux_done_f; a.timeout_f = h->aux_timeout_f;
+  a.packed = h->packed_rows;
   switch (view) {
     case VSS_VIEW_SA: return launch_step<VSS_VIEW_SA, false>(h, a, stream);
     case VSS_VIEW_CMA: return launch_step<VSS_VIEW_CMA, false>(h, a, stream);
@@ -647,11 +537,17 @@ VSS_API int vss_set_step_aux(vss_handle h, void* obs_bf16, float* done_f32, floa
   return VSS_OK;
 }
 
+VSS_API int vss_set_step_packed(vss_handle h, void* rows) {
+  if (!h) return fail(VSS_E_INVALID, "vss_set_step_packed: null handle");
+  if (reinterpret_cast<uintptr_t>(rows) & 15u) return fail(VSS_E_INVALID, "vss_set_step_packed: rows must be 16-byte aligned");
+  h->packed_rows = rows;
+  return VSS_OK;
+}
+
 VSS_API int64_t vss_step_granularity(vss_handle h) {
   if (!h) return 0;
-  int wpb, sync, fpw; unsigned grid; size_t smem;
-  launch_cfg(h->n, &wpb, &grid, &smem, &sync, &fpw);
-  return (int64_t)wpb * fpw;
+  const LaunchShape ls = launch_shape(h->n);
+  return (int64_t)ls.wpb * ls.fpw;
 }
 
 VSS_API int vss_set_step_range(vss_handle h, int64_t first_field, int64_t num_fields) {
@@ -686,12 +582,11 @@ VSS_API int vss_gae(const float* rewards, const float* values, const float* next
   if (T <= 0 || N <= 0) return fail(VSS_E_INVALID, "vss_gae: T and N must be > 0");
   // 64 columns per CTA: at N = 65536 that is 1024 CTAs = 6.9 per SM (128 per CTA: 3.46 per SM, i.e. a
   // quarter of the SMs carry a third more columns than the rest)
-  static const int gae_block = env_int("VSS_GAE_BLOCK", 64);
+  const int gae_block = 64;
   const unsigned grid = (unsigned)((N + gae_block - 1) / gae_block);
   // prefetch while the batch has fewer than ~28 warps per SM (measured: N = 65536 51.7 -> 39.8 us with it,
   // N = 196608 112.8 -> 122.9 us)
-  static const int pf_knob = env_int("VSS_GAE_PREFETCH", -1);
-  const bool prefetch = pf_knob >= 0 ? pf_knob != 0 : N <= 131072;
+  const bool prefetch = N <= 131072;
   if (prefetch)
     k_gae<true><<<grid, gae_block, 0, (cudaStream_t)stream>>>(rewards, values, next_values, next_dones, next_timeouts,
                                                             advantages, returns, T, N, (float)gamma,

@@ -38,6 +38,7 @@ class Engine:
                                   idx, int(seed) & 0xFFFFFFFFFFFFFFFF))
         self.ld = int(self.lib.vss_state_ld(self._h))
         self._aux_set = False
+        self._packed_set = False
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -106,10 +107,11 @@ class Engine:
 
     def step_view(self, view, policy_action, action_buf, reset_buf, obs_v, term_obs_v, rews_v, reward_v, done_v,
                   timeout_v, progress_v, ep_ret=None, ep_len=None, ret_ret=None, ret_len=None, obs_bf16=None,
-                  done_f=None, timeout_f=None):
+                  done_f=None, timeout_f=None, packed=None):
         """`obs_bf16 (N',64) bf16`, `done_f (N') f32`, `timeout_f (N') f32`: optional side outputs
         (vss_set_step_aux) — the observation as the tensor-core MLP reads it, the flags as the GAE
-        kernel reads them."""
+        kernel reads them. `packed (N',112) uint8`: optional packed per-agent rows (vss_set_step_packed),
+        a CUDA tensor or a pinned host tensor (the kernel then stores across PCIe)."""
         n = self.num_envs
         nv = n * 3 if view == VIEW_DMA else n
         adim = 6 if view == VIEW_CMA else 2
@@ -118,6 +120,16 @@ class Engine:
                                             _ptr(done_f, torch.float32, nv, "done_f"),
                                             _ptr(timeout_f, torch.float32, nv, "timeout_f")))
             self._aux_set = obs_bf16 is not None or done_f is not None or timeout_f is not None
+        if packed is not None or self._packed_set:
+            ptr = None
+            if packed is not None:
+                if packed.dtype != torch.uint8 or not packed.is_contiguous() or packed.numel() != nv * _lib.PACKED_ROW_BYTES:
+                    raise ValueError(f"packed: expected a contiguous uint8 tensor of {nv} x {_lib.PACKED_ROW_BYTES} bytes")
+                if not (packed.is_cuda or packed.is_pinned()):
+                    raise TypeError("packed: expected a CUDA tensor or a pinned host tensor")
+                ptr = packed.data_ptr()
+            check(self.lib.vss_set_step_packed(self._h, ptr))
+            self._packed_set = packed is not None
         check(self.lib.vss_step_view(
             self._h, int(view), _ptr(policy_action, torch.float32, nv * adim, "policy_action"),
             _ptr(action_buf, torch.float32, n * 12, "action_buf"), _ptr(reset_buf, torch.int64, n, "reset_buf"),

@@ -72,6 +72,7 @@ class _FusedView(Wrapper):
         self.episode_returns = self.episode_lengths = None
         self.returned_episode_returns = self.returned_episode_lengths = None
         self._host = None
+        self._packed_out = None  # set by step_host: where this step's packed rows go
 
     # ---- running episode statistics fused into the step epilogue (wrappers.py:50-87)
     def enable_episode_stats(self):
@@ -105,7 +106,7 @@ class _FusedView(Wrapper):
                               self._rews, reward, self._done, self._timeout_u8, self._progress,
                               self.episode_returns, self.episode_lengths, self.returned_episode_returns,
                               self.returned_episode_lengths, obs_bf16=obs_bf16_out, done_f=done_f_out,
-                              timeout_f=timeout_f_out)
+                              timeout_f=timeout_f_out, packed=self._packed_out)
         task._obs_stale = True
         infos = task.extras
         infos["rews"] = self._rews
@@ -117,37 +118,61 @@ class _FusedView(Wrapper):
     # ---- the same call with HOST buffers (pinned): action in, (obs, reward, done) out
     HOST_CHUNKS = 8            # large batches are stepped in this many field ranges ...
     HOST_CHUNK_MIN_FIELDS = 1 << 17   # ... when there are at least this many fields
+    HOST_WRITE = "direct"      # packed rows: "direct" = the kernel stores into the mapped pinned buffer across
+                               # PCIe, no copy is issued; "staged" = device staging + one cudaMemcpyAsync per range
 
-    def step_host(self, action_host):
-        """One step with host buffers. Large batches are pipelined: the fields are split into ranges
-        (`vss_set_step_range`), each with its own H2D copy -> kernel -> D2H copies on one of two side
-        streams, so the device-to-host copy of one range (PCIe-bound, 220 B per field) overlaps the
-        kernel of the next. Same kernels, same RNG keys: the results are bit-identical to `step()`."""
+    def _host_buffers(self, packed):
+        from .. import _lib
+        from ..hostmem import pinned_empty
         task, nv = self.task, self.num_view_envs
         if self._host is None:
             self._host = dict(
                 act=torch.empty((nv, self.ACT_DIM), device=task.device, dtype=torch.float32),
-                obs=torch.empty((nv, task.num_obs), dtype=torch.float32).pin_memory(),
-                reward=torch.empty(nv, dtype=torch.float32).pin_memory(),
-                done=torch.empty(nv, dtype=torch.long).pin_memory(),
                 streams=[torch.cuda.Stream(device=task.device) for _ in range(2)])
         h = self._host
+        if packed and "rows" not in h:
+            rows = pinned_empty((nv, _lib.PACKED_ROW_BYTES), torch.uint8, task.device)
+            h["rows"] = rows
+            h["rows_dev"] = torch.zeros((nv, _lib.PACKED_ROW_BYTES), device=task.device, dtype=torch.uint8)
+            # zero-copy views of the 112-byte rows (include/vss_b200.h: vss_set_step_packed)
+            h["obs16"] = rows.view(torch.bfloat16)[:, :task.num_obs]
+            h["reward_p"] = rows.view(torch.float32)[:, 26]
+            h["done_p"], h["timeout_p"] = rows[:, 108], rows[:, 109]
+        if not packed and "obs" not in h:
+            h["obs"] = pinned_empty((nv, task.num_obs), torch.float32, task.device)
+            h["reward"] = pinned_empty((nv,), torch.float32, task.device)
+            h["done"] = pinned_empty((nv,), torch.long, task.device)
+        return h
+
+    def step_host(self, action_host, obs_dtype=torch.bfloat16, host_write=None):
+        """One step with HOST buffers: pinned policy action in, what `step()` returns to the policy out
+        (envs/wrappers.py:108-115: observation, scalar reward, done) in pinned host memory.
+
+        `obs_dtype=torch.bfloat16` (default): one packed 112-byte row per view env (52 bf16 observation
+        values, f32 reward, u8 done, u8 time-out), written by the step kernel itself; returns zero-copy
+        views `(obs (N',52) bf16, reward (N') f32, done (N') uint8)` of that buffer (`host_timeouts` is the
+        fourth column). `obs_dtype=torch.float32`: the reference's own types (f32 observation, int64 done),
+        220 bytes per view env, copied from the view's device buffers.
+
+        Large batches are pipelined: the fields are split into ranges (`vss_set_step_range`), each with its
+        own H2D copy -> kernel (-> D2H copy) on one of two side streams. Same kernels, same RNG keys: the
+        device-side results are bit-identical to `step()`."""
+        task, nv = self.task, self.num_view_envs
+        packed = obs_dtype == torch.bfloat16
+        if not packed and obs_dtype != torch.float32:
+            raise ValueError("step_host: obs_dtype must be torch.bfloat16 or torch.float32")
+        direct = (host_write or self.HOST_WRITE) == "direct"
+        h = self._host_buffers(packed)
         act_host = action_host.view(h["act"].shape)
         n, agents = task.num_fields, nv // task.num_fields
         chunks = self.HOST_CHUNKS if n >= self.HOST_CHUNK_MIN_FIELDS else 1
         cur = torch.cuda.current_stream(task.device)
-        if chunks == 1:
-            h["act"].copy_(act_host, non_blocking=True)
-            obs, reward, done, _ = self.step(h["act"])
-            h["obs"].copy_(obs["obs"], non_blocking=True)
-            h["reward"].copy_(reward, non_blocking=True)
-            h["done"].copy_(done, non_blocking=True)
-            cur.synchronize()
-            return h["obs"], h["reward"], h["done"]
         g = task.engine.step_granularity
         per = -(-n // (chunks * g)) * g
+        self._packed_out = (h["rows"] if direct else h["rows_dev"]) if packed else None
         start = torch.cuda.Event()
         start.record(cur)
+        ok = False
         try:
             for c in range(chunks):
                 f0 = c * per
@@ -155,21 +180,50 @@ class _FusedView(Wrapper):
                 if cnt <= 0:
                     break
                 v0, v1 = f0 * agents, (f0 + cnt) * agents
-                s = h["streams"][c & 1]
+                s = h["streams"][c & 1] if chunks > 1 else cur
                 with torch.cuda.stream(s):
                     s.wait_event(start)
                     h["act"][v0:v1].copy_(act_host[v0:v1], non_blocking=True)
-                    task.engine.set_step_range(f0, cnt)
+                    if chunks > 1:
+                        task.engine.set_step_range(f0, cnt)
                     obs, reward, done, _ = self.step(h["act"])
-                    h["obs"][v0:v1].copy_(obs["obs"][v0:v1], non_blocking=True)
-                    h["reward"][v0:v1].copy_(reward[v0:v1], non_blocking=True)
-                    h["done"][v0:v1].copy_(done[v0:v1], non_blocking=True)
+                    if packed:
+                        if not direct:
+                            h["rows"][v0:v1].copy_(h["rows_dev"][v0:v1], non_blocking=True)
+                    else:
+                        h["obs"][v0:v1].copy_(obs["obs"][v0:v1], non_blocking=True)
+                        h["reward"][v0:v1].copy_(reward[v0:v1], non_blocking=True)
+                        h["done"][v0:v1].copy_(done[v0:v1], non_blocking=True)
+            ok = True
         finally:
-            task.engine.set_step_range(0, 0)
-        for s in h["streams"]:
-            cur.wait_stream(s)
+            self._packed_out = None
+            if chunks > 1:
+                task.engine.set_step_range(0, 0)
+            if not ok:  # a step abandoned after some of its range launches: forget the partial CTA count
+                torch.cuda.synchronize(task.device)
+                task.engine.step_count = task.engine.step_count
+        if chunks > 1:
+            for s in h["streams"]:
+                cur.wait_stream(s)
         cur.synchronize()
+        if packed:
+            return h["obs16"], h["reward_p"], h["done_p"]
         return h["obs"], h["reward"], h["done"]
+
+    @property
+    def host_timeouts(self):
+        """(N') uint8 view of the time-out column of the packed rows of the last `step_host`."""
+        return self._host["timeout_p"]
+
+    @staticmethod
+    def host_outputs_as_f32(obs, reward, done):
+        """The reference's own types (f32 observation, f32 reward, int64 done) from either host format."""
+        return obs.float(), reward.float().contiguous(), done.long()
+
+    def d2h_bytes(self, obs_dtype=torch.bfloat16):
+        from .. import _lib
+        per = _lib.PACKED_ROW_BYTES if obs_dtype == torch.bfloat16 else self.task.num_obs * 4 + 4 + 8
+        return self.num_view_envs * per
 
     @property
     def h2d_bytes_per_step(self):
@@ -177,7 +231,7 @@ class _FusedView(Wrapper):
 
     @property
     def d2h_bytes_per_step(self):
-        return self.num_view_envs * (self.task.num_obs * 4 + 4 + 8)
+        return self.d2h_bytes(torch.bfloat16)
 
 
 class SingleAgent(_FusedView):

@@ -14,6 +14,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NT, NR, NOBS = 2, 3, 52
+PACKED_ROW_BYTES = 112
 VIEW_FULL, VIEW_SA, VIEW_CMA, VIEW_DMA = -1, 0, 1, 2
 
 
@@ -64,13 +65,14 @@ class EmuBackend:
         return obs
 
     def _call(self, view, actions, inject, reset_buf, obs, term_obs, rew, timeout, progress_f, policy_action=None,
-              action_buf=None, reward_v=None, done_v=None, ep_ret=None, ep_len=None, ret_ret=None, ret_len=None):
+              action_buf=None, reward_v=None, done_v=None, ep_ret=None, ep_len=None, ret_ret=None, ret_len=None,
+              packed=None):
         rc = self.lib().emu_step(C.byref(self.params), C.c_int(view), _p(self.state), C.c_longlong(self.n),
                                  C.c_longlong(self.ld), C.c_ulonglong(self.goff), C.c_ulonglong(self.seed),
                                  C.c_uint(self.step_count & 0xFFFFFFFF), _p(actions), _p(inject), _p(reset_buf),
                                  _p(obs), _p(term_obs), _p(rew), _p(timeout), _p(progress_f), _p(policy_action),
                                  _p(action_buf), _p(reward_v), _p(done_v), _p(ep_ret), _p(ep_len), _p(ret_ret),
-                                 _p(ret_len))
+                                 _p(ret_len), _p(packed))
         assert rc == 0
         self.step_count += 1
 
@@ -86,9 +88,10 @@ class EmuBackend:
                    out["progress_f"])
         return out
 
-    def step_view(self, view, policy_action, action_buf, reset_buf, ep_ret=None, ep_len=None):
+    def step_view(self, view, policy_action, action_buf, reset_buf, ep_ret=None, ep_len=None, packed=False):
         n, nv = self.n, _nv(self.n, view)
         policy_action = np.ascontiguousarray(policy_action, np.float32)
+        pk = np.zeros((nv, PACKED_ROW_BYTES), np.uint8) if packed else None
         out = dict(obs=np.zeros((nv, NOBS), np.float32), term_obs=np.zeros((nv, NOBS), np.float32),
                    rews=np.zeros((nv, 4), np.float32), reward=np.zeros((nv,), np.float32),
                    done=np.zeros((nv,), np.int64), timeout=np.zeros((nv,), np.uint8),
@@ -99,7 +102,9 @@ class EmuBackend:
             out["ret_ret"], out["ret_len"] = ret_ret, ret_len
         self._call(view, None, None, reset_buf, out["obs"], out["term_obs"], out["rews"], out["timeout"],
                    out["progress"], policy_action, action_buf, out["reward"], out["done"], ep_ret, ep_len, ret_ret,
-                   ret_len)
+                   ret_len, packed=pk)
+        if packed:
+            out["packed"] = pk
         return out
 
 
@@ -163,7 +168,7 @@ class GpuBackend:
         return dict(obs=obs.cpu().numpy(), term_obs=tobs.cpu().numpy(), rew=rew.cpu().numpy(),
                     timeout=tout.cpu().numpy(), progress_f=prog.cpu().numpy())
 
-    def step_view(self, view, policy_action, action_buf, reset_buf, ep_ret=None, ep_len=None):
+    def step_view(self, view, policy_action, action_buf, reset_buf, ep_ret=None, ep_len=None, packed=False):
         t, n = self.torch, self.n
         nv = _nv(n, view)
         z = lambda shape, dt: t.zeros(shape, dtype=dt, device=self.dev)
@@ -174,14 +179,17 @@ class GpuBackend:
         if ep_ret is not None:
             er, el = self._t(ep_ret), self._t(ep_len)
             rr, rl = z((nv, 4), t.float32), z((nv,), t.int32)
+        pk = z((nv, PACKED_ROW_BYTES), t.uint8) if packed else None
         self.eng.step_view(view, self._t(np.ascontiguousarray(policy_action, np.float32)), ab, rb, obs, tobs, rews,
-                           reward, done, tout, prog, er, el, rr, rl)
+                           reward, done, tout, prog, er, el, rr, rl, packed=pk)
         t.cuda.synchronize()
         reset_buf[...] = rb.cpu().numpy()
         action_buf[...] = ab.cpu().numpy()
         out = dict(obs=obs.cpu().numpy(), term_obs=tobs.cpu().numpy(), rews=rews.cpu().numpy(),
                    reward=reward.cpu().numpy(), done=done.cpu().numpy(), timeout=tout.cpu().numpy(),
                    progress=prog.cpu().numpy())
+        if packed:
+            out["packed"] = pk.cpu().numpy()
         if ep_ret is not None:
             ep_ret[...] = er.cpu().numpy()
             ep_len[...] = el.cpu().numpy()

@@ -48,13 +48,16 @@ static void emu_step_t(const StepArgs& a, const DevParams& P) {
     }
     float* ob = a.obs + env0 * (PER_FIELD * 4);
     float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
+    void* pk = (VIEW != VIEW_FULL && a.packed)
+                   ? static_cast<void*>(static_cast<char*>(a.packed) + env0 * (ViewShape<VIEW>::AGENTS * VSS_PACKED_ROW_BYTES))
+                   : nullptr;
     for (int lane = 0; lane < 32; ++lane) {
-      if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD>(T, g_tab.v, lane, valid, tob, ob, done_mask);
-      else write_obs_tile(T, g_tab.v, lane, valid, PER_FIELD, tob, ob, done_mask);
+      if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD>(T, g_tab.v, lane, valid, tob, ob, done_mask, nullptr, pk);
+      else write_obs_tile(T, g_tab.v, lane, valid, PER_FIELD, tob, ob, done_mask, nullptr, pk);
     }
     for (int lane = 0; lane < valid; ++lane)
       if (done[lane]) reset_lane(T + lane, P, make_key(a, env0 + lane));
-    for (int lane = 0; lane < 32; ++lane) write_obs_fields(T, g_tab.v, lane, PER_FIELD, ob, done_mask);
+    for (int lane = 0; lane < 32; ++lane) write_obs_fields(T, g_tab.v, lane, PER_FIELD, ob, done_mask, nullptr, pk);
     for (int lane = 0; lane < valid; ++lane) lane_phase5<VIEW>(T + lane, env0 + lane, a, ended[lane]);
   }
 }
@@ -66,7 +69,7 @@ __attribute__((visibility("default"))) int emu_step(
     unsigned long long seed, unsigned int step, const float* actions, const float* inject, long long* reset_buf,
     float* obs, float* term_obs, float* rew, uint8_t* timeout, float* progress_f, const float* policy_action,
     float* action_buf, float* reward_v, long long* done_v, float* ep_ret, int* ep_len, float* ret_ret,
-    int* ret_len) {
+    int* ret_len, void* packed) {
   const DevParams P = derive_params(*p);
   StepArgs a;
   memset(&a, 0, sizeof(a));
@@ -76,7 +79,7 @@ __attribute__((visibility("default"))) int emu_step(
   a.actions = actions; a.inject = inject; a.reset_buf = reset_buf; a.obs = obs; a.term_obs = term_obs;
   a.rew = rew; a.timeout = timeout; a.progress_f = progress_f; a.policy_action = policy_action;
   a.action_buf = action_buf; a.reward_v = reward_v; a.done_v = done_v; a.ep_ret = ep_ret; a.ep_len = ep_len;
-  a.ret_ret = ret_ret; a.ret_len = ret_len;
+  a.ret_ret = ret_ret; a.ret_len = ret_len; a.packed = packed;
   if (view == VIEW_FULL) { if (inject) emu_step_t<VIEW_FULL, true>(a, P); else emu_step_t<VIEW_FULL, false>(a, P); }
   else if (view == VSS_VIEW_SA) emu_step_t<VSS_VIEW_SA, false>(a, P);
   else if (view == VSS_VIEW_CMA) emu_step_t<VSS_VIEW_CMA, false>(a, P);

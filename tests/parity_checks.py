@@ -563,3 +563,140 @@ def check_nonfinite_guard(Backend, n=96):
     assert np.array_equal(bits(out["obs"][poisoned]), bits(out["term_obs"][poisoned]))   # fresh state in both
     compare_full_step(out, ref, rb, rb_ref, n, "non-finite guard", exact_physics=False)
     assert np.isfinite(be.get_state()[:58, :n]).all()
+
+
+# --------------------------------------------------------------------------- RNG statistics
+def philox4x32_10_np(ctr, key):
+    """Vectorised Philox4x32-10 (Salmon et al. 2011): ctr (N,4) uint32, key (2,) -> (N,4) uint32. Written
+    from the published algorithm, independent of the product's and the oracle's C versions (checked
+    against the oracle's on a few counters by the callers)."""
+    c = np.ascontiguousarray(ctr, np.uint32).astype(np.uint64)
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    m0, m1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    x, y, z, w = c[:, 0], c[:, 1], c[:, 2], c[:, 3]
+    for _ in range(10):
+        p0, p1 = m0 * x, m1 * z
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        x, y, z, w = hi1 ^ y ^ k0, lo1, hi0 ^ w ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack([x, y, z, w], 1).astype(np.uint32)
+
+
+def first_attempt_positions(p, seed, goff, n, episode=0):
+    """The FIRST placement draw of reset_dones for fields goff .. goff+n-1 (envs/vss.py:283-287: 7 XY pairs
+    ~ U(-0.5, 0.5) * field_scale), from the Philox stream DESIGN.md §5 documents, in numpy."""
+    gid = np.uint64(goff) + np.arange(n, dtype=np.uint64)
+    u = np.empty((n, 16), np.uint32)
+    for b in range(4):
+        ctr = np.stack([(gid & np.uint64(0xFFFFFFFF)).astype(np.uint32), (gid >> np.uint64(32)).astype(np.uint32),
+                        np.full(n, episode, np.uint32), np.full(n, (0 << 28) | b, np.uint32)], 1)
+        u[:, 4 * b:4 * b + 4] = philox4x32_10_np(ctr, (seed & 0xFFFFFFFF, seed >> 32))
+    u01 = (u >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    px = (u01[:, 0:14:2] - np.float32(0.5)) * np.float32(p.reset_scale_x)
+    py = (u01[:, 1:14:2] - np.float32(0.5)) * np.float32(p.reset_scale_y)
+    return np.stack([px, py], -1)  # (n, 7, 2): ball, then robots in team-major order
+
+
+def check_reset_reject_rate(Backend, n=60000, seed=21, goff=3 << 32):
+    """envs/vss.py:281-299 redraws all 7 entities while any pair is closer than 0.07 m; SURVEY App. D
+    measured P(reject) = 0.1799 per draw on the reference's distribution. Here: the share of fields whose
+    final placement is NOT their first draw, and the first draws themselves must be what the rule says."""
+    ctr = np.array([1, 2, 3, 4], np.uint32)
+    assert np.array_equal(philox4x32_10_np(ctr[None], (7, 9))[0], orc.philox4x32_10(ctr, np.array([7, 9], np.uint32)))
+    be, p = make_backend_pair(Backend, n, seed, goff)
+    be.reset_dones(np.ones(n, np.int64))
+    got = oracle_from_backend(be)
+    ent = np.concatenate([got.ball_pos[:, None, :], got.r_pos.reshape(n, 6, 2)], 1)
+    first = first_attempt_positions(p, seed, goff, n)
+    d = np.linalg.norm(first[:, :, None, :].astype(np.float64) - first[:, None, :, :], axis=-1) + np.eye(7) * 10
+    first_ok = d.min((1, 2)) >= 0.07 + 1e-6          # clearly accepted by the rule
+    first_bad = d.min((1, 2)) < 0.07 - 1e-6          # clearly rejected
+    kept_first = (bits(ent) == bits(first)).reshape(n, -1).all(1)
+    assert kept_first[first_ok].all(), "an acceptable first draw was redrawn"
+    assert not kept_first[first_bad].any(), "a first draw with a pair closer than 0.07 m was kept"
+    rate = 1.0 - kept_first.mean()
+    assert abs(rate - 0.18) < 0.01, rate
+    return rate
+
+
+def check_ou_moments(Backend, view=orc.VIEW_SA, n=16384, steps=6, seed=17):
+    """The in-kernel opponent noise (envs/wrappers.py:5-19: prev - 0.1 prev + N(0, 0.15), clamp +-1):
+    innovation mean 0, std 0.15, Gaussian 4th moment, uncorrelated between steps and between slots."""
+    be, p = make_backend_pair(Backend, n, seed, 0)
+    nv = n * 3 if view == orc.VIEW_DMA else n
+    adim = 6 if view == orc.VIEW_CMA else 2
+    rb = np.ones(n, np.int64)
+    be.reset_dones(rb)
+    rb[:] = 0
+    abuf = np.zeros((n, 2, 3, 2), np.float32)
+    free = np.ones((2, 3, 2), bool)                  # slots the policy does not overwrite
+    free[0, 0 if view == orc.VIEW_SA else slice(None)] = False
+    innov = []
+    for t in range(steps):
+        prev = abuf.copy()
+        pa = np.zeros((nv, adim), np.float32)
+        be.step_view(view, pa, abuf, rb)
+        live = rb == 0                               # rows of done fields are zeroed after the step
+        x = abuf[live][:, free] - np.float32(0.9) * prev[live][:, free]
+        unclamped = np.abs(abuf[live][:, free]) < 1.0
+        innov.append(np.where(unclamped, x, np.nan))
+        assert np.all(abuf[~live] == 0)
+        assert np.all(abuf[live][:, ~free] == 0)     # the policy action (zeros here) landed in its slots
+    m = min(len(v) for v in innov)
+    z = np.stack([v[:m] for v in innov])             # (steps, fields, free slots)
+    flat = z[np.isfinite(z)].astype(np.float64)
+    k = flat.size
+    assert k > 0.99 * z.size                         # hardly anything reaches the clamp from zero in a few steps
+    assert abs(flat.mean()) < 5 * 0.15 / np.sqrt(k), flat.mean()
+    assert abs(flat.std() - 0.15) < 5 * 0.15 / np.sqrt(2 * k) + 1e-4, flat.std()
+    assert abs(np.mean((flat / 0.15) ** 4) - 3.0) < 5 * np.sqrt(96.0 / k) + 1e-2
+    zz = np.nan_to_num(z) / 0.15
+    lag = np.mean(zz[1:] * zz[:-1])                  # consecutive steps, same slot
+    cross = np.mean(zz[:, :, :-1] * zz[:, :, 1:])    # neighbouring slots, same step
+    assert abs(lag) < 5 / np.sqrt(zz[1:].size) and abs(cross) < 5 / np.sqrt(zz[:, :, 1:].size), (lag, cross)
+    return dict(mean=flat.mean(), std=flat.std(), samples=k)
+
+
+# --------------------------------------------------------------------------- packed host rows
+def unpack_rows(pk):
+    """(obs f32 (n,52) from bf16, reward f32 (n), done u8 (n), timeout u8 (n), pad u16 (n)) of packed rows."""
+    pk = np.ascontiguousarray(pk, np.uint8)
+    n = pk.shape[0]
+    obs16 = pk[:, :104].copy().view(np.uint16).reshape(n, 52)
+    obs = (obs16.astype(np.uint32) << 16).view(np.float32)
+    reward = pk[:, 104:108].copy().view(np.float32).reshape(n)
+    return obs, reward, pk[:, 108], pk[:, 109], pk[:, 110:112].copy().view(np.uint16).reshape(n)
+
+
+def bf16_rne(x):
+    """float32 -> bf16 (round to nearest even) -> float32, in numpy."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint32) << 16
+    return r.view(np.float32)
+
+
+def check_packed_rows(Backend, view, n=500, steps=5, seed=23):
+    """vss_set_step_packed: the 112-byte rows carry exactly bf16(obs), reward, done, timeout of the same
+    launch's ordinary outputs (rows of reset fields hold the post-reset observation, like obs)."""
+    be, p = make_backend_pair(Backend, n, seed, 0)
+    rng = np.random.default_rng(seed)
+    nv = n * 3 if view == orc.VIEW_DMA else n
+    adim = 6 if view == orc.VIEW_CMA else 2
+    rb = np.ones(n, np.int64)
+    be.reset_dones(rb)
+    rb[:] = 0
+    stage_interesting_state(be, rng)
+    abuf = np.zeros((n, 2, 3, 2), np.float32)
+    ndone = 0
+    for t in range(steps):
+        pa = rng.uniform(-1.2, 1.2, (nv, adim)).astype(np.float32)
+        out = be.step_view(view, pa, abuf, rb, packed=True)
+        obs, reward, done, tmo, pad = unpack_rows(out["packed"])
+        assert_bits_equal(obs, bf16_rne(out["obs"]), f"packed obs step {t}")
+        assert_bits_equal(reward, out["reward"], f"packed reward step {t}")
+        assert np.array_equal(done, out["done"].astype(np.uint8)) and np.array_equal(tmo, out["timeout"])
+        assert np.all(pad == 0)
+        ndone += int(done.sum())
+    assert ndone > 0
+    return ndone

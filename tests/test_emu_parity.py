@@ -57,3 +57,21 @@ def test_robot_pair_contacts_track_oracle():
 
 def test_physics_model_embodies_the_scene_spec():
     pc.check_physics_spec(EmuBackend)
+
+
+def test_reset_reject_rate_matches_the_reference_rule():
+    """envs/vss.py:281-299; SURVEY App. D: P(reject) = 0.1799 per draw."""
+    rate = pc.check_reset_reject_rate(EmuBackend, n=40000)
+    assert 0.17 < rate < 0.19
+
+
+@pytest.mark.parametrize("view", [orc.VIEW_SA, orc.VIEW_DMA])
+def test_ou_noise_moments(view):
+    """envs/wrappers.py:5-19: innovation N(0, 0.15)."""
+    pc.check_ou_moments(EmuBackend, view, n=8192, steps=5)
+
+
+@pytest.mark.parametrize("view", [orc.VIEW_SA, orc.VIEW_CMA, orc.VIEW_DMA])
+def test_packed_host_rows(view):
+    """include/vss_b200.h vss_set_step_packed: 52 bf16 obs | f32 reward | u8 done | u8 timeout."""
+    pc.check_packed_rows(EmuBackend, view)

@@ -178,3 +178,113 @@ def test_robot_pair_contacts_track_oracle(Gpu):
 
 def test_physics_model_embodies_the_scene_spec(Gpu):
     pc.check_physics_spec(Gpu)
+
+
+# ----------------------------------------------------------------------------------------------------
+# The launch shapes the benchmark times (csrc/vss_step.cu::launch_shape), against the oracle:
+#   4 096 fields   -> 8 fields per warp,  2 warps per CTA, no barriers      (BASELINE configs[1] ppo-sa)
+#   16 384, 21 845 -> 16 fields per warp, 2 warps per CTA                    (configs[2] cma; configs[3] dma fields)
+#   65 536         -> 32 fields per warp, 2 warps per CTA                    (configs[3], sweep)
+#   100 003        -> 4 warps per CTA + CTA-wide barriers, ragged against the 128-field CTAs, one wave
+#   131 072        -> the same shape with the first-wave stagger (> 888 CTAs): what BENCH / SCALE time at 2^20
+# ----------------------------------------------------------------------------------------------------
+TIMED_SIZES = [4096, 16384, 21845, 65536, 100003, 131072]
+
+
+@pytest.mark.parametrize("n", TIMED_SIZES)
+def test_timed_launch_shapes_rollout_tracks_oracle(Gpu, n):
+    r = pc.check_rollout(Gpu, n=n, steps=4, seed=n % 97)
+    assert r["dones"] > 0 and r["timeouts"] > 0 and r["goals"] > 0
+
+
+@pytest.mark.parametrize("n", TIMED_SIZES)
+def test_timed_launch_shapes_injected_step_is_exact(Gpu, n):
+    assert pc.check_injected(Gpu, n=n, steps=2, seed=n % 89) > 0
+
+
+@pytest.mark.parametrize("view,n", [(orc.VIEW_SA, 4096), (orc.VIEW_CMA, 16384), (orc.VIEW_DMA, 21845),
+                                    (orc.VIEW_SA, 65536), (orc.VIEW_SA, 100003), (orc.VIEW_SA, 131072),
+                                    (orc.VIEW_CMA, 131072), (orc.VIEW_DMA, 131072)])
+def test_timed_launch_shapes_views_track_oracle(Gpu, view, n):
+    pc.check_views(Gpu, view, n=n, steps=3, seed=5 + n % 7)
+
+
+def test_timed_launch_shape_wall_and_pair_contacts(Gpu):
+    """The contact stress checks on the 4-warp, barrier-synchronised, staggered shape."""
+    pc.check_wall_stress(Gpu, n=131072, steps=3)
+    pc.check_pair_stress(Gpu, n=131072, steps=3)
+
+
+def test_step_ranges_at_full_size_match_oracle():
+    """2^20 fields (the benchmark's size) stepped through `SingleAgent.step_host`, i.e. as 8 field ranges
+    (vss_set_step_range) on two streams: every range against the oracle's view step from the same state,
+    and the whole against one un-chunked launch of a twin engine."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rsoccer_isaac_cleanrl_b200.envs import VSS, SingleAgent, load_cfg
+    n, seed = 1 << 20, 31
+    cfg = load_cfg()
+    cfg["env"]["numEnvs"] = n
+    task = VSS(cfg, "cuda:0", "cuda:0", 0, True, seed=seed)
+    twin = VSS(cfg, "cuda:0", "cuda:0", 0, True, seed=seed)
+    view, view2 = SingleAgent(task), SingleAgent(twin)
+    assert n >= view.HOST_CHUNK_MIN_FIELDS and view.HOST_CHUNKS > 1
+    task.reset_buf.zero_(); twin.reset_buf.zero_()
+    rng = np.random.default_rng(0)
+    st = task.engine.get_state()
+    st[58, :n] = torch.from_numpy(rng.integers(380, 400, n).astype(np.int32)).cuda().view(torch.float32)
+    task.engine.set_state(st); twin.engine.set_state(st)
+    del st
+    p = orc.default_params()
+    abuf = np.zeros((n, 2, 3, 2), np.float32)
+    rb = np.zeros(n, np.int64)
+    for t in range(2):
+        ost = orc.State.from_soa(task.engine.get_state().cpu().numpy(), n)
+        pa = torch.from_numpy(rng.uniform(-1.2, 1.2, (n, 2)).astype(np.float32)).pin_memory()
+        step_index = task.engine.step_count
+        assert step_index == t
+        obs_h, rew_h, done_h = view.step_host(pa)
+        o2, r2, d2, _ = view2.step(pa.cuda())
+        # (a) chunked == un-chunked, bit for bit (same kernels, same RNG keys)
+        assert torch.equal(view._obs, o2["obs"]) and torch.equal(view._reward, r2) and torch.equal(view._done, d2)
+        assert torch.equal(view.action_buf, view2.action_buf)
+        assert torch.equal(task.engine.get_state(), twin.engine.get_state())
+        # (b) what the caller receives on the host == the device buffers
+        host = view.host_outputs_as_f32(obs_h, rew_h, done_h)
+        assert torch.equal(host[1], view._reward.cpu()) and torch.equal(host[2], view._done.cpu())
+        np.testing.assert_allclose(host[0].numpy(), view._obs.cpu().numpy(), rtol=2 ** -8, atol=0)
+        # (c) against the oracle
+        rb_ref = rb.copy()
+        ref = orc.step_view(p, seed, 0, step_index, ost, orc.VIEW_SA, pa.numpy(), abuf, rb_ref)
+        rb[...] = task.reset_buf.cpu().numpy()
+        same = rb == rb_ref
+        tol = lambda a, b: np.abs(a - b) <= 3 * (pc.PHYS_ATOL + pc.PHYS_RTOL * np.abs(b))
+        good = same & tol(view._term_obs.cpu().numpy(), ref["term_obs"]).all(1) & tol(view._reward.cpu().numpy(), ref["reward"])
+        good &= (view._done.cpu().numpy() == ref["done"]) & (view._timeout_u8.cpu().numpy() == ref["timeout"])
+        assert (~good).sum() <= pc.FLIP_FRACTION * n, int((~good).sum())
+        assert rb.sum() > 0
+        both = good & (rb != 0)   # fields reset by both: the fresh observation agrees
+        pc.assert_obs_equal(view._obs.cpu().numpy()[both], ref["obs"][both], "obs after reset", trig_atol=1e-6)
+        np.testing.assert_allclose(view.action_buf.cpu().numpy()[same], abuf[same], rtol=0, atol=2e-6)
+        abuf[...] = view.action_buf.cpu().numpy()
+    assert task.engine.step_count == 2
+
+
+def test_reset_reject_rate_matches_the_reference_rule(Gpu):
+    """envs/vss.py:281-299; SURVEY App. D: P(reject) = 0.1799 per draw."""
+    rate = pc.check_reset_reject_rate(Gpu, n=200000)
+    assert abs(rate - 0.18) < 0.005, rate
+
+
+@pytest.mark.parametrize("view", [orc.VIEW_SA, orc.VIEW_CMA, orc.VIEW_DMA])
+def test_ou_noise_moments(Gpu, view):
+    """envs/wrappers.py:5-19: the in-kernel N(0, 0.15) innovation of the opponents' action buffer."""
+    r = pc.check_ou_moments(Gpu, view, n=65536, steps=6)
+    assert abs(r["std"] - 0.15) < 5e-4
+
+
+@pytest.mark.parametrize("view,n", [(orc.VIEW_SA, 500), (orc.VIEW_CMA, 4097), (orc.VIEW_DMA, 21845), (orc.VIEW_SA, 131072)])
+def test_packed_host_rows(Gpu, view, n):
+    """include/vss_b200.h vss_set_step_packed: 52 bf16 obs | f32 reward | u8 done | u8 timeout."""
+    pc.check_packed_rows(Gpu, view, n=n, steps=4)
