@@ -231,6 +231,12 @@ VSS_API int vss_set_state(vss_handle h, const float* state_in, void* stream);
  * some of its range launches must call it before the next step); values above UINT32_MAX are rejected
  * (the index is one 32-bit word of the Philox counter). */
 VSS_API uint64_t vss_step_count(vss_handle h);
+/* Safety net that the reference does not have: a field whose state is not finite at the end of the
+ * physics (a blow-up of the 2-D model; never observed in the stress tests) is re-randomised on the spot
+ * and reported with done = 1, time-out = 0 and zero reward, so that one bad field cannot poison a
+ * training run. This returns how many fields that has happened to over the engine's life (device
+ * counter; the call synchronises). A non-zero value is worth a look. */
+VSS_API uint64_t vss_sanitised_count(vss_handle h);
 VSS_API int vss_set_step_count(vss_handle h, uint64_t n);
 
 /* Replaces the GAE loop, ppo_continuous_action_isaacgym.py:282-296. All arrays (T,N) f32

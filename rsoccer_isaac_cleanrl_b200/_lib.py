@@ -74,6 +74,7 @@ _SYMBOLS = {
     "vss_set_state": (C.c_int, [_VP, _VP, _VP]),
     "vss_step_count": (C.c_uint64, [_VP]),
     "vss_set_step_count": (C.c_int, [_VP, C.c_uint64]),
+    "vss_sanitised_count": (C.c_uint64, [_VP]),
     "vss_gae": (C.c_int, [_VP] * 7 + [C.c_int32, C.c_int64, C.c_double, C.c_double, _VP]),
     "vss_gemm_bf16_tn": (C.c_int, [_VP, C.c_int, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _VP,
                                   _VP, C.c_int, C.c_int, C.c_int, _VP]),

@@ -802,8 +802,8 @@ struct StepArgs {
   float* state; long long n, ld; unsigned long long goff;  // n = end of the field range of this launch
   long long env_begin;         // first field of this launch (0 unless vss_set_step_range restricts it)
   uint32_t seed_lo, seed_hi;
-  // Device-resident step index (keys the OU stream): step_ctr[0] = index, step_ctr[1] = CTAs of the
-  // current step that have finished. The CTA that brings the count to `grid` (the CTAs of a whole-engine
+  // Device words: step_ctr[2] = fields the non-finite guard has re-randomised so far; step_ctr[0] =
+  // device-resident step index (keys the OU stream), step_ctr[1] = CTAs of the current step that have finished. The CTA that brings the count to `grid` (the CTAs of a whole-engine
   // launch; a step issued as several range launches adds up to the same number) clears it and advances
   // the index, so a CUDA graph that replays the launch advances the index without a second kernel.
   unsigned long long* step_ctr;
@@ -925,6 +925,16 @@ VSS_HD bool state_finite(const float* S) {
 
 enum : int { LANE_RUNNING = 0, LANE_DONE = 1, LANE_SANITISED = 2 };
 
+// step_ctr[2]: fields re-randomised by the non-finite guard over the engine's life (vss_sanitised_count)
+VSS_HD_COLD void count_sanitised(const StepArgs& a) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(a.step_ctr + 2, 1ull);
+#else
+#pragma omp atomic
+  a.step_ctr[2] += 1ull;
+#endif
+}
+
 // Phase 1d: post_physics_step — progress, rewards, dones, per-field outputs (vss.py:189-193,
 // 218-265). Returns LANE_DONE if the episode ended this step (masked reset follows in phase 3).
 // Safety net (not in the reference): a field whose state is not finite is re-randomised on the
@@ -943,6 +953,7 @@ VSS_HD int lane_phase1d(float* S, long long env, const StepArgs& a, const DevPar
     reset_lane(S, P, key);
 #pragma unroll
     for (int k = 0; k < VSS_REW_PER_FIELD; ++k) rew[k] = 0.0f;
+    count_sanitised(a);
   }
   const bool done = !finite || is_goal(S[0], S[LDS], P) || progress >= P.max_len;
   const bool tmo = done && finite && progress >= P.max_len - 1;  // VecTask.step timeout_buf

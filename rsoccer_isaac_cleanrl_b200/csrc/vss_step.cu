@@ -285,7 +285,8 @@ struct vss_engine {
   int device;
   int64_t n, ld, goff;
   uint64_t seed;
-  unsigned long long* d_step;  // device words: [0] step index (keys the OU stream), [1] CTAs of the current step that finished
+  unsigned long long* d_step;  // device words: [0] step index (keys the OU stream), [1] CTAs of the current step that
+                               // finished, [2] fields re-randomised by the non-finite guard
   vss_params params;
   DevParams dp;
   float* state;
@@ -431,8 +432,8 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
   e = cudaMalloc(&h->state, bytes);
   if (e != cudaSuccess) { delete h; return fail(VSS_E_NOMEM, "vss_create: cudaMalloc(state)", e); }
   e = cudaMemset(h->state, 0, bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_step, 2 * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(h->d_step, 0, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_step, 3 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_step, 0, 3 * sizeof(unsigned long long));
   if (e != cudaSuccess) { cudaFree(h->state); cudaFree(h->d_step); delete h; return fail(VSS_E_CUDA, "vss_create: cudaMemset", e); }
   *out = h;
   return VSS_OK;
@@ -454,6 +455,13 @@ VSS_API uint64_t vss_step_count(vss_handle h) {
   unsigned long long v = 0;
   if (use_device(h) != VSS_OK) return 0;
   if (cudaMemcpy(&v, h->d_step, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return v;
+}
+VSS_API uint64_t vss_sanitised_count(vss_handle h) {
+  if (!h) return 0;
+  unsigned long long v = 0;
+  if (use_device(h) != VSS_OK) return 0;
+  if (cudaMemcpy(&v, h->d_step + 2, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   return v;
 }
 VSS_API int vss_set_step_count(vss_handle h, uint64_t n) {

@@ -77,6 +77,11 @@ class Engine:
     def step_count(self, n):
         check(self.lib.vss_set_step_count(self._h, int(n)))
 
+    @property
+    def sanitised_count(self):
+        """Fields re-randomised by the non-finite guard so far (include/vss_b200.h); synchronises."""
+        return int(self.lib.vss_sanitised_count(self._h))
+
     # ---- pipelining one step over several streams (include/vss_b200.h: vss_set_step_range)
     @property
     def step_granularity(self):

@@ -118,8 +118,10 @@ class _FusedView(Wrapper):
     # ---- the same call with HOST buffers (pinned): action in, (obs, reward, done) out
     HOST_CHUNKS = 8            # large batches are stepped in this many field ranges ...
     HOST_CHUNK_MIN_FIELDS = 1 << 17   # ... when there are at least this many fields
-    HOST_WRITE = "direct"      # packed rows: "direct" = the kernel stores into the mapped pinned buffer across
-                               # PCIe, no copy is issued; "staged" = device staging + one cudaMemcpyAsync per range
+    # Packed rows go to a device staging buffer and cross PCIe as ONE cudaMemcpyAsync per field range.
+    # (The kernel can also store straight into the mapped pinned buffer — `vss_set_step_packed` takes any
+    # device-accessible pointer — but 8-byte stores across PCIe reach 21 GB/s where the copy engine reaches
+    # 55 GB/s: 5.51 vs 2.37 ms per 2^20-field step, profiles/r02_a_e2e_host_rows.md.)
 
     def _host_buffers(self, packed):
         from .. import _lib
@@ -144,7 +146,7 @@ class _FusedView(Wrapper):
             h["done"] = pinned_empty((nv,), torch.long, task.device)
         return h
 
-    def step_host(self, action_host, obs_dtype=torch.bfloat16, host_write=None):
+    def step_host(self, action_host, obs_dtype=torch.bfloat16):
         """One step with HOST buffers: pinned policy action in, what `step()` returns to the policy out
         (envs/wrappers.py:108-115: observation, scalar reward, done) in pinned host memory.
 
@@ -161,7 +163,6 @@ class _FusedView(Wrapper):
         packed = obs_dtype == torch.bfloat16
         if not packed and obs_dtype != torch.float32:
             raise ValueError("step_host: obs_dtype must be torch.bfloat16 or torch.float32")
-        direct = (host_write or self.HOST_WRITE) == "direct"
         h = self._host_buffers(packed)
         act_host = action_host.view(h["act"].shape)
         n, agents = task.num_fields, nv // task.num_fields
@@ -169,7 +170,7 @@ class _FusedView(Wrapper):
         cur = torch.cuda.current_stream(task.device)
         g = task.engine.step_granularity
         per = -(-n // (chunks * g)) * g
-        self._packed_out = (h["rows"] if direct else h["rows_dev"]) if packed else None
+        self._packed_out = h["rows_dev"] if packed else None
         start = torch.cuda.Event()
         start.record(cur)
         ok = False
@@ -188,8 +189,7 @@ class _FusedView(Wrapper):
                         task.engine.set_step_range(f0, cnt)
                     obs, reward, done, _ = self.step(h["act"])
                     if packed:
-                        if not direct:
-                            h["rows"][v0:v1].copy_(h["rows_dev"][v0:v1], non_blocking=True)
+                        h["rows"][v0:v1].copy_(h["rows_dev"][v0:v1], non_blocking=True)
                     else:
                         h["obs"][v0:v1].copy_(obs["obs"][v0:v1], non_blocking=True)
                         h["reward"][v0:v1].copy_(reward[v0:v1], non_blocking=True)

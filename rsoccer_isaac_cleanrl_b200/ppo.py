@@ -41,7 +41,10 @@ def parse_args(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--exp-name", type=str, help="the name of this experiment")
     p.add_argument("--seed", type=int, default=1)
-    p.add_argument("--torch-deterministic", type=b, default=True, nargs="?", const=True)
+    p.add_argument("--torch-deterministic", type=b, default=True, nargs="?", const=True,
+                   help="sets torch.backends.cudnn.deterministic as the reference does; run-to-run bit "
+                        "reproducibility additionally needs --mlp-backend torch (the tcgen05 path reduces "
+                        "split-K partial sums and statistics with floating-point atomics in arbitrary order)")
     p.add_argument("--cuda", type=b, default=True, nargs="?", const=True)
     p.add_argument("--track", type=b, default=False, nargs="?", const=True)
     p.add_argument("--wandb-project-name", type=str, default="ppo-isaac-cleanrl")
@@ -77,6 +80,8 @@ def parse_args(argv=None):
     p.add_argument("--cuda-graph", type=b, default=True, nargs="?", const=True,
                    help="capture the whole T-step rollout (+ critic on terminal obs + GAE) in one CUDA graph")
     p.add_argument("--quiet", type=b, default=False, nargs="?", const=True)
+    p.add_argument("--tensorboard", type=b, default=True, nargs="?", const=True,
+                   help="write the reference's scalar tags (losses/*, Charts/SPS, rws/episodic_*) with SummaryWriter")
     args = p.parse_args(argv)
     args.batch_size = int(args.num_envs * args.num_steps)
     args.minibatch_size = int(args.batch_size // args.num_minibatches)
@@ -192,6 +197,105 @@ class FlatAdam:
                   self.eps)
 
 
+def anneal_lr(update, num_updates, learning_rate):
+    """ppo…:250-254: linear decay, `update` counts from 1."""
+    return (1.0 - (update - 1.0) / num_updates) * learning_rate
+
+
+def torch_minibatch_grad(agent, args, batch, inds, stats=None, clipfrac_sum=None):
+    """One minibatch of ppo…:314-352 with torch autograd (fp32): the clipped-surrogate / value / entropy
+    loss of the rows `inds` of `batch` (dict of b_obs, b_actions, b_logprobs, b_advantages, b_returns,
+    b_values) and its gradient into the parameters' .grad buffers (zeroed first). No host sync: the
+    statistics go to the device scalars in `stats`."""
+    _, newlogprob, entropy, newvalue = agent.get_action_and_value(batch["b_obs"][inds], batch["b_actions"][inds])
+    logratio = newlogprob - batch["b_logprobs"][inds]
+    ratio = logratio.exp()
+    with torch.no_grad():
+        if stats is not None:
+            stats["old_approx_kl"].copy_((-logratio).mean())
+            stats["approx_kl"].copy_(((ratio - 1) - logratio).mean())
+        if clipfrac_sum is not None:
+            clipfrac_sum.add_(((ratio - 1.0).abs() > args.clip_coef).float().mean())
+    mb_advantages = batch["b_advantages"][inds]
+    if args.norm_adv:
+        mb_advantages = (mb_advantages - mb_advantages.mean()) / (mb_advantages.std() + 1e-8)
+    pg_loss = torch.max(-mb_advantages * ratio,
+                        -mb_advantages * torch.clamp(ratio, 1 - args.clip_coef, 1 + args.clip_coef)).mean()
+    newvalue = newvalue.view(-1)
+    mb_returns = batch["b_returns"][inds]
+    if args.clip_vloss:
+        mb_values = batch["b_values"][inds]
+        v_clipped = mb_values + torch.clamp(newvalue - mb_values, -args.clip_coef, args.clip_coef)
+        v_loss = 0.5 * torch.max((newvalue - mb_returns) ** 2, (v_clipped - mb_returns) ** 2).mean()
+    else:
+        v_loss = 0.5 * ((newvalue - mb_returns) ** 2).mean()
+    entropy_loss = entropy.mean()
+    loss = pg_loss - args.ent_coef * entropy_loss + v_loss * args.vf_coef
+    if stats is not None:
+        with torch.no_grad():
+            stats["v_loss"].copy_(v_loss); stats["pg_loss"].copy_(pg_loss); stats["entropy"].copy_(entropy_loss)
+    for p in agent.parameters():
+        if p.grad is not None:
+            p.grad.zero_()
+    loss.backward()
+    return loss
+
+
+def update_policy(args, batch_size, randperm, run_minibatch, optimizer, read_kl):
+    """The epoch / minibatch schedule of ppo…:308-365 around a caller-supplied minibatch step.
+
+    `run_minibatch(mb_inds)` does forward, loss, backward, gradient clip and the optimiser step for the
+    given rows (including the shorter remainder minibatch that `range(0, batch_size, minibatch_size)`
+    visits when batch_size is not a multiple of it, ppo…:310-312). `read_kl()` returns the approx-KL of the
+    LAST minibatch as a float (mean over ranks); it is only called when a flag needs it, because it
+    synchronises. Adaptive LR (ppo…:356-361) looks at every minibatch; the target-KL stop (ppo…:363-365)
+    looks at the last minibatch of an epoch, after the inner loop. Returns (minibatches run, epochs run)."""
+    n_mb = 0
+    epochs = 0
+    for epoch in range(args.update_epochs):
+        epochs += 1
+        b_inds = randperm(batch_size)
+        for start in range(0, batch_size, args.minibatch_size):
+            run_minibatch(b_inds[start:start + args.minibatch_size])
+            n_mb += 1
+            if args.adaptative_lr:
+                kl = read_kl()
+                current_lr = optimizer.param_groups[0]["lr"]
+                if kl > 2.0 * args.threshold_kl:
+                    optimizer.param_groups[0]["lr"] = max(current_lr / 1.5, 1e-6)
+                elif kl < 0.5 * args.threshold_kl:
+                    optimizer.param_groups[0]["lr"] = min(current_lr * 1.5, 1e-2)
+        if args.target_kl is not None and read_kl() > args.target_kl:
+            break
+    return n_mb, epochs
+
+
+
+def _make_writer(args, rank, log):
+    """SummaryWriter of ppo…:195-199 (rank 0; None when --quiet, --tensorboard false or tensorboard is not
+    installed). W&B (--track) and video capture are out of scope: say so instead of
+    silently ignoring the flags."""
+    if rank != 0:
+        return None
+    if args.track:
+        log("warning: --track (Weights & Biases) is not implemented by this engine; the TensorBoard event file "
+            "carries the same scalars")
+    if args.capture_video:
+        log("warning: --capture-video is not implemented by this engine (no renderer); flag ignored")
+    if args.quiet or not getattr(args, "tensorboard", True):
+        return None
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+    except Exception as e:
+        log(f"warning: tensorboard is not available ({e}); no event file is written")
+        return None
+    run_name = f"{args.exp_name}_ppo-{args.env_id}_{args.seed}"
+    writer = SummaryWriter(os.path.join(getattr(args, "save_path", "runs"), run_name))
+    writer.add_text("hyperparameters", "|param|value|\n|-|-|\n%s" % (
+        "\n".join([f"|{key}|{value}|" for key, value in vars(args).items()])))
+    return writer
+
+
 def train(args, log=print, hook=None):
     import torch.distributed as dist
     from .envs import RecordEpisodeStatisticsTorch, make_env
@@ -205,6 +309,7 @@ def train(args, log=print, hook=None):
     torch.backends.cudnn.deterministic = args.torch_deterministic
     device = torch.device("cuda", local)
 
+    writer = _make_writer(args, rank, log)
     unwrapped_env, envs = make_env(args)
     envs = ExtractObsWrapper(envs)
     envs = RecordEpisodeStatisticsTorch(envs, device)
@@ -338,37 +443,17 @@ def train(args, log=print, hook=None):
         backward_explicit(mw_actor, hs_a, d_mean)
         join_side()
 
-    def forward_backward():
+    batch = dict(b_obs=b_obs, b_actions=b_actions, b_logprobs=b_logprobs, b_advantages=b_advantages,
+                 b_returns=b_returns, b_values=b_values)
+
+    def forward_backward(inds=None):
         """One minibatch: clipped-surrogate loss and its gradient into flat_grad (ppo…:314-352).
-        Reads the static index buffer mb_inds; no host sync (the reference's `.item()` at :322 is
-        replaced by device-side accumulation), so it can be replayed as a CUDA graph."""
-        if fused:
+        Reads the static index buffer mb_inds (or `inds`: the eager path of a remainder minibatch); no
+        host sync (the reference's `.item()` at :322 is replaced by device-side accumulation), so it can
+        be replayed as a CUDA graph."""
+        if fused and inds is None:
             return forward_backward_fused()
-        _, newlogprob, entropy, newvalue = agent.get_action_and_value(b_obs[mb_inds], b_actions[mb_inds])
-        logratio = newlogprob - b_logprobs[mb_inds]
-        ratio = logratio.exp()
-        with torch.no_grad():
-            mb_stats["old_approx_kl"].copy_((-logratio).mean())
-            mb_stats["approx_kl"].copy_(((ratio - 1) - logratio).mean())
-            clipfrac_sum.add_(((ratio - 1.0).abs() > args.clip_coef).float().mean())
-        mb_advantages = b_advantages[mb_inds]
-        if args.norm_adv:
-            mb_advantages = (mb_advantages - mb_advantages.mean()) / (mb_advantages.std() + 1e-8)
-        pg_loss = torch.max(-mb_advantages * ratio,
-                            -mb_advantages * torch.clamp(ratio, 1 - args.clip_coef, 1 + args.clip_coef)).mean()
-        newvalue = newvalue.view(-1)
-        if args.clip_vloss:
-            v_loss_unclipped = (newvalue - b_returns[mb_inds]) ** 2
-            v_clipped = b_values[mb_inds] + torch.clamp(newvalue - b_values[mb_inds], -args.clip_coef, args.clip_coef)
-            v_loss = 0.5 * torch.max(v_loss_unclipped, (v_clipped - b_returns[mb_inds]) ** 2).mean()
-        else:
-            v_loss = 0.5 * ((newvalue - b_returns[mb_inds]) ** 2).mean()
-        entropy_loss = entropy.mean()
-        loss = pg_loss - args.ent_coef * entropy_loss + v_loss * args.vf_coef
-        with torch.no_grad():
-            mb_stats["v_loss"].copy_(v_loss); mb_stats["pg_loss"].copy_(pg_loss); mb_stats["entropy"].copy_(entropy_loss)
-        flat_grad.zero_()
-        loss.backward()
+        torch_minibatch_grad(agent, args, batch, mb_inds if inds is None else inds, mb_stats, clipfrac_sum)
 
     def clip_and_step():
         """nn.utils.clip_grad_norm_ + Adam on the flat buffer (ppo…:353-354); flat_grad holds the SUM
@@ -381,16 +466,103 @@ def train(args, log=print, hook=None):
         flat_grad.mul_(torch.clamp(args.max_grad_norm / (gnorm + 1e-6), max=1.0))
         optimizer.step()
 
-    rollout_graph = fb_graph = opt_graph = None
+    def reduce_gradient():
+        """The one collective of the path: sum of the flat gradient over ranks (clip_and_step divides)."""
+        if world > 1:
+            dist.all_reduce(flat_grad)
+
+    # Can this process group's all-reduce be recorded into a CUDA graph? (Then the whole minibatch —
+    # forward, backward, all-reduce, clip, Adam — is ONE graph replay and the collective no longer sits
+    # between two replays with Python in between.) Probed once on a scratch tensor.
+    nccl_in_graph = False
+    if world > 1 and args.cuda_graph:
+        try:
+            probe = torch.zeros(1024, device=device)
+            dist.all_reduce(probe)            # (communicator set-up happens outside capture)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                dist.all_reduce(probe)
+            g.replay()
+            torch.cuda.synchronize()
+            nccl_in_graph = True
+            del g, probe
+        except Exception as e:  # keep the collective between the graphs, as before
+            log(f"[rank {rank}] NCCL all-reduce is not graph-capturable here ({type(e).__name__}: {e}); using the eager collective")
+            torch.cuda.synchronize()
+
+    def minibatch_step():
+        """forward + backward + all-reduce + clip + Adam of the rows in mb_inds (graph-capturable)."""
+        forward_backward()
+        reduce_gradient()
+        clip_and_step()
+
+    rollout_graph = None
+    mb_graph = fb_graph = opt_graph = None
+    state = {"update": 0}
+
+    def run_minibatch(inds):
+        optimizer.sync_lr()
+        if inds.numel() != args.minibatch_size:
+            # the shorter remainder minibatch of ppo…:310-312 (only when batch_size is not a multiple of
+            # num_minibatches): eager, torch autograd, its own index tensor
+            forward_backward(inds)
+            reduce_gradient()
+            clip_and_step()
+            return
+        nonlocal mb_graph, fb_graph, opt_graph
+        mb_inds.copy_(inds)
+        capture = args.cuda_graph and state["update"] >= 2
+        if world == 1 or nccl_in_graph:
+            if mb_graph is not None:
+                mb_graph.replay()
+            elif capture:
+                torch.cuda.synchronize()
+                mb_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(mb_graph):
+                    minibatch_step()
+                mb_graph.replay()
+            else:
+                minibatch_step()
+            return
+        if fb_graph is not None:
+            fb_graph.replay()
+        elif capture:
+            torch.cuda.synchronize()
+            fb_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(fb_graph):
+                forward_backward()
+            fb_graph.replay()
+        else:
+            forward_backward()
+        reduce_gradient()
+        if opt_graph is not None:
+            opt_graph.replay()
+        elif capture:
+            torch.cuda.synchronize()
+            opt_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(opt_graph):
+                clip_and_step()
+            opt_graph.replay()
+        else:
+            clip_and_step()
+
+    def read_kl():
+        kl = mb_stats["approx_kl"].detach().clone()
+        if world > 1:
+            dist.all_reduce(kl); kl /= world
+        return float(kl)
+
     global_step = 0
     start_time = time.time()
     next_obs = envs.reset()
     num_updates = args.total_timesteps // (args.batch_size * world)
-    stats = {"sps": [], "updates": 0, "update_wall": [], "rollout_wall": []}
+    stats = {"sps": [], "updates": 0, "update_wall": [], "rollout_wall": [], "lr": [], "minibatches": [], "epochs": []}
     t_roll = t_upd = 0.0
     for update in range(1, num_updates + 1):
+        state["update"] = update
         if args.anneal_lr:
-            optimizer.param_groups[0]["lr"] = (1.0 - (update - 1.0) / num_updates) * args.learning_rate
+            optimizer.param_groups[0]["lr"] = anneal_lr(update, num_updates, args.learning_rate)
         tr0 = time.time()
         global_step += T * N * world
         if rollout_graph is not None:
@@ -410,54 +582,9 @@ def train(args, log=print, hook=None):
         t_roll += tu0 - tr0
 
         clipfrac_sum.zero_()
-        n_mb = 0
-        stop = False
-        for epoch in range(args.update_epochs):
-            b_inds = torch.randperm(args.batch_size, device=device)
-            # full minibatches only (the reference's loop at ppo…:310 also visits a shorter remainder when
-            # batch_size is not a multiple of num_minibatches; with the default flags there is none)
-            for start in range(0, args.batch_size - args.minibatch_size + 1, args.minibatch_size):
-                mb_inds.copy_(b_inds[start:start + args.minibatch_size])
-                optimizer.sync_lr()
-                if fb_graph is not None:
-                    fb_graph.replay()
-                elif args.cuda_graph and update >= 2:
-                    torch.cuda.synchronize()
-                    fb_graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(fb_graph):
-                        forward_backward()
-                    fb_graph.replay()
-                else:
-                    forward_backward()
-                if world > 1:  # the one collective of the path: mean gradient over ranks
-                    dist.all_reduce(flat_grad)
-                if opt_graph is not None:
-                    opt_graph.replay()
-                elif args.cuda_graph and update >= 2:
-                    torch.cuda.synchronize()
-                    opt_graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(opt_graph):
-                        clip_and_step()
-                    opt_graph.replay()
-                else:
-                    clip_and_step()
-                n_mb += 1
-
-                if args.adaptative_lr or args.target_kl is not None:
-                    kl = mb_stats["approx_kl"].detach().clone()
-                    if world > 1:
-                        dist.all_reduce(kl); kl /= world
-                    kl = float(kl)
-                    if args.adaptative_lr:
-                        cur = optimizer.param_groups[0]["lr"]
-                        if kl > 2.0 * args.threshold_kl:
-                            optimizer.param_groups[0]["lr"] = max(cur / 1.5, 1e-6)
-                        elif kl < 0.5 * args.threshold_kl:
-                            optimizer.param_groups[0]["lr"] = min(cur * 1.5, 1e-2)
-                    if args.target_kl is not None and kl > args.target_kl:
-                        stop = True
-            if stop:
-                break
+        n_mb, n_ep = update_policy(args, args.batch_size, lambda n_: torch.randperm(n_, device=device), run_minibatch,
+                                   optimizer, read_kl)
+        stats["lr"].append(optimizer.param_groups[0]["lr"]); stats["minibatches"].append(n_mb); stats["epochs"].append(n_ep)
         torch.cuda.synchronize()
         t_upd += time.time() - tu0
         if hook is not None:  # diagnostics: called once per update with the live tensors
@@ -470,6 +597,26 @@ def train(args, log=print, hook=None):
         sps = int(global_step / (time.time() - start_time))
         stats["sps"].append(sps)
         stats["updates"] = update
+        if writer is not None:  # the reference's tags (ppo…:273-279, 367-376); one host read per update
+            writer.add_scalar("losses/learning_rate", optimizer.param_groups[0]["lr"], global_step)
+            writer.add_scalar("losses/value_loss", mb_stats["v_loss"].item(), global_step)
+            writer.add_scalar("losses/policy_loss", mb_stats["pg_loss"].item(), global_step)
+            writer.add_scalar("losses/entropy", mb_stats["entropy"].item(), global_step)
+            writer.add_scalar("losses/old_approx_kl", mb_stats["old_approx_kl"].item(), global_step)
+            writer.add_scalar("losses/approx_kl", mb_stats["approx_kl"].item(), global_step)
+            writer.add_scalar("losses/clipfrac", (clipfrac_sum / max(n_mb, 1)).item(), global_step)
+            writer.add_scalar("Charts/SPS", sps, global_step)
+            writer.add_scalar("engine/sanitised_fields", unwrapped_env.engine.sanitised_count, global_step)
+            # an episode that ended on the rollout's last step (the reference samples steps 0-2 of the rollout
+            # on the host; here the rollout is one CUDA graph, so the sample is taken after it)
+            ended = next_dones[T - 1].nonzero()
+            if ended.numel():
+                idx = int(ended[0])
+                r4 = envs.returned_episode_returns[idx]
+                for j, key in enumerate(("goal", "grad", "move", "energy")):
+                    writer.add_scalar(f"rws/episodic_{key}", r4[j].item(), global_step)
+                writer.add_scalar("rws/episodic_return", r4.sum().item(), global_step)
+                writer.add_scalar("rws/episodic_length", envs.returned_episode_lengths[idx].item(), global_step)
         if rank == 0 and not args.quiet:
             r = envs.returned_episode_returns.sum(1)
             log(f"update {update}/{num_updates} step {global_step} SPS {sps} lr {optimizer.param_groups[0]['lr']:.2e} "
@@ -479,6 +626,10 @@ def train(args, log=print, hook=None):
     stats.update(global_step=global_step, wall=time.time() - start_time, rollout_s=t_roll, update_s=t_upd,
                  final_sps=(global_step / max(time.time() - start_time, 1e-9)))
     stats["mlp_backend"] = "tcgen05-bf16" if backend == "tc" else "torch-fp32"
+    stats["nccl_in_graph"] = nccl_in_graph
+    stats["sanitised_fields"] = unwrapped_env.engine.sanitised_count
+    if writer is not None:
+        writer.close()
     stats["agent"] = agent
     stats["env"] = unwrapped_env
     return stats

@@ -138,6 +138,10 @@ class GpuBackend:
     def _t(self, a):
         return None if a is None else self.torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
 
+    @property
+    def sanitised_count(self):
+        return self.eng.sanitised_count
+
     def set_reward_weights(self, goal, grad, move, energy):
         self.eng.set_reward_weights(goal, grad, move, energy)
 

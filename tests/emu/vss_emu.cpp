@@ -74,8 +74,8 @@ __attribute__((visibility("default"))) int emu_step(
   StepArgs a;
   memset(&a, 0, sizeof(a));
   a.state = state; a.n = n; a.ld = ld; a.goff = goff;
-  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); unsigned long long step_ctr = step;  // grid = 1: the counter is the step index
-  a.step_ctr = &step_ctr; a.grid = 1;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); unsigned long long step_ctr[3] = {step, 0, 0};  // index, CTA count, sanitised fields
+  a.step_ctr = step_ctr; a.grid = 1;
   a.actions = actions; a.inject = inject; a.reset_buf = reset_buf; a.obs = obs; a.term_obs = term_obs;
   a.rew = rew; a.timeout = timeout; a.progress_f = progress_f; a.policy_action = policy_action;
   a.action_buf = action_buf; a.reward_v = reward_v; a.done_v = done_v; a.ep_ret = ep_ret; a.ep_len = ep_len;

@@ -2,7 +2,8 @@
 
 Run in the build container only (needs /root/reference, which does not exist on the GPU
 box):   python tests/golden/make_golden.py
-Outputs (committed): tests/golden/jit_functions.npz, gae.npz, wrappers.npz, agent.npz, ppo_defaults.json
+Outputs (committed): tests/golden/jit_functions.npz, gae.npz, wrappers.npz, agent.npz, ppo_update.npz,
+play.npz, ppo_schedule.npz, ppo_defaults.json
 
 Nothing from the reference is copied into the repo: the source ranges below are read from
 /root/reference at generation time and exec'd in a scratch namespace.
@@ -397,6 +398,209 @@ def gen_ppo_update():
 
 
 
+# ------------------------------------------------------------------ play.py: teams + match runner
+class FakeMatchTask:
+    """Raw-task stand-in for play_matches (play.py:131-164): replays fixed VSS.step outputs, records
+    every action buffer it is stepped with."""
+
+    def __init__(self, steps, obs0):
+        self.steps, self.obs0 = steps, obs0
+        n = obs0.shape[0]
+        self.cfg = {"env": {"numEnvs": n}}
+        self.device = "cpu"
+        self.action_space = types.SimpleNamespace(shape=(2, 3, 2))
+        self.observation_space = types.SimpleNamespace(shape=(2, 3, 52))
+        self.reset_buf = torch.zeros(n, dtype=torch.long)
+        self.reset_dones_calls, self.t, self.seen_actions = 0, 0, []
+
+    def reset_dones(self):
+        assert bool((self.reset_buf == 1).all())  # play.py:132-133 forces a full reset first
+        self.reset_dones_calls += 1
+
+    def reset(self):
+        return {"obs": torch.from_numpy(self.obs0).clone()}
+
+    def step(self, actions):
+        self.seen_actions.append(actions.clone().numpy())
+        s = self.steps[self.t]
+        self.t += 1
+        infos = {"progress_buffer": torch.from_numpy(s["progress_f"]).clone()}
+        return ({"obs": torch.from_numpy(s["obs"]).clone()}, torch.from_numpy(s["rew"]).clone(),
+                torch.from_numpy(s["reset"]).clone(), infos)
+
+
+def play_fixture(rng, n=1100, T=6):
+    obs0 = rng.normal(size=(n, 2, 3, 52)).astype(np.float32)
+    steps = []
+    for t in range(T):
+        reset = (rng.uniform(size=n) < 0.02).astype(np.int64)
+        reset[1065:] = 1  # fields beyond the first 1065 are never counted (play.py:158)
+        rew = np.zeros((n, 2, 3, 4), np.float32)
+        rew[..., 0] = rng.choice([-1.0, 0.0, 1.0], size=(n, 1, 1)).astype(np.float32) * np.float32([[1], [-1]])
+        steps.append(dict(obs=rng.normal(size=(n, 2, 3, 52)).astype(np.float32), rew=rew, reset=reset,
+                          progress_f=rng.integers(1, 401, n).astype(np.float32)))
+    return obs0, steps
+
+
+def weight_checksum(t):
+    """(sum, sum of |x|) in float64: identifies a weight tensor without storing it."""
+    a = t.detach().double()
+    return np.float64([a.sum().item(), a.abs().sum().item()])
+
+
+def weight_sample(t, stride=97, count=256):
+    """A strided sample of a tensor's elements (keeps the fixtures small)."""
+    return t.detach().reshape(-1)[::stride][:count].numpy().copy()
+
+
+def gen_play():
+    """Executes the reference's play.py:1-102 (teams, get_team) and :131-164 (play_matches) — 'cuda:0'
+    rewritten to 'cpu', BASELINE_TEAMS (:105-128, loads the missing base_nets at import) left out — over
+    the gym shim, the reference's own Agent (ppo…:121-164) and a fake task that replays fixed outputs."""
+    import tempfile
+    gym = _gym_shim()
+
+    class ObservationWrapper(gym.Wrapper):
+        def reset(self, **kw):
+            return self.observation(self.env.reset(**kw))
+
+        def step(self, action):
+            o, r, d, i = self.env.step(action)
+            return self.observation(o), r, d, i
+
+    gym.ObservationWrapper = ObservationWrapper
+    sys.modules["gym"] = gym
+    ppo_ns = dict(torch=torch, nn=torch.nn, np=np, gym=gym)
+    exec("from torch.distributions.normal import Normal\n" + _lines("ppo_continuous_action_isaacgym.py", 121, 169), ppo_ns)
+    fake_ppo = types.ModuleType("ppo_continuous_action_isaacgym")
+    fake_ppo.Agent, fake_ppo.ExtractObsWrapper = ppo_ns["Agent"], ppo_ns["ExtractObsWrapper"]
+    sys.modules["ppo_continuous_action_isaacgym"] = fake_ppo
+    src = (_lines("play.py", 1, 102) + "\n" + _lines("play.py", 131, 164)).replace("'cuda:0'", "'cpu'")
+    P = {}
+    exec(src, P)
+    rng = np.random.default_rng(21)
+    obs0, steps = play_fixture(rng)
+    # (the inputs are not stored: the test regenerates them with play_fixture(default_rng(21)); a checksum
+    # guards against a numpy whose generator streams differ)
+    out = {"T": np.int64(len(steps)), "obs0_sum": np.float64(obs0.astype(np.float64).sum()),
+           "last_obs_sum": np.float64(steps[-1]["obs"].astype(np.float64).sum())}
+    # checkpoints in the reference's own format: torch.save(agent.state_dict()) (ppo…:379)
+    tmp = tempfile.mkdtemp(prefix="vss_play_")
+    dummy = lambda adim: types.SimpleNamespace(single_observation_space=types.SimpleNamespace(shape=(52,)),
+                                               single_action_space=types.SimpleNamespace(shape=(adim,)))
+    ckpt = {}
+    for adim in (2, 6):
+        torch.manual_seed(40 + adim)
+        agent = ppo_ns["Agent"](dummy(adim))
+        with torch.no_grad():
+            agent.actor_mean[8].weight.mul_(30.0)
+            agent.actor_logstd.fill_(-1.0)
+        ckpt[adim] = os.path.join(tmp, f"agent{adim}.pt")
+        torch.save(agent.state_dict(), ckpt[adim])
+        # (weights are not stored: the test rebuilds them from the same seed with the product's Agent — same
+        # layer order and initialisers — and checks these per-tensor checksums)
+        for k, v in agent.state_dict().items():
+            out[f"ckpt{adim}_sum_{k}"] = weight_checksum(v)
+    cases = {"zero_vs_ou": ("zero", None, "ou", None), "sa_vs_zero": ("ppo-sa", 2, "zero", None),
+             "cma_vs_dma": ("ppo-cma", 6, "ppo-dma", 2), "sax3_vs_sa": ("ppo-sa-x3", 2, "ppo-sa", 2)}
+    for name, (ba, bd, ya, yd) in cases.items():
+        torch.manual_seed(77)
+        blue = P["get_team"](ba, ckpt.get(bd))
+        yellow = P["get_team"](ya, ckpt.get(yd))
+        task = FakeMatchTask(steps, obs0)
+        n_matches = 60
+        score, length = P["play_matches"](task, blue, yellow, n_matches)
+        assert task.reset_dones_calls == 1
+        out[f"{name}_score"], out[f"{name}_length"] = np.float64(score), np.float64(length)
+        out[f"{name}_steps"] = np.int64(task.t)
+        for t, a in enumerate(task.seen_actions):
+            out[f"{name}_act{t}"] = a
+    np.savez_compressed(os.path.join(OUT, "play.npz"), **out)
+    print("play.npz", len(out), "arrays")
+
+
+# ------------------------------------------------------------------ PPO update schedule
+def schedule_fixture(adim=2, R=14):
+    g = torch.Generator().manual_seed(123)
+    r = lambda *s: torch.randn(*s, generator=g)
+    return dict(obs=r(R, 52), actions=r(R, adim) * 0.7, dlogp=0.3 * r(R), dval=0.3 * r(R), adv=r(R) * 1.5 + 0.2, ret=r(R))
+
+
+def gen_ppo_schedule():
+    """Executes the reference's whole optimisation phase (ppo…:298-365: flatten, epochs, randperm,
+    minibatches incl. the shorter remainder, adaptive LR, target-KL stop) and its LR annealing lines
+    (:250-254) on its own Agent, batch 14 = 7 envs x 2 steps, minibatch 14 // 4 = 3 (-> 3,3,3,3,2)."""
+    sys.modules.setdefault("gym", _gym_shim())
+    ns0 = dict(torch=torch, nn=torch.nn, np=np)
+    exec("from torch.distributions.normal import Normal\n" + _lines("ppo_continuous_action_isaacgym.py", 121, 164), ns0)
+    body = textwrap.dedent(_lines("ppo_continuous_action_isaacgym.py", 298, 365))
+    anneal = textwrap.dedent(_lines("ppo_continuous_action_isaacgym.py", 250, 254))
+    out = {}
+    fx = schedule_fixture()
+    for k, v in fx.items():
+        out[f"fx_{k}"] = v.numpy().copy()
+    cases = {"plain": {}, "adaptive": dict(adaptative_lr=True, threshold_kl=0.008),
+             "adaptive_up": dict(adaptative_lr=True, threshold_kl=50.0),
+             "target_kl": dict(target_kl=0.002), "clipv_nonorm": dict(clip_vloss=True, norm_adv=False)}
+    for name, over in cases.items():
+        torch.manual_seed(9)
+        envs = types.SimpleNamespace(single_observation_space=types.SimpleNamespace(shape=(52,)),
+                                     single_action_space=types.SimpleNamespace(shape=(2,)))
+        agent = ns0["Agent"](envs)
+        with torch.no_grad():
+            agent.actor_mean[8].weight.mul_(20.0)
+            agent.actor_logstd.fill_(-0.3)
+        if name == "plain":
+            for k, v in agent.state_dict().items():
+                out[f"init_sum_{k}"] = weight_checksum(v)
+        with torch.no_grad():
+            _, lp, _, val = agent.get_action_and_value(fx["obs"], fx["actions"])
+        T, N = 2, 7
+        args = types.SimpleNamespace(num_envs=N, num_steps=T, batch_size=T * N, minibatch_size=(T * N) // 4,
+                                     update_epochs=3, clip_coef=0.2, norm_adv=True, clip_vloss=False, ent_coef=0.005,
+                                     vf_coef=4.0, max_grad_norm=1.5, adaptative_lr=False, threshold_kl=0.008,
+                                     target_kl=None, learning_rate=3e-3)
+        for k, v in over.items():
+            setattr(args, k, v)
+        optimizer = torch.optim.Adam(agent.parameters(), lr=args.learning_rate, eps=1e-5)
+        lr_trace, kl_trace = [], []
+
+        class Spy(torch.optim.Adam):
+            pass
+
+        orig_step = optimizer.step
+
+        def step_spy(*a, **k):
+            lr_trace.append(optimizer.param_groups[0]["lr"])
+            return orig_step(*a, **k)
+
+        optimizer.step = step_spy
+        env = dict(ns0, agent=agent, args=args, optimizer=optimizer, device="cpu", envs=envs,
+                   obs=fx["obs"].view(T, N, 52), logprobs=(lp + fx["dlogp"]).view(T, N),
+                   actions=fx["actions"].view(T, N, 2), advantages=fx["adv"].view(T, N), returns=fx["ret"].view(T, N),
+                   values=(val.view(-1) + fx["dval"]).view(T, N))
+        torch.manual_seed(31)  # the randperm stream of the update phase
+        exec(body, env)
+        out[f"{name}_lr_at_step"] = np.float64(lr_trace)
+        out[f"{name}_lr_final"] = np.float64(optimizer.param_groups[0]["lr"])
+        out[f"{name}_minibatches"] = np.int64(len(lr_trace))
+        out[f"{name}_last_kl"] = np.float32(env["approx_kl"].item())
+        out[f"{name}_clipfracs"] = np.float32(env["clipfracs"])
+        for k, v in agent.state_dict().items():
+            out[f"{name}_final_{k}"] = weight_sample(v)
+    # annealing: lr at update u of num_updates
+    lrs = []
+    for u in (1, 2, 7, 48):
+        opt = types.SimpleNamespace(param_groups=[{"lr": None}])
+        env = dict(args=types.SimpleNamespace(anneal_lr=True, learning_rate=1e-3), update=u, num_updates=48, optimizer=opt)
+        exec(anneal, env)
+        lrs.append(opt.param_groups[0]["lr"])
+    out["anneal_updates"], out["anneal_lr"] = np.int64([1, 2, 7, 48]), np.float64(lrs)
+    np.savez_compressed(os.path.join(OUT, "ppo_schedule.npz"), **out)
+    print("ppo_schedule.npz", len(out), "arrays", {k: int(out[f"{k}_minibatches"]) for k in cases})
+
+
+
 def gen_ppo_defaults():
     """Defaults of every CLI flag: the reference's parse_args (ppo…:48-118) executed with no argv."""
     import argparse
@@ -433,3 +637,5 @@ if __name__ == "__main__":
     gen_wrappers()
     gen_agent()
     gen_ppo_update()
+    gen_play()
+    gen_ppo_schedule()

@@ -563,6 +563,8 @@ def check_nonfinite_guard(Backend, n=96):
     assert np.array_equal(bits(out["obs"][poisoned]), bits(out["term_obs"][poisoned]))   # fresh state in both
     compare_full_step(out, ref, rb, rb_ref, n, "non-finite guard", exact_physics=False)
     assert np.isfinite(be.get_state()[:58, :n]).all()
+    if hasattr(be, "sanitised_count"):   # the event is counted (vss_sanitised_count), not silent
+        assert be.sanitised_count == len(poisoned)
 
 
 # --------------------------------------------------------------------------- RNG statistics
