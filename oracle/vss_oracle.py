@@ -234,13 +234,14 @@ def physics(params, state: State):
     lib().orc_physics(C.byref(params), C.byref(cs))
 
 
-def step(params, seed, global_offset, state: State, actions, reset_buf, post_state=None):
+def step(params, seed, global_offset, state: State, actions, reset_buf, post_state=None, out=None):
     """VSS.step (envs/vss.py:180-203 + VecTask.step). reset_buf (N) int64 is updated in
-    place. Returns dict(obs, term_obs, rew, timeout, progress_f)."""
+    place. Returns dict(obs, term_obs, rew, timeout, progress_f); `out` = a dict returned by an
+    earlier call, to write into the same (persistent) buffers as the reference does."""
     n = state.n
     actions = _f32(actions).reshape(n, NT, NR, 2)
     assert reset_buf.dtype == np.int64 and reset_buf.flags.c_contiguous
-    out = dict(
+    out = out if out is not None else dict(
         obs=np.empty((n, NT, NR, NOBS), np.float32), term_obs=np.empty((n, NT, NR, NOBS), np.float32),
         rew=np.empty((n, NT, NR, 4), np.float32), timeout=np.empty((n,), np.uint8),
         progress_f=np.empty((n,), np.float32))
@@ -259,21 +260,23 @@ VIEW_SA, VIEW_CMA, VIEW_DMA = 0, 1, 2
 
 
 def step_view(params, seed, global_offset, step_index, state: State, view, policy_action, action_buf,
-              reset_buf, ep_ret=None, ep_len=None):
-    """SingleAgent/CMA/DMA.step + RecordEpisodeStatisticsTorch.step (envs/wrappers.py)."""
+              reset_buf, ep_ret=None, ep_len=None, out=None):
+    """SingleAgent/CMA/DMA.step + RecordEpisodeStatisticsTorch.step (envs/wrappers.py). `out` = a dict
+    returned by an earlier call (same view, same statistics arguments): reuse its buffers."""
     n = state.n
     nv = n * 3 if view == VIEW_DMA else n
     policy_action = _f32(policy_action)
     assert action_buf.dtype == np.float32 and action_buf.flags.c_contiguous
-    out = dict(
+    out = out if out is not None else dict(
         obs=np.empty((nv, NOBS), np.float32), term_obs=np.empty((nv, NOBS), np.float32),
         rews=np.empty((nv, 4), np.float32), reward=np.empty((nv,), np.float32),
         done=np.empty((nv,), np.int64), timeout=np.empty((nv,), np.uint8),
         progress=np.empty((nv,), np.float32))
     ret_ret = ret_len = None
     if ep_ret is not None:
-        ret_ret, ret_len = np.empty((nv, 4), np.float32), np.empty((nv,), np.int32)
-        out["ret_ret"], out["ret_len"] = ret_ret, ret_len
+        if "ret_ret" not in out:
+            out["ret_ret"], out["ret_len"] = np.empty((nv, 4), np.float32), np.empty((nv,), np.int32)
+        ret_ret, ret_len = out["ret_ret"], out["ret_len"]
     cs = state._c()
     lib().orc_step_view(C.byref(params), C.c_uint64(seed), C.c_int64(global_offset), C.c_uint32(step_index),
                         C.byref(cs), C.c_int(view), _p(policy_action), _p(action_buf), _p(reset_buf),
