@@ -679,6 +679,7 @@ ORC_API void orc_view_outputs(int64_t N, int view, const float* obs, const float
                               float* reward_v, int64_t* done_v, uint8_t* timeout_v, float* progress_v,
                               float* ep_ret, int32_t* ep_len, float* ret_ret, int32_t* ret_len) {
   const int per = (view == VSS_VIEW_DMA) ? 3 : 1;
+#pragma omp parallel for schedule(static)
   for (int64_t n = 0; n < N; ++n) {
     /* action_buf[env_ids] *= 0 for done envs, wrappers.py:105-107 */
     if (reset_buf[n] != 0)
@@ -722,11 +723,20 @@ ORC_API void orc_step_view(const vss_params* p, uint64_t seed, int64_t global_of
                            float* reward_v, int64_t* done_v, uint8_t* timeout_v, float* progress_v,
                            float* ep_ret, int32_t* ep_len, float* ret_ret, int32_t* ret_len) {
   const int64_t N = s->n;
-  float* obs = (float*)malloc(sizeof(float) * N * VSS_OBS_PER_FIELD);
-  float* tobs = (float*)malloc(sizeof(float) * N * VSS_OBS_PER_FIELD);
-  float* rew = (float*)malloc(sizeof(float) * N * VSS_REW_PER_FIELD);
-  uint8_t* tout = (uint8_t*)malloc(N);
-  float* prog = (float*)malloc(sizeof(float) * N);
+  /* the raw task's persistent buffers (obs_buf, rew_buf, ... of envs/vss.py:75-97): kept between calls, as
+   * the reference keeps them, so that a timed run does not pay 2.6 KB per field of page faults per step */
+  static float *obs = NULL, *tobs = NULL, *rew = NULL, *prog = NULL;
+  static uint8_t* tout = NULL;
+  static int64_t cap = 0;
+  if (N > cap) {
+    free(obs); free(tobs); free(rew); free(tout); free(prog);
+    obs = (float*)malloc(sizeof(float) * N * VSS_OBS_PER_FIELD);
+    tobs = (float*)malloc(sizeof(float) * N * VSS_OBS_PER_FIELD);
+    rew = (float*)malloc(sizeof(float) * N * VSS_REW_PER_FIELD);
+    tout = (uint8_t*)malloc(N);
+    prog = (float*)malloc(sizeof(float) * N);
+    cap = N;
+  }
   /* action_buf = random_ou(action_buf); act_view[:] = action  (wrappers.py:102-103) */
 #pragma omp parallel for schedule(static)
   for (int64_t n = 0; n < N; ++n) {
@@ -738,7 +748,6 @@ ORC_API void orc_step_view(const vss_params* p, uint64_t seed, int64_t global_of
   orc_step(p, seed, global_offset, s, action_buf, NULL, 0, reset_buf, obs, tobs, rew, tout, prog);
   orc_view_outputs(N, view, obs, tobs, rew, reset_buf, tout, prog, action_buf, obs_v, term_obs_v, rews_v,
                    reward_v, done_v, timeout_v, progress_v, ep_ret, ep_len, ret_ret, ret_len);
-  free(obs); free(tobs); free(rew); free(tout); free(prog);
 }
 
 /* ------------------------------------------------------------------------- */
