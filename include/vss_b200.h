@@ -217,6 +217,15 @@ VSS_API int vss_set_step_packed(vss_handle h, void* rows);
  * first_field and num_fields must be multiples of vss_step_granularity(h), except that the last range
  * may end at num_envs. Host-side state of the handle, like vss_set_step_aux. */
 VSS_API int64_t vss_step_granularity(vss_handle h);
+
+/* Launch shape of the step kernels: how many warps share one 32-field tile. 1 = one warp per tile (one
+ * lane per field walks the 6 robots and the ball in turn: the shape of large batches, HBM-bound);
+ * 2..8 = the bodies of a tile are dealt to that many warps, which shortens the critical path of a tile
+ * (small and medium batches, latency-bound). 0 (default) = chosen from num_envs. Every shape computes
+ * bit-identical results; the setter exists for tuning runs and for the parity tests that cover all of
+ * them. Changes vss_step_granularity(). Host-side state of the handle. */
+VSS_API int vss_set_step_warps_per_tile(vss_handle h, int warps);
+VSS_API int vss_step_warps_per_tile(vss_handle h);
 VSS_API int vss_set_step_range(vss_handle h, int64_t first_field, int64_t num_fields);
 
 /* State access for parity tests and checkpointing: copies the SoA state

@@ -55,6 +55,11 @@ constexpr int TILE_STATE_WORDS = SM_WORDS * LDS;  // the staged columns of one 3
 // of 1 byte (the per-field contact tasks, 32 x 4 bytes, reuse the same space in an earlier phase)
 constexpr int QUEUE_WORDS = 104;
 constexpr int TILE_WORDS = TILE_STATE_WORDS + QUEUE_WORDS;  // shared-memory words per warp
+// k_step_cta (one tile shared by up to MAX_WPT warps): the staged columns + one scratch word per warp
+// and field (the warp's share of the broadphase candidate mask)
+constexpr int MAX_WPT = 8;
+constexpr int W_SCR = SM_WORDS;
+constexpr int TILE_CTA_WORDS = (SM_WORDS + MAX_WPT) * LDS;
 constexpr int F4_PER_FIELD = VSS_OBS_PER_FIELD / 4;  // 78 float4 per (2,3,52) observation
 constexpr int F4_PER_ROW = VSS_NUM_OBS / 4;          // 13
 constexpr int RESET_MAX_ATTEMPTS = 64;
@@ -543,63 +548,86 @@ VSS_HD void sincos_small(float a, float& sa, float& ca) {
   sa = sinf(a); ca = cosf(a);
 #endif
 }
+// A. wheel drive + integration of robot r
+VSS_HD void integrate_robot(float* S, int r, const DevParams& P) {
+  float* b = S + (4 + 9 * r) * LDS;
+  float x = b[0], y = b[LDS], vx = b[2 * LDS], vy = b[3 * LDS], c = b[4 * LDS], s = b[5 * LDS];
+  float w = b[6 * LDS];
+  const float al = b[7 * LDS], ar = b[8 * LDS];
+  float v = vx * c + vy * s, u = -vx * s + vy * c;
+  // torque = k_imp (42 a - wheel speed), wheel speeds (v -+ w b) / r_w: the constants are folded
+  const float tv = P.k_v * v, tw = P.k_w * w;
+  const float tl = clampf(P.k_act * al - tv + tw, -P.tmax, P.tmax);
+  const float tr = clampf(P.k_act * ar - tv - tw, -P.tmax, P.tmax);
+  v += clampf((tl + tr) * P.fv, -P.dv_max, P.dv_max);
+  w += (tr - tl) * P.fw;
+  u -= clampf(u, -P.du_max, P.du_max);
+  vx = v * c - u * s; vy = v * s + u * c;
+  x += vx * P.h; y += vy * P.h;
+  float sa, ca;
+  sincos_small(w * P.h, sa, ca);
+  const float c2 = c * ca - s * sa, s2 = s * ca + c * sa;
+  // |(c2,s2)|^2 = 1 + O(1e-7): one Newton step of 1/sqrt around 1 renormalises to below 1e-13
+  const float inv = 1.5f - 0.5f * (c2 * c2 + s2 * s2);
+  b[0] = x; b[LDS] = y; b[2 * LDS] = vx; b[3 * LDS] = vy; b[4 * LDS] = c2 * inv; b[5 * LDS] = s2 * inv;
+  b[6 * LDS] = w;
+}
+// B. ball: exponential rolling drag
+VSS_HD void integrate_ball(float* S, const DevParams& P) {
+  const float vx = S[2 * LDS] * P.ball_decay, vy = S[3 * LDS] * P.ball_decay;
+  S[2 * LDS] = vx; S[3 * LDS] = vy;
+  S[0] += vx * P.h; S[LDS] += vy * P.h;
+}
+// C. broadphase of pair q (0-5: ball-robot q; 6-20: robot pairs in lexicographic order): the bit of the
+// candidate mask, from the post-integration positions.
+VSS_HD uint32_t broadphase_pair(const float* S, int q, const DevParams& P) {
+  float ax, ay, bx, by, reach2;
+  if (q < 6) {
+    ax = S[0]; ay = S[LDS]; bx = S[(4 + 9 * q) * LDS]; by = S[(5 + 9 * q) * LDS]; reach2 = P.br_reach2;
+  } else {
+    // lexicographic pair index -> (i, j): 3 bits each
+    const uint64_t PI = (1ull << 15) | (1ull << 18) | (1ull << 21) | (1ull << 24) | (2ull << 27) | (2ull << 30) |
+                        (2ull << 33) | (3ull << 36) | (3ull << 39) | (4ull << 42);
+    const uint64_t PJ = (1ull << 0) | (2ull << 3) | (3ull << 6) | (4ull << 9) | (5ull << 12) | (2ull << 15) |
+                        (3ull << 18) | (4ull << 21) | (5ull << 24) | (3ull << 27) | (4ull << 30) | (5ull << 33) |
+                        (4ull << 36) | (5ull << 39) | (5ull << 42);
+    const int p = q - 6, i = (int)((PI >> (3 * p)) & 7), j = (int)((PJ >> (3 * p)) & 7);
+    ax = S[(4 + 9 * i) * LDS]; ay = S[(5 + 9 * i) * LDS]; bx = S[(4 + 9 * j) * LDS]; by = S[(5 + 9 * j) * LDS];
+    reach2 = P.rr_reach2;
+  }
+  const float dx = ax - bx, dy = ay - by;
+  return dx * dx + dy * dy < reach2 ? 1u << q : 0u;
+}
+// The whole candidate mask of one field: bits 0-5 ball-robot r, bits 6-20 robot pairs.
+VSS_HD uint32_t broadphase_lane(const float* S, const DevParams& P) {
+  uint32_t mask = 0;
+  const float bx = S[0], by = S[LDS];
+  float rx[6], ry[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) { rx[r] = S[(4 + 9 * r) * LDS]; ry[r] = S[(5 + 9 * r) * LDS]; }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const float dx = bx - rx[r], dy = by - ry[r];
+    if (dx * dx + dy * dy < P.br_reach2) mask |= 1u << r;
+  }
+  int bit = 6;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) {
+      const float dx = rx[i] - rx[j], dy = ry[i] - ry[j];
+      if (dx * dx + dy * dy < P.rr_reach2) mask |= 1u << bit;
+      ++bit;
+    }
+  return mask;
+}
 // Phases A-B of a substep for one field plus the broadphase of phase C. Returns the 21-bit
 // candidate mask: bits 0-5 ball-robot r, bits 6-20 robot pairs in lexicographic order.
 VSS_HD uint32_t substep_integrate_lane(float* S, const DevParams& P) {
-  // A. wheel drive + integration
 #pragma unroll(INTEG_UNROLL)
-  for (int r = 0; r < 6; ++r) {
-    float* b = S + (4 + 9 * r) * LDS;
-    float x = b[0], y = b[LDS], vx = b[2 * LDS], vy = b[3 * LDS], c = b[4 * LDS], s = b[5 * LDS];
-    float w = b[6 * LDS];
-    const float al = b[7 * LDS], ar = b[8 * LDS];
-    float v = vx * c + vy * s, u = -vx * s + vy * c;
-    // torque = k_imp (42 a - wheel speed), wheel speeds (v -+ w b) / r_w: the constants are folded
-    const float tv = P.k_v * v, tw = P.k_w * w;
-    const float tl = clampf(P.k_act * al - tv + tw, -P.tmax, P.tmax);
-    const float tr = clampf(P.k_act * ar - tv - tw, -P.tmax, P.tmax);
-    v += clampf((tl + tr) * P.fv, -P.dv_max, P.dv_max);
-    w += (tr - tl) * P.fw;
-    u -= clampf(u, -P.du_max, P.du_max);
-    vx = v * c - u * s; vy = v * s + u * c;
-    x += vx * P.h; y += vy * P.h;
-    float sa, ca;
-    sincos_small(w * P.h, sa, ca);
-    const float c2 = c * ca - s * sa, s2 = s * ca + c * sa;
-    // |(c2,s2)|^2 = 1 + O(1e-7): one Newton step of 1/sqrt around 1 renormalises to below 1e-13
-    const float inv = 1.5f - 0.5f * (c2 * c2 + s2 * s2);
-    b[0] = x; b[LDS] = y; b[2 * LDS] = vx; b[3 * LDS] = vy; b[4 * LDS] = c2 * inv; b[5 * LDS] = s2 * inv;
-    b[6 * LDS] = w;
-  }
-  // B. ball: exponential rolling drag
-  {
-    const float vx = S[2 * LDS] * P.ball_decay, vy = S[3 * LDS] * P.ball_decay;
-    S[2 * LDS] = vx; S[3 * LDS] = vy;
-    S[0] += vx * P.h; S[LDS] += vy * P.h;
-  }
-  // C. broadphase once, then flagged pairs in fixed order
-  uint32_t mask = 0;
-  {
-    const float bx = S[0], by = S[LDS];
-    float rx[6], ry[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) { rx[r] = S[(4 + 9 * r) * LDS]; ry[r] = S[(5 + 9 * r) * LDS]; }
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      const float dx = bx - rx[r], dy = by - ry[r];
-      if (dx * dx + dy * dy < P.br_reach2) mask |= 1u << r;
-    }
-    int bit = 6;
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = i + 1; j < 6; ++j) {
-        const float dx = rx[i] - rx[j], dy = ry[i] - ry[j];
-        if (dx * dx + dy * dy < P.rr_reach2) mask |= 1u << bit;
-        ++bit;
-      }
-  }
-  return mask;
+  for (int r = 0; r < 6; ++r) integrate_robot(S, r, P);
+  integrate_ball(S, P);
+  return broadphase_lane(S, P);  // C. broadphase once, then flagged pairs in fixed order
 }
 
 // Narrow phase + impulses of the flagged pairs of one field, in fixed order. Touches only that
@@ -744,23 +772,25 @@ VSS_HD_COLD void reset_lane(float* S, const DevParams& P, const RngKey& key) {
 }
 
 // ---- OU noise on the 12 action slots of one field: envs/wrappers.py:5-19 -------------------
-VSS_HD void ou_lane(float a[VSS_ACT_PER_FIELD], const DevParams& P, const RngKey& key, uint32_t step) {
+// Philox block b of the step's OU stream drives slots 4b .. 4b+3 (robots 2b and 2b+1).
+VSS_HD void ou_block(float a4[4], const DevParams& P, const RngKey& key, uint32_t step, uint32_t b) {
+  const U4 g = rng_block(key, step, STREAM_OU, b);
+  const uint32_t u[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-  for (uint32_t b = 0; b < 3; ++b) {
-    const U4 g = rng_block(key, step, STREAM_OU, b);
-    const uint32_t u[4] = {g.x, g.y, g.z, g.w};
+  for (int h = 0; h < 2; ++h) {
+    const float rad = fsqrt(fmul(-2.0f, logf(u01_open(u[2 * h]))));
+    const float ang = fmul(6.283185307179586f, u01(u[2 * h + 1]));
+    const float z[2] = {fmul(rad, cosf(ang)), fmul(rad, sinf(ang))};
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float rad = fsqrt(fmul(-2.0f, logf(u01_open(u[2 * h]))));
-      const float ang = fmul(6.283185307179586f, u01(u[2 * h + 1]));
-      const float z[2] = {fmul(rad, cosf(ang)), fmul(rad, sinf(ang))};
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float& v = a[4 * b + 2 * h + c];
-        v = clampf(fadd(fsub(v, fmul(P.ou_theta, v)), fmul(P.ou_sigma, z[c])), -1.0f, 1.0f);
-      }
+    for (int c = 0; c < 2; ++c) {
+      float& v = a4[2 * h + c];
+      v = clampf(fadd(fsub(v, fmul(P.ou_theta, v)), fmul(P.ou_sigma, z[c])), -1.0f, 1.0f);
     }
   }
+}
+VSS_HD void ou_lane(float a[VSS_ACT_PER_FIELD], const DevParams& P, const RngKey& key, uint32_t step) {
+#pragma unroll
+  for (uint32_t b = 0; b < 3; ++b) ou_block(a + 4 * b, P, key, step, b);
 }
 
 
@@ -902,6 +932,52 @@ VSS_HD void lane_phase1a(float* S, long long env, const StepArgs& a, const DevPa
   }
 }
 
+// ---- the same phase 1a in pieces, for the kernel that spreads one tile over several warps -------
+// (k_step_cta: warp j owns bodies j, j+W, ...; body 0-5 = robot, 6 = ball). Together the pieces do
+// exactly what lane_phase1a does, word for word.
+VSS_HD void load_state_words(float* S, const float* state, long long ld, long long env, int w0, int wstep) {
+  const float* src = state + env;
+  for (int w = w0; w < VSS_STATE_WORDS; w += wstep) S[w * LDS] = ldg(src + (long long)w * ld);
+}
+VSS_HD void store_state_words(const float* S, float* state, long long ld, long long env, int w0, int wstep) {
+  float* dst = state + env;
+  for (int w = w0; w < VSS_STATE_WORDS; w += wstep) dst[(long long)w * ld] = S[w * LDS];
+}
+// Action slots 4b .. 4b+3 of the field (robots 2b, 2b+1): load, OU noise + policy overwrite (views),
+// write-back of the view's buffer, clamp into the state (vss.py:180-187; wrappers.py:102-103).
+template <int VIEW>
+VSS_HD void actions_block(float* S, long long env, const StepArgs& a, const DevParams& P, const RngKey& key, int b) {
+  float* ab = const_cast<float*>(VIEW == VIEW_FULL ? a.actions : a.action_buf) + env * VSS_ACT_PER_FIELD + 4 * b;
+  const F4 v = ld4(ab);
+  float act[4] = {v.x, v.y, v.z, v.w};
+  if (VIEW != VIEW_FULL) {
+    ou_block(act, P, key, step_index(a), (uint32_t)b);
+    if (VIEW == VSS_VIEW_SA) {
+      if (b == 0) { act[0] = a.policy_action[2 * env]; act[1] = a.policy_action[2 * env + 1]; }
+    } else {  // cma (N,6) and dma (3N,2): the same 6 contiguous floats per field
+      for (int q = 4 * b; q < 6 && q < 4 * b + 4; ++q) act[q - 4 * b] = a.policy_action[6 * env + q];
+    }
+    st4(ab, F4{act[0], act[1], act[2], act[3]});
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = 2 * b + k;
+    S[(11 + 9 * r) * LDS] = clampf(act[2 * k], -1.0f, 1.0f);
+    S[(12 + 9 * r) * LDS] = clampf(act[2 * k + 1], -1.0f, 1.0f);
+  }
+}
+// prev_* clone of one body (vss.py:219-220): ball potential (body 6) or robot-ball distance
+VSS_HD void prev_term_body(float* S, int body, const DevParams& P) {
+  const float pbx = S[0], pby = S[LDS];
+  if (body == 6) S[W_PREV * LDS] = ball_potential(pbx, pby, P.HL);
+  else S[(W_PREV + 1 + body) * LDS] = norm2(fsub(S[(4 + 9 * body) * LDS], pbx), fsub(S[(5 + 9 * body) * LDS], pby));
+}
+// Walls of one body after the pair contacts (phases D / E), in place
+VSS_HD void walls_body(float* S, int body, const DevParams& P) {
+  if (body == 6) { if (ball_near_walls(S, P)) ball_walls_task(S, P); }
+  else if (robot_near_walls(S, body, P)) robot_walls_task(S, body, P);
+}
+
 // Parity hook: take the post-physics state from `inject` instead of simulating.
 VSS_HD void lane_inject(float* S, long long env, const StepArgs& a) {
   const float* inj = a.inject + env;
@@ -1002,17 +1078,18 @@ VSS_HD int lane_phase1d(float* S, long long env, const StepArgs& a, const DevPar
 }
 
 // Phase 5: state out (+ zero the view's action buffer row of a done field, wrappers.py:105-107)
+VSS_HD void zero_action_row(long long env, const StepArgs& a) {
+  float* ap = a.action_buf + env * VSS_ACT_PER_FIELD;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const F4 v = ld4(ap + 4 * q);  // `*= 0` keeps the sign of zero
+    st4(ap + 4 * q, F4{fmul(v.x, 0.0f), fmul(v.y, 0.0f), fmul(v.z, 0.0f), fmul(v.w, 0.0f)});
+  }
+}
 template <int VIEW>
 VSS_HD void lane_phase5(const float* S, long long env, const StepArgs& a, bool done) {
   store_state(S, a.state, a.ld, env);
-  if (VIEW != VIEW_FULL && done) {
-    float* ap = a.action_buf + env * VSS_ACT_PER_FIELD;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const F4 v = ld4(ap + 4 * q);  // `*= 0` keeps the sign of zero
-      st4(ap + 4 * q, F4{fmul(v.x, 0.0f), fmul(v.y, 0.0f), fmul(v.z, 0.0f), fmul(v.w, 0.0f)});
-    }
-  }
+  if (VIEW != VIEW_FULL && done) zero_action_row(env, a);
 }
 
 // Cooperative, coalesced observation write of one tile (all 32 lanes call it).
@@ -1024,11 +1101,13 @@ VSS_HD int bf16_pad_offset(int f) { const int row = f / F4_PER_ROW; return row *
 constexpr int PACKED_ROW_ELEMS = VSS_PACKED_ROW_BYTES / 2;
 VSS_HD int packed_offset(int f) { const int row = f / F4_PER_ROW; return row * PACKED_ROW_ELEMS + (f - row * F4_PER_ROW) * 4; }
 
+// (part, parts): this caller is warp `part` of `parts` warps that share the tile (k_step_cta); 0, 1 = alone.
 VSS_HD void write_obs_tile(const float* T, const uint32_t* tab, int lane, int valid, int per_field, float* tob,
-                           float* ob, uint32_t skip_mask, void* obh = nullptr, void* pk = nullptr) {
+                           float* ob, uint32_t skip_mask, void* obh = nullptr, void* pk = nullptr, int part = 0,
+                           int parts = 1) {
   const int total = valid * per_field;
 #pragma unroll 4
-  for (int f = lane; f < total; f += 32) {
+  for (int f = lane + 32 * part; f < total; f += 32 * parts) {
     const int e = f / per_field, j = f - e * per_field;
     const F4 v = obs_gather(T, tab[j], e);
     if (tob) st4(tob + 4 * f, v);
@@ -1048,9 +1127,10 @@ VSS_HD void write_obs_tile(const float* T, const uint32_t* tab, int lane, int va
 // warp-wide store of a full slot covers 512 contiguous bytes. The slots left over after the full
 // ones (78 = 2 x 32 + 14, 39 = 32 + 7) are packed G fields to a store instruction: lane group g
 // (16 or 8 lanes wide) writes the tail of field e + g.
-template <int PER_FIELD>
+template <int PER_FIELD, bool MULTI = false>
 VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, int valid, float* tob, float* ob,
-                                uint32_t skip_mask, void* obh = nullptr, void* pk = nullptr) {
+                                uint32_t skip_mask, void* obh = nullptr, void* pk = nullptr, int part = 0,
+                                int parts = 1) {
   constexpr int FULL = PER_FIELD / 32, TAIL = PER_FIELD - 32 * FULL;
   constexpr int TW = TAIL <= 1 ? 1 : TAIL <= 2 ? 2 : TAIL <= 4 ? 4 : TAIL <= 8 ? 8 : TAIL <= 16 ? 16 : 32;
   constexpr int G = 32 / TW, SLOTS = FULL + (TAIL ? 1 : 0);
@@ -1069,41 +1149,51 @@ VSS_HD void write_obs_tile_rows(const float* T, const uint32_t* tab, int lane, i
       sgn[sl][c] = (by >> 7) << 31;
     }
   }
+  // MULTI (k_step_cta: `parts` warps share the tile): warp `part` takes the field groups part, part + parts,
+  // ... of GRP consecutive fields, so that the packed tail slots of a group stay with one warp.
+  constexpr int GRP = MULTI ? (TAIL ? G : 1) : 32;
+  const int e_first = MULTI ? part * GRP : 0, e_jump = MULTI ? parts * GRP : 32;
+#pragma unroll 1
+  for (int e0 = e_first; e0 < valid; e0 += e_jump) {
+    const int e1 = e0 + GRP < valid ? e0 + GRP : valid;
 #pragma unroll(OBS_UNROLL)
-  for (int e = 0; e < valid; ++e) {
-    const bool keep = !((skip_mask >> e) & 1u);
+    for (int e = e0; e < e1; ++e) {
+      const bool keep = !((skip_mask >> e) & 1u);
 #pragma unroll
-    for (int sl = 0; sl < FULL; ++sl) {
-      const F4 v{bitsf(fbits(T[off[sl][0] + e]) ^ sgn[sl][0]), bitsf(fbits(T[off[sl][1] + e]) ^ sgn[sl][1]),
-                 bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
-      const int idx = 4 * (e * PER_FIELD + lane + 32 * sl);
-      if (tob) st4_stream(tob + idx, v);
-      if (keep) {
-        st4_stream(ob + idx, v);
-        if (obh) st_bf16x4(obh, bf16_pad_offset(idx >> 2), v);
-        if (pk) st_bf16x4(pk, packed_offset(idx >> 2), v);
+      for (int sl = 0; sl < FULL; ++sl) {
+        const F4 v{bitsf(fbits(T[off[sl][0] + e]) ^ sgn[sl][0]), bitsf(fbits(T[off[sl][1] + e]) ^ sgn[sl][1]),
+                   bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
+        const int idx = 4 * (e * PER_FIELD + lane + 32 * sl);
+        if (tob) st4_stream(tob + idx, v);
+        if (keep) {
+          st4_stream(ob + idx, v);
+          if (obh) st_bf16x4(obh, bf16_pad_offset(idx >> 2), v);
+          if (pk) st_bf16x4(pk, packed_offset(idx >> 2), v);
+        }
       }
-    }
-    if (TAIL && (e % G) == 0 && tail_lane && e + sub < valid) {  // fields e .. e+G-1, one lane group each
-      constexpr int sl = SLOTS - 1;
-      const F4 v{bitsf(fbits(T[off[sl][0] + e]) ^ sgn[sl][0]), bitsf(fbits(T[off[sl][1] + e]) ^ sgn[sl][1]),
-                 bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
-      const int idx = 4 * ((e + sub) * PER_FIELD + jt);
-      if (tob) st4_stream(tob + idx, v);
-      if (!((skip_mask >> (e + sub)) & 1u)) {
-        st4_stream(ob + idx, v);
-        if (obh) st_bf16x4(obh, bf16_pad_offset(idx >> 2), v);
-        if (pk) st_bf16x4(pk, packed_offset(idx >> 2), v);
+      if (TAIL && (e % G) == 0 && tail_lane && e + sub < valid) {  // fields e .. e+G-1, one lane group each
+        constexpr int sl = SLOTS - 1;
+        const F4 v{bitsf(fbits(T[off[sl][0] + e]) ^ sgn[sl][0]), bitsf(fbits(T[off[sl][1] + e]) ^ sgn[sl][1]),
+                   bitsf(fbits(T[off[sl][2] + e]) ^ sgn[sl][2]), bitsf(fbits(T[off[sl][3] + e]) ^ sgn[sl][3])};
+        const int idx = 4 * ((e + sub) * PER_FIELD + jt);
+        if (tob) st4_stream(tob + idx, v);
+        if (!((skip_mask >> (e + sub)) & 1u)) {
+          st4_stream(ob + idx, v);
+          if (obh) st_bf16x4(obh, bf16_pad_offset(idx >> 2), v);
+          if (pk) st_bf16x4(pk, packed_offset(idx >> 2), v);
+        }
       }
     }
   }
 }
 
 VSS_HD void write_obs_fields(const float* T, const uint32_t* tab, int lane, int per_field, float* ob,
-                             uint32_t field_mask, void* obh = nullptr, void* pk = nullptr) {
+                             uint32_t field_mask, void* obh = nullptr, void* pk = nullptr, int part = 0, int parts = 1) {
+  int k = 0;
   while (field_mask) {
     const int e = ffs32(field_mask) - 1;
     field_mask &= field_mask - 1;
+    if ((k++) % parts != part) continue;  // the k-th flagged field goes to warp k mod parts
     for (int j = lane; j < per_field; j += 32) {
       const F4 v = obs_gather(T, tab[j], e);
       st4(ob + 4 * (e * per_field + j), v);

@@ -170,6 +170,110 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
   if (VIEW != VIEW_FULL) step_done(a, ctr);
 }
 
+// ----------------------------------------------------------------------------------------
+// k_step_cta — the same step with ONE 32-field tile per CTA, shared by W = blockDim / 32 warps.
+// Small and medium batches leave SMs idle and are bound by the critical path of a tile (one warp
+// = one field per lane walks 6 robots + the ball one after the other: ~12 000 dependent instructions,
+// 31-37 us). Here warp j owns the bodies j, j + W, ... (0-5 = robots, 6 = ball) of all 32 fields:
+// every dense phase still runs with 32 active lanes, lane = field, conflict-free on the same staged
+// columns, but 7 bodies advance side by side. Phases that couple bodies are separated by CTA
+// barriers: integrate | broadphase (pairs dealt round-robin to the warps, partial masks in the
+// scratch words) | pair contacts (field l by warp l mod W: the sequential impulse order inside a
+// field is unchanged) | walls (per body, in place). The cooperative parts — state load / store by
+// words, observation rows by field groups, the masked resets — are dealt to the warps the same way.
+// Results are bit-identical to k_step: the same per-body code in the same order per field.
+// ----------------------------------------------------------------------------------------
+template <int VIEW, bool INJECT>
+__global__ void __launch_bounds__(32 * MAX_WPT)
+k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) {
+  extern __shared__ __align__(16) float smem[];
+  uint32_t* tab = reinterpret_cast<uint32_t*>(smem);
+  for (int i = threadIdx.x; i < F4_PER_FIELD; i += blockDim.x) tab[i] = c_obs_table.v[i];
+  float* T = smem + TAB_WORDS;
+  uint32_t* ctr = reinterpret_cast<uint32_t*>(T + TILE_CTA_WORDS);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  if (threadIdx.x == 0) ctr[3] = 0u;  // warps of this CTA that have finished
+  const long long env0 = a.env_begin + (long long)blockIdx.x * 32;
+  float* S = T + lane;
+  const long long env = env0 + lane;
+  const bool active = env < a.n;
+  const int valid = (int)max(0LL, min(32LL, a.n - env0));
+  constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
+  const RngKey key = make_key(a, env);
+  // 1a. state in (words dealt to the warps), then actions / OU noise per Philox block, progress restart,
+  //     prev_* clones per body
+  if (active) load_state_words(S, a.state, a.ld, env, warp, W);
+  __syncthreads();
+  if (active) {
+    for (int b = warp; b < 3; b += W) actions_block<VIEW>(S, env, a, P, key, b);
+    if (warp == 3 % W && a.reset_buf[env] != 0) S[VSS_W_PROGRESS * LDS] = bitsf(0u);  // vss.py:182-183
+    for (int b = warp; b < 7; b += W) prev_term_body(S, b, P);
+  }
+  __syncthreads();
+  // physics (replaces gym.simulate)
+  if (INJECT) {
+    if (warp == 0 && active) lane_inject(S, env, a);
+  } else {
+#pragma unroll 1
+    for (int it = 0; it < P.substeps; ++it) {
+      if (active)
+        for (int b = warp; b < 7; b += W) { if (b < 6) integrate_robot(S, b, P); else integrate_ball(S, P); }
+      __syncthreads();
+      {
+        uint32_t m = 0u;
+        if (active)
+          for (int q = warp; q < 21; q += W) m |= broadphase_pair(S, q, P);
+        S[(W_SCR + warp) * LDS] = bitsf(m);
+      }
+      __syncthreads();
+      if (active && lane % W == warp) {
+        uint32_t m = 0u;
+        for (int j = 0; j < W; ++j) m |= fbits(S[(W_SCR + j) * LDS]);
+        if (m) contacts_task(S, m, P);
+      }
+      __syncthreads();
+      if (active)
+        for (int b = warp; b < 7; b += W) walls_body(S, b, P);  // (the next integrate of a body is by the same thread)
+    }
+  }
+  __syncthreads();
+  // 1d. post_physics_step per field (warp 0): progress, rewards, dones, per-field outputs
+  if (warp == 0) {
+    int code = LANE_RUNNING;
+    if (active) code = lane_phase1d<VIEW>(S, env, a, P, key);
+    const uint32_t dm = __ballot_sync(0xffffffffu, code == LANE_DONE);      // needs the masked reset of phase 3
+    const uint32_t em = __ballot_sync(0xffffffffu, code != LANE_RUNNING);  // episode ended (done or sanitised)
+    if (lane == 0) { ctr[0] = dm; ctr[1] = em; }
+  }
+  __syncthreads();
+  const uint32_t done_mask = ctr[0], ended_mask = ctr[1];
+  // 2. terminal observation + observation of the fields that keep their state (vss.py:195-196)
+  float* ob = a.obs + env0 * (PER_FIELD * 4);
+  float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
+  void* obh = (VIEW != VIEW_FULL && a.obs_bf16)
+                  ? static_cast<void*>(static_cast<unsigned short*>(a.obs_bf16) + env0 * (ViewShape<VIEW>::AGENTS * 64))
+                  : nullptr;
+  void* pk = (VIEW != VIEW_FULL && a.packed)
+                 ? static_cast<void*>(static_cast<char*>(a.packed) + env0 * (ViewShape<VIEW>::AGENTS * VSS_PACKED_ROW_BYTES))
+                 : nullptr;
+  if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD, true>(T, tab, lane, valid, tob, ob, done_mask, obh, pk, warp, W);
+  else write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, done_mask, obh, pk, warp, W);
+  __syncthreads();
+  // 3. masked reset (vss.py:202, 267-333): the k-th done field by warp k mod W
+  if ((done_mask >> lane) & 1u) {
+    const int k = __popc(done_mask & ((1u << lane) - 1u));
+    if (k % W == warp) reset_lane(S, P, key);
+  }
+  __syncthreads();
+  // 4. observation of the fields that were reset (vss.py:203); 5. state out
+  write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask, obh, pk, warp, W);
+  if (active) store_state_words(S, a.state, a.ld, env, warp, W);
+  if (VIEW != VIEW_FULL) {
+    if (warp == 0 && ((ended_mask >> lane) & 1u)) zero_action_row(env, a);  // wrappers.py:105-107
+    step_done(a, ctr);
+  }
+}
+
 // reset_dones() + compute_observations(): vss.py:72-73, 267-333, 205-216
 __global__ void __launch_bounds__(384)
 k_reset_dones(float* state, long long n, long long ld, unsigned long long goff, uint32_t seed_lo,
@@ -292,6 +396,7 @@ struct vss_engine {
   float* state;
   void* aux_obs_bf16; float* aux_done_f; float* aux_timeout_f;  // vss_set_step_aux
   void* packed_rows;                                            // vss_set_step_packed
+  int wpt_override;                                             // vss_set_step_warps_per_tile (0 = automatic)
   int64_t range_first, range_count;                             // vss_set_step_range (count 0 = all fields)
 };
 
@@ -326,15 +431,30 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 // First-wave stagger (profiles/r01_g_*.md): 5 us per resident CTA of an SM, measured best of 0-12 us
 // at 2^20 fields (675 -> 652 us per step); only for the barrier-synchronised shape and only when the
 // launch is longer than one wave of 148 x 6 CTAs.
+// `wpt` (warps per tile) > 1 selects k_step_cta: one 32-field tile per CTA shared by wpt warps (bodies dealt
+// to the warps). It shortens a tile's critical path ~wpt-fold and is used while the batch cannot fill the
+// SMs with one warp per tile: 7 warps (one per body) up to 512 tiles, 4 up to 888, 2 up to 2 368.
 struct LaunchShape {
-  int wpb, fpw, stagger_ns;
+  int wpb, fpw, stagger_ns, wpt;
   bool sync;
   unsigned grid;  // CTAs of a whole-engine launch
   size_t smem;
 };
 
-static LaunchShape launch_shape(int64_t n, bool step_kernel = true) {
+static int auto_wpt(int64_t n) {
+  const int64_t tiles = (n + 31) / 32;
+  return tiles <= 512 ? 7 : (tiles <= 888 ? 4 : (tiles <= 2368 ? 2 : 1));
+}
+
+static LaunchShape launch_shape(int64_t n, bool step_kernel = true, int wpt_override = 0) {
   LaunchShape s;
+  s.wpt = !step_kernel ? 1 : (wpt_override > 0 ? wpt_override : auto_wpt(n));
+  if (s.wpt > 1) {
+    s.wpb = s.wpt; s.fpw = 32; s.sync = true; s.stagger_ns = 0;
+    s.grid = (unsigned)((n + 31) / 32);
+    s.smem = sizeof(float) * (TAB_WORDS + TILE_CTA_WORDS + CTR_WORDS);
+    return s;
+  }
   s.fpw = !step_kernel ? 32 : (n < 148 * 40 ? 8 : (n < 148 * 192 ? 16 : 32));
   const int64_t tiles = (n + s.fpw - 1) / s.fpw;
   s.wpb = tiles < 148 * 2 ? 1 : (tiles < 148 * 20 ? 2 : 4);
@@ -362,19 +482,20 @@ static StepArgs base_args(vss_handle h) {
 
 template <int VIEW, bool INJECT>
 static int launch_step(vss_handle h, StepArgs a, void* stream) {
-  const LaunchShape ls = launch_shape(h->n);
+  const LaunchShape ls = launch_shape(h->n, true, h->wpt_override);
   a.fpw = ls.fpw; a.stagger_ns = ls.stagger_ns;
   a.grid = ls.grid;  // a step is complete when this many CTAs have finished, over all its range launches
   unsigned grid = ls.grid;
   if (h->range_count > 0) {  // vss_set_step_range: this launch covers [first, first + count) — same CTA shape, fewer CTAs
-    const int64_t per_cta = (int64_t)ls.wpb * ls.fpw;
+    const int64_t per_cta = ls.wpt > 1 ? 32 : (int64_t)ls.wpb * ls.fpw;
     if (h->range_first % per_cta != 0 || (h->range_count % per_cta != 0 && h->range_first + h->range_count != h->n))
       return fail(VSS_E_INVALID, "step range: first / count must be multiples of vss_step_granularity()");
     a.env_begin = h->range_first;
     a.n = h->range_first + h->range_count;
     grid = (unsigned)((h->range_count + per_cta - 1) / per_cta);
   }
-  if (ls.sync) k_step<VIEW, INJECT, true><<<grid, ls.wpb * 32, ls.smem, (cudaStream_t)stream>>>(a, h->dp);
+  if (ls.wpt > 1) k_step_cta<VIEW, INJECT><<<grid, ls.wpt * 32, ls.smem, (cudaStream_t)stream>>>(a, h->dp);
+  else if (ls.sync) k_step<VIEW, INJECT, true><<<grid, ls.wpb * 32, ls.smem, (cudaStream_t)stream>>>(a, h->dp);
   else k_step<VIEW, INJECT, false><<<grid, ls.wpb * 32, ls.smem, (cudaStream_t)stream>>>(a, h->dp);
   VSS_CUDA(cudaGetLastError());
   return VSS_OK;
@@ -426,7 +547,7 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
   if (!h) return fail(VSS_E_NOMEM, "vss_create: host allocation failed");
   h->device = device; h->n = num_envs; h->ld = (num_envs + 31) / 32 * 32; h->goff = global_env_offset;
   h->aux_obs_bf16 = nullptr; h->aux_done_f = nullptr; h->aux_timeout_f = nullptr; h->packed_rows = nullptr;
-  h->range_first = 0; h->range_count = 0;
+  h->range_first = 0; h->range_count = 0; h->wpt_override = 0;
   h->seed = seed; h->d_step = nullptr; h->params = *p; h->dp = derive_params(*p); h->state = nullptr;
   const size_t bytes = sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld;
   e = cudaMalloc(&h->state, bytes);
@@ -552,10 +673,20 @@ VSS_API int vss_set_step_packed(vss_handle h, void* rows) {
   return VSS_OK;
 }
 
+VSS_API int vss_set_step_warps_per_tile(vss_handle h, int warps) {
+  if (!h) return fail(VSS_E_INVALID, "vss_set_step_warps_per_tile: null handle");
+  if (warps < 0 || warps > MAX_WPT) return fail(VSS_E_INVALID, "vss_set_step_warps_per_tile: 0 (automatic) .. 8");
+  h->wpt_override = warps;
+  return VSS_OK;
+}
+VSS_API int vss_step_warps_per_tile(vss_handle h) {
+  return h ? launch_shape(h->n, true, h->wpt_override).wpt : 0;
+}
+
 VSS_API int64_t vss_step_granularity(vss_handle h) {
   if (!h) return 0;
-  const LaunchShape ls = launch_shape(h->n);
-  return (int64_t)ls.wpb * ls.fpw;
+  const LaunchShape ls = launch_shape(h->n, true, h->wpt_override);
+  return ls.wpt > 1 ? 32 : (int64_t)ls.wpb * ls.fpw;
 }
 
 VSS_API int vss_set_step_range(vss_handle h, int64_t first_field, int64_t num_fields) {

@@ -87,6 +87,15 @@ class Engine:
     def step_granularity(self):
         return int(self.lib.vss_step_granularity(self._h))
 
+    @property
+    def warps_per_tile(self):
+        """Launch shape of the step kernels (include/vss_b200.h: vss_set_step_warps_per_tile); 0 on write = automatic."""
+        return int(self.lib.vss_step_warps_per_tile(self._h))
+
+    @warps_per_tile.setter
+    def warps_per_tile(self, w):
+        check(self.lib.vss_set_step_warps_per_tile(self._h, int(w)))
+
     def set_step_range(self, first_field=0, num_fields=0):
         check(self.lib.vss_set_step_range(self._h, int(first_field), int(num_fields)))
 

@@ -38,6 +38,8 @@ class EmuBackend:
             cls._lib = C.CDLL(os.path.join(d, "libvss_emu.so"))
         return cls._lib
 
+    wpt = 1   # warps per tile: 1 = the k_step structure, 2..8 = the k_step_cta structure
+
     def __init__(self, n, seed=0, goff=0, params=None):
         from oracle import vss_oracle as orc
         self.n, self.seed, self.goff = n, seed, goff
@@ -72,7 +74,7 @@ class EmuBackend:
                                  C.c_uint(self.step_count & 0xFFFFFFFF), _p(actions), _p(inject), _p(reset_buf),
                                  _p(obs), _p(term_obs), _p(rew), _p(timeout), _p(progress_f), _p(policy_action),
                                  _p(action_buf), _p(reward_v), _p(done_v), _p(ep_ret), _p(ep_len), _p(ret_ret),
-                                 _p(ret_len), _p(packed))
+                                 _p(ret_len), _p(packed), C.c_int(self.wpt))
         assert rc == 0
         self.step_count += 1
 
@@ -112,6 +114,7 @@ class GpuBackend:
     """libvss_b200.so through the product's Engine wrapper (C-ABI) on cuda:0."""
 
     name = "gpu"
+    wpt = None   # None = the library's automatic launch shape; 1..8 forces warps per tile
 
     def __init__(self, n, seed=0, goff=0, params=None):
         import torch
@@ -124,6 +127,8 @@ class GpuBackend:
                 setattr(p, k, getattr(params, k))
         self.params = p
         self.eng = R.Engine(n, "cuda:0", seed=seed, global_env_offset=goff, params=p)
+        if self.wpt is not None:
+            self.eng.warps_per_tile = self.wpt
         self.ld = self.eng.ld
         self.dev = torch.device("cuda:0")
 
@@ -199,3 +204,8 @@ class GpuBackend:
             ep_len[...] = el.cpu().numpy()
             out["ret_ret"], out["ret_len"] = rr.cpu().numpy(), rl.cpu().numpy()
         return out
+
+
+def with_wpt(Backend, wpt):
+    """The same backend with a forced launch shape (warps per tile)."""
+    return type(f"{Backend.__name__}W{wpt}", (Backend,), {"wpt": wpt})

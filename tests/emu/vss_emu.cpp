@@ -62,6 +62,76 @@ static void emu_step_t(const StepArgs& a, const DevParams& P) {
   }
 }
 
+// Mirror of k_step_cta (one tile shared by W warps, bodies dealt to the warps): the phases below are
+// the kernel's, each CTA barrier becomes the end of a loop over (warp, lane).
+template <int VIEW, bool INJECT>
+static void emu_step_cta_t(const StepArgs& a, const DevParams& P, int W) {
+  constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
+  const long long tiles = (a.n + 31) / 32;
+#pragma omp parallel for schedule(static)
+  for (long long tile = 0; tile < tiles; ++tile) {
+    std::vector<float> Tbuf(TILE_CTA_WORDS, 0.0f);
+    float* T = Tbuf.data();
+    const long long env0 = tile * 32;
+    const int valid = (int)std::min(32LL, a.n - env0);
+#define EACH_THREAD for (int warp = 0; warp < W; ++warp) for (int lane = 0; lane < valid; ++lane)
+    EACH_THREAD load_state_words(T + lane, a.state, a.ld, env0 + lane, warp, W);
+    EACH_THREAD {
+      float* S = T + lane;
+      const long long env = env0 + lane;
+      const RngKey key = make_key(a, env);
+      for (int b = warp; b < 3; b += W) actions_block<VIEW>(S, env, a, P, key, b);
+      if (warp == 3 % W && a.reset_buf[env] != 0) S[VSS_W_PROGRESS * LDS] = bitsf(0u);
+      for (int b = warp; b < 7; b += W) prev_term_body(S, b, P);
+    }
+    if (INJECT) {
+      for (int lane = 0; lane < valid; ++lane) lane_inject(T + lane, env0 + lane, a);
+    } else {
+      for (int it = 0; it < P.substeps; ++it) {
+        EACH_THREAD for (int b = warp; b < 7; b += W) { if (b < 6) integrate_robot(T + lane, b, P); else integrate_ball(T + lane, P); }
+        EACH_THREAD {
+          uint32_t m = 0u;
+          for (int q = warp; q < 21; q += W) m |= broadphase_pair(T + lane, q, P);
+          T[(W_SCR + warp) * LDS + lane] = bitsf(m);
+        }
+        EACH_THREAD if (lane % W == warp) {
+          uint32_t m = 0u;
+          for (int j = 0; j < W; ++j) m |= fbits(T[(W_SCR + j) * LDS + lane]);
+          if (m) contacts_task(T + lane, m, P);
+        }
+        EACH_THREAD for (int b = warp; b < 7; b += W) walls_body(T + lane, b, P);
+      }
+    }
+    uint32_t done_mask = 0, ended_mask = 0;
+    for (int lane = 0; lane < valid; ++lane) {
+      const int code = lane_phase1d<VIEW>(T + lane, env0 + lane, a, P, make_key(a, env0 + lane));
+      if (code == LANE_DONE) done_mask |= 1u << lane;
+      if (code != LANE_RUNNING) ended_mask |= 1u << lane;
+    }
+    float* ob = a.obs + env0 * (PER_FIELD * 4);
+    float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
+    void* pk = (VIEW != VIEW_FULL && a.packed)
+                   ? static_cast<void*>(static_cast<char*>(a.packed) + env0 * (ViewShape<VIEW>::AGENTS * VSS_PACKED_ROW_BYTES))
+                   : nullptr;
+    for (int warp = 0; warp < W; ++warp)
+      for (int lane = 0; lane < 32; ++lane) {
+        if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD, true>(T, g_tab.v, lane, valid, tob, ob, done_mask, nullptr, pk, warp, W);
+        else write_obs_tile(T, g_tab.v, lane, valid, PER_FIELD, tob, ob, done_mask, nullptr, pk, warp, W);
+      }
+    EACH_THREAD if ((done_mask >> lane) & 1u) {
+      const int k = __builtin_popcount(done_mask & ((1u << lane) - 1u));
+      if (k % W == warp) reset_lane(T + lane, P, make_key(a, env0 + lane));
+    }
+    for (int warp = 0; warp < W; ++warp)
+      for (int lane = 0; lane < 32; ++lane) write_obs_fields(T, g_tab.v, lane, PER_FIELD, ob, done_mask, nullptr, pk, warp, W);
+    EACH_THREAD store_state_words(T + lane, a.state, a.ld, env0 + lane, warp, W);
+    if (VIEW != VIEW_FULL)
+      for (int lane = 0; lane < valid; ++lane)
+        if ((ended_mask >> lane) & 1u) zero_action_row(env0 + lane, a);
+#undef EACH_THREAD
+  }
+}
+
 extern "C" {
 
 __attribute__((visibility("default"))) int emu_step(
@@ -69,7 +139,7 @@ __attribute__((visibility("default"))) int emu_step(
     unsigned long long seed, unsigned int step, const float* actions, const float* inject, long long* reset_buf,
     float* obs, float* term_obs, float* rew, uint8_t* timeout, float* progress_f, const float* policy_action,
     float* action_buf, float* reward_v, long long* done_v, float* ep_ret, int* ep_len, float* ret_ret,
-    int* ret_len, void* packed) {
+    int* ret_len, void* packed, int wpt) {
   const DevParams P = derive_params(*p);
   StepArgs a;
   memset(&a, 0, sizeof(a));
@@ -80,6 +150,15 @@ __attribute__((visibility("default"))) int emu_step(
   a.rew = rew; a.timeout = timeout; a.progress_f = progress_f; a.policy_action = policy_action;
   a.action_buf = action_buf; a.reward_v = reward_v; a.done_v = done_v; a.ep_ret = ep_ret; a.ep_len = ep_len;
   a.ret_ret = ret_ret; a.ret_len = ret_len; a.packed = packed;
+  if (wpt > 1) {  // the k_step_cta structure
+    if (wpt > MAX_WPT) return -1;
+    if (view == VIEW_FULL) { if (inject) emu_step_cta_t<VIEW_FULL, true>(a, P, wpt); else emu_step_cta_t<VIEW_FULL, false>(a, P, wpt); }
+    else if (view == VSS_VIEW_SA) emu_step_cta_t<VSS_VIEW_SA, false>(a, P, wpt);
+    else if (view == VSS_VIEW_CMA) emu_step_cta_t<VSS_VIEW_CMA, false>(a, P, wpt);
+    else if (view == VSS_VIEW_DMA) emu_step_cta_t<VSS_VIEW_DMA, false>(a, P, wpt);
+    else return -1;
+    return 0;
+  }
   if (view == VIEW_FULL) { if (inject) emu_step_t<VIEW_FULL, true>(a, P); else emu_step_t<VIEW_FULL, false>(a, P); }
   else if (view == VSS_VIEW_SA) emu_step_t<VSS_VIEW_SA, false>(a, P);
   else if (view == VSS_VIEW_CMA) emu_step_t<VSS_VIEW_CMA, false>(a, P);

@@ -288,3 +288,54 @@ def test_ou_noise_moments(Gpu, view):
 def test_packed_host_rows(Gpu, view, n):
     """include/vss_b200.h vss_set_step_packed: 52 bf16 obs | f32 reward | u8 done | u8 timeout."""
     pc.check_packed_rows(Gpu, view, n=n, steps=4)
+
+
+# ---- launch shapes: k_step (one warp per tile) and k_step_cta (2..8 warps share a tile)
+def test_every_launch_shape_is_bit_identical(Gpu):
+    """include/vss_b200.h vss_set_step_warps_per_tile: every shape computes the same words (full contract
+    and the three views), on a size that is ragged against the 32-field tiles, over contact-heavy steps."""
+    from backends import with_wpt
+    n = 4097
+    shapes = [1, 2, 4, 7, 8]
+    bes = [with_wpt(Gpu, w)(n, seed=3, goff=9) for w in shapes]
+    assert [b.eng.warps_per_tile for b in bes] == shapes
+    rbs = [np.ones(n, np.int64) for _ in bes]
+    obs = [b.reset_dones(rb) for b, rb in zip(bes, rbs)]
+    for rb in rbs:
+        rb[:] = 0
+    for b in bes:
+        pc.stage_interesting_state(b, np.random.default_rng(5))
+    rng = np.random.default_rng(1)
+    o = obs[0]
+    for t in range(12):
+        act = pc.chase_actions(o, rng.uniform(-1.2, 1.2, (n, 2, 3, 2)))
+        outs = [b.step(act, rb) for b, rb in zip(bes, rbs)]
+        for w, x, rb in zip(shapes[1:], outs[1:], rbs[1:]):
+            for k in ("obs", "term_obs", "rew", "timeout", "progress_f"):
+                assert np.array_equal(outs[0][k].view(np.uint8), x[k].view(np.uint8)), (t, w, k)
+            assert np.array_equal(rbs[0], rb)
+        o = outs[0]["obs"]
+    for view in (orc.VIEW_SA, orc.VIEW_CMA, orc.VIEW_DMA):
+        nv, adim = (3 * n if view == orc.VIEW_DMA else n), (6 if view == orc.VIEW_CMA else 2)
+        abufs = [np.zeros((n, 2, 3, 2), np.float32) for _ in bes]
+        ers, els = [np.zeros((nv, 4), np.float32) for _ in bes], [np.zeros(nv, np.int32) for _ in bes]
+        for b in bes:
+            b.step_count = 0
+        for t in range(3):
+            pa = rng.uniform(-1.2, 1.2, (nv, adim)).astype(np.float32)
+            outs = [b.step_view(view, pa, ab, rb, er, el, packed=True) for b, ab, rb, er, el in zip(bes, abufs, rbs, ers, els)]
+            for w, x, ab in zip(shapes[1:], outs[1:], abufs[1:]):
+                for k in x:
+                    assert np.array_equal(outs[0][k].view(np.uint8), x[k].view(np.uint8)), (view, t, w, k)
+                assert np.array_equal(abufs[0].view(np.uint32), ab.view(np.uint32))
+        assert all(b.step_count == 3 for b in bes)
+
+
+@pytest.mark.parametrize("wpt,n", [(7, 4096), (4, 21845), (2, 65536), (8, 1000), (2, 131072)])
+def test_cta_launch_shapes_track_oracle(Gpu, wpt, n):
+    from backends import with_wpt
+    B = with_wpt(Gpu, wpt)
+    r = pc.check_rollout(B, n=n, steps=4, seed=n % 97)
+    assert r["dones"] > 0 and r["timeouts"] > 0 and r["goals"] > 0
+    assert pc.check_injected(B, n=min(n, 20000), steps=2) > 0
+    pc.check_views(B, orc.VIEW_DMA, n=min(n, 20000), steps=3)
