@@ -59,7 +59,8 @@ constexpr int TILE_WORDS = TILE_STATE_WORDS + QUEUE_WORDS;  // shared-memory wor
 // and field (the warp's share of the broadphase candidate mask)
 constexpr int MAX_WPT = 8;
 constexpr int W_SCR = SM_WORDS;
-constexpr int TILE_CTA_WORDS = (SM_WORDS + MAX_WPT) * LDS;
+constexpr int W_SHADOW = SM_WORDS + MAX_WPT;  // a second set of state columns: the helper warp's speculative resets
+constexpr int TILE_CTA_WORDS = (W_SHADOW + VSS_STATE_WORDS) * LDS;
 constexpr int F4_PER_FIELD = VSS_OBS_PER_FIELD / 4;  // 78 float4 per (2,3,52) observation
 constexpr int F4_PER_ROW = VSS_NUM_OBS / 4;          // 13
 constexpr int RESET_MAX_ATTEMPTS = 64;
@@ -581,22 +582,13 @@ VSS_HD void integrate_ball(float* S, const DevParams& P) {
 // C. broadphase of pair q (0-5: ball-robot q; 6-20: robot pairs in lexicographic order): the bit of the
 // candidate mask, from the post-integration positions.
 VSS_HD uint32_t broadphase_pair(const float* S, int q, const DevParams& P) {
-  float ax, ay, bx, by, reach2;
-  if (q < 6) {
-    ax = S[0]; ay = S[LDS]; bx = S[(4 + 9 * q) * LDS]; by = S[(5 + 9 * q) * LDS]; reach2 = P.br_reach2;
-  } else {
-    // lexicographic pair index -> (i, j): 3 bits each
-    const uint64_t PI = (1ull << 15) | (1ull << 18) | (1ull << 21) | (1ull << 24) | (2ull << 27) | (2ull << 30) |
-                        (2ull << 33) | (3ull << 36) | (3ull << 39) | (4ull << 42);
-    const uint64_t PJ = (1ull << 0) | (2ull << 3) | (3ull << 6) | (4ull << 9) | (5ull << 12) | (2ull << 15) |
-                        (3ull << 18) | (4ull << 21) | (5ull << 24) | (3ull << 27) | (4ull << 30) | (5ull << 33) |
-                        (4ull << 36) | (5ull << 39) | (5ull << 42);
-    const int p = q - 6, i = (int)((PI >> (3 * p)) & 7), j = (int)((PJ >> (3 * p)) & 7);
-    ax = S[(4 + 9 * i) * LDS]; ay = S[(5 + 9 * i) * LDS]; bx = S[(4 + 9 * j) * LDS]; by = S[(5 + 9 * j) * LDS];
-    reach2 = P.rr_reach2;
-  }
-  const float dx = ax - bx, dy = ay - by;
-  return dx * dx + dy * dy < reach2 ? 1u << q : 0u;
+  // x word of the two bodies of pair q (the y word is the next one): ball = word 0, robot r = word 4 + 9 r
+  constexpr unsigned char A[21] = {0, 0, 0, 0, 0, 0, 4, 4, 4, 4, 4, 13, 13, 13, 13, 22, 22, 22, 31, 31, 40};
+  constexpr unsigned char B[21] = {4, 13, 22, 31, 40, 49, 13, 22, 31, 40, 49, 22, 31, 40, 49, 31, 40, 49, 40, 49, 49};
+  const float* pa = S + A[q] * LDS;
+  const float* pb = S + B[q] * LDS;
+  const float dx = pa[0] - pb[0], dy = pa[LDS] - pb[LDS];
+  return dx * dx + dy * dy < (q < 6 ? P.br_reach2 : P.rr_reach2) ? 1u << q : 0u;
 }
 // The whole candidate mask of one field: bits 0-5 ball-robot r, bits 6-20 robot pairs.
 VSS_HD uint32_t broadphase_lane(const float* S, const DevParams& P) {
@@ -1016,20 +1008,23 @@ VSS_HD_COLD void count_sanitised(const StepArgs& a) {
 // Safety net (not in the reference): a field whose state is not finite is re-randomised on the
 // spot and reported as done with zero reward (LANE_SANITISED), so that one bad field cannot
 // poison a training run.
+// `finite` = state_finite(S) at the end of the physics; a field that was not finite has already been
+// re-randomised by the caller (lane_sanitise).
+VSS_HD_COLD void lane_sanitise(float* S, const StepArgs& a, const DevParams& P, const RngKey& key) {
+  reset_lane(S, P, key);
+  count_sanitised(a);
+}
 template <int VIEW>
-VSS_HD int lane_phase1d(float* S, long long env, const StepArgs& a, const DevParams& P, const RngKey& key) {
+VSS_HD int lane_outputs(float* S, long long env, const StepArgs& a, const DevParams& P, bool finite) {
   constexpr int AGENTS = ViewShape<VIEW>::AGENTS;
   const int progress = (int)fbits(S[VSS_W_PROGRESS * LDS]) + 1;
   S[VSS_W_PROGRESS * LDS] = bitsf((uint32_t)progress);
   float rew[VSS_REW_PER_FIELD];
-  const bool finite = state_finite(S);
   if (finite) {
     rewards_lane(S, P, rew);
   } else {
-    reset_lane(S, P, key);
 #pragma unroll
     for (int k = 0; k < VSS_REW_PER_FIELD; ++k) rew[k] = 0.0f;
-    count_sanitised(a);
   }
   const bool done = !finite || is_goal(S[0], S[LDS], P) || progress >= P.max_len;
   const bool tmo = done && finite && progress >= P.max_len - 1;  // VecTask.step timeout_buf
@@ -1075,6 +1070,12 @@ VSS_HD int lane_phase1d(float* S, long long env, const StepArgs& a, const DevPar
     }
   }
   return !done ? LANE_RUNNING : (finite ? LANE_DONE : LANE_SANITISED);
+}
+template <int VIEW>
+VSS_HD int lane_phase1d(float* S, long long env, const StepArgs& a, const DevParams& P, const RngKey& key) {
+  const bool finite = state_finite(S);
+  if (!finite) lane_sanitise(S, a, P, key);
+  return lane_outputs<VIEW>(S, env, a, P, finite);
 }
 
 // Phase 5: state out (+ zero the view's action buffer row of a done field, wrappers.py:105-107)

@@ -171,16 +171,26 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
 }
 
 // ----------------------------------------------------------------------------------------
-// k_step_cta — the same step with ONE 32-field tile per CTA, shared by W = blockDim / 32 warps.
+// k_step_cta — the same step with ONE 32-field tile per CTA, shared by NW = blockDim / 32 warps:
+// W = NW - 1 "body" warps and one helper warp.
 // Small and medium batches leave SMs idle and are bound by the critical path of a tile (one warp
 // = one field per lane walks 6 robots + the ball one after the other: ~12 000 dependent instructions,
-// 31-37 us). Here warp j owns the bodies j, j + W, ... (0-5 = robots, 6 = ball) of all 32 fields:
+// 31-37 us). Here body warp j owns the bodies j, j + W, ... (0-5 = robots, 6 = ball) of all 32 fields:
 // every dense phase still runs with 32 active lanes, lane = field, conflict-free on the same staged
-// columns, but 7 bodies advance side by side. Phases that couple bodies are separated by CTA
+// columns, but up to 7 bodies advance side by side. Phases that couple bodies are separated by CTA
 // barriers: integrate | broadphase (pairs dealt round-robin to the warps, partial masks in the
 // scratch words) | pair contacts (field l by warp l mod W: the sequential impulse order inside a
-// field is unchanged) | walls (per body, in place). The cooperative parts — state load / store by
-// words, observation rows by field groups, the masked resets — are dealt to the warps the same way.
+// field is unchanged) | walls (per body, in place).
+// The helper warp spends the physics phase computing the masked reset of EVERY field of the tile
+// into a shadow set of columns (the reset depends only on (seed, field id, episode counter), all
+// known at the start): 32 dense lanes, off the critical path; phase 3 copies the shadow columns of
+// the fields that did end. Without it the ~1 100 dependent instructions of a reset (4-5 Philox
+// blocks, 21 distance tests, 6 sincos) sit at the end of whichever tile has a done field — and with
+// >= 100 tiles per launch some tile always has one.
+// After the physics, warp 0 computes rewards / dones / per-field outputs while the other warps
+// already write the observation rows (for all fields: the rows of fields that turn out to be done
+// are written again after the reset, phase 4). The cooperative parts — state load / store by words,
+// observation rows by field groups — are dealt to all NW warps.
 // Results are bit-identical to k_step: the same per-body code in the same order per field.
 // ----------------------------------------------------------------------------------------
 template <int VIEW, bool INJECT>
@@ -191,10 +201,12 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
   for (int i = threadIdx.x; i < F4_PER_FIELD; i += blockDim.x) tab[i] = c_obs_table.v[i];
   float* T = smem + TAB_WORDS;
   uint32_t* ctr = reinterpret_cast<uint32_t*>(T + TILE_CTA_WORDS);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5, W = NW - 1;
+  const bool helper = warp == W;
   if (threadIdx.x == 0) ctr[3] = 0u;  // warps of this CTA that have finished
   const long long env0 = a.env_begin + (long long)blockIdx.x * 32;
   float* S = T + lane;
+  float* Sh = S + W_SHADOW * LDS;  // the field's shadow column
   const long long env = env0 + lane;
   const bool active = env < a.n;
   const int valid = (int)max(0LL, min(32LL, a.n - env0));
@@ -202,52 +214,55 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
   const RngKey key = make_key(a, env);
   // 1a. state in (words dealt to the warps), then actions / OU noise per Philox block, progress restart,
   //     prev_* clones per body
-  if (active) load_state_words(S, a.state, a.ld, env, warp, W);
+  if (active) load_state_words(S, a.state, a.ld, env, warp, NW);
   __syncthreads();
-  if (active) {
+  if (active && !helper) {
     for (int b = warp; b < 3; b += W) actions_block<VIEW>(S, env, a, P, key, b);
     if (warp == 3 % W && a.reset_buf[env] != 0) S[VSS_W_PROGRESS * LDS] = bitsf(0u);  // vss.py:182-183
     for (int b = warp; b < 7; b += W) prev_term_body(S, b, P);
   }
   __syncthreads();
-  // physics (replaces gym.simulate)
+  // physics (replaces gym.simulate) on the body warps; speculative resets on the helper warp. The helper
+  // takes part in every barrier of the substep loop (the barrier counts all threads of the CTA).
+  if (helper && active) {
+    Sh[VSS_W_EPISODE * LDS] = S[VSS_W_EPISODE * LDS];
+    reset_lane(Sh, P, key);
+  }
   if (INJECT) {
     if (warp == 0 && active) lane_inject(S, env, a);
   } else {
 #pragma unroll 1
     for (int it = 0; it < P.substeps; ++it) {
-      if (active)
+      if (active && !helper)
         for (int b = warp; b < 7; b += W) { if (b < 6) integrate_robot(S, b, P); else integrate_ball(S, P); }
       __syncthreads();
-      {
+      if (!helper) {
         uint32_t m = 0u;
         if (active)
           for (int q = warp; q < 21; q += W) m |= broadphase_pair(S, q, P);
         S[(W_SCR + warp) * LDS] = bitsf(m);
       }
       __syncthreads();
-      if (active && lane % W == warp) {
+      if (active && !helper && lane % W == warp) {
         uint32_t m = 0u;
         for (int j = 0; j < W; ++j) m |= fbits(S[(W_SCR + j) * LDS]);
         if (m) contacts_task(S, m, P);
       }
       __syncthreads();
-      if (active)
+      if (active && !helper)
         for (int b = warp; b < 7; b += W) walls_body(S, b, P);  // (the next integrate of a body is by the same thread)
     }
   }
   __syncthreads();
-  // 1d. post_physics_step per field (warp 0): progress, rewards, dones, per-field outputs
-  if (warp == 0) {
-    int code = LANE_RUNNING;
-    if (active) code = lane_phase1d<VIEW>(S, env, a, P, key);
-    const uint32_t dm = __ballot_sync(0xffffffffu, code == LANE_DONE);      // needs the masked reset of phase 3
-    const uint32_t em = __ballot_sync(0xffffffffu, code != LANE_RUNNING);  // episode ended (done or sanitised)
-    if (lane == 0) { ctr[0] = dm; ctr[1] = em; }
+  // non-finite guard: every warp looks at the same 32 fields, so the branch is uniform over the CTA
+  const bool finite = !active || state_finite(S);
+  if (__ballot_sync(0xffffffffu, !finite)) {
+    __syncthreads();
+    if (warp == 0 && !finite) lane_sanitise(S, a, P, key);
+    __syncthreads();
   }
-  __syncthreads();
-  const uint32_t done_mask = ctr[0], ended_mask = ctr[1];
-  // 2. terminal observation + observation of the fields that keep their state (vss.py:195-196)
+  // 1d. post_physics_step per field (warp 0): progress, rewards, dones, per-field outputs — while the other
+  // warps write 2. terminal observation + observation (vss.py:195-196) of all fields
   float* ob = a.obs + env0 * (PER_FIELD * 4);
   float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
   void* obh = (VIEW != VIEW_FULL && a.obs_bf16)
@@ -256,18 +271,28 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
   void* pk = (VIEW != VIEW_FULL && a.packed)
                  ? static_cast<void*>(static_cast<char*>(a.packed) + env0 * (ViewShape<VIEW>::AGENTS * VSS_PACKED_ROW_BYTES))
                  : nullptr;
-  if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD, true>(T, tab, lane, valid, tob, ob, done_mask, obh, pk, warp, W);
-  else write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, done_mask, obh, pk, warp, W);
-  __syncthreads();
-  // 3. masked reset (vss.py:202, 267-333): the k-th done field by warp k mod W
-  if ((done_mask >> lane) & 1u) {
-    const int k = __popc(done_mask & ((1u << lane) - 1u));
-    if (k % W == warp) reset_lane(S, P, key);
+  if (warp == 0) {
+    int code = LANE_RUNNING;
+    if (active) code = lane_outputs<VIEW>(S, env, a, P, finite);
+    const uint32_t dm = __ballot_sync(0xffffffffu, code == LANE_DONE);      // needs the masked reset of phase 3
+    const uint32_t em = __ballot_sync(0xffffffffu, code != LANE_RUNNING);  // episode ended (done or sanitised)
+    if (lane == 0) { ctr[0] = dm; ctr[1] = em; }
+  } else if (PER_FIELD >= 32) {
+    write_obs_tile_rows<PER_FIELD, true>(T, tab, lane, valid, tob, ob, 0u, obh, pk, warp - 1, NW - 1);
+  } else {
+    write_obs_tile(T, tab, lane, valid, PER_FIELD, tob, ob, 0u, obh, pk, warp - 1, NW - 1);
   }
   __syncthreads();
+  const uint32_t done_mask = ctr[0], ended_mask = ctr[1];
+  // 3. masked reset (vss.py:202, 267-333): the shadow column replaces the state (not the progress counter,
+  //    which restarts at the next step's pre_physics_step)
+  if ((done_mask >> lane) & 1u)
+    for (int w = warp; w < VSS_STATE_WORDS; w += NW)
+      if (w != VSS_W_PROGRESS) S[w * LDS] = Sh[w * LDS];
+  __syncthreads();
   // 4. observation of the fields that were reset (vss.py:203); 5. state out
-  write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask, obh, pk, warp, W);
-  if (active) store_state_words(S, a.state, a.ld, env, warp, W);
+  write_obs_fields(T, tab, lane, PER_FIELD, ob, done_mask, obh, pk, warp, NW);
+  if (active) store_state_words(S, a.state, a.ld, env, warp, NW);
   if (VIEW != VIEW_FULL) {
     if (warp == 0 && ((ended_mask >> lane) & 1u)) zero_action_row(env, a);  // wrappers.py:105-107
     step_done(a, ctr);
@@ -431,9 +456,9 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 // First-wave stagger (profiles/r01_g_*.md): 5 us per resident CTA of an SM, measured best of 0-12 us
 // at 2^20 fields (675 -> 652 us per step); only for the barrier-synchronised shape and only when the
 // launch is longer than one wave of 148 x 6 CTAs.
-// `wpt` (warps per tile) > 1 selects k_step_cta: one 32-field tile per CTA shared by wpt warps (bodies dealt
-// to the warps). It shortens a tile's critical path ~wpt-fold and is used while the batch cannot fill the
-// SMs with one warp per tile: 7 warps (one per body) up to 512 tiles, 4 up to 888, 2 up to 2 368.
+// `wpt` (warps per tile) > 1 selects k_step_cta: one 32-field tile per CTA shared by wpt - 1 body warps (bodies
+// dealt to the warps) and a helper warp. It shortens a tile's critical path and is used while the batch cannot
+// fill the SMs with one warp per tile.
 struct LaunchShape {
   int wpb, fpw, stagger_ns, wpt;
   bool sync;
@@ -443,7 +468,7 @@ struct LaunchShape {
 
 static int auto_wpt(int64_t n) {
   const int64_t tiles = (n + 31) / 32;
-  return tiles <= 512 ? 7 : (tiles <= 888 ? 4 : (tiles <= 2368 ? 2 : 1));
+  return tiles <= 512 ? 8 : 1;
 }
 
 static LaunchShape launch_shape(int64_t n, bool step_kernel = true, int wpt_override = 0) {

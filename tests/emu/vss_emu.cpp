@@ -62,11 +62,13 @@ static void emu_step_t(const StepArgs& a, const DevParams& P) {
   }
 }
 
-// Mirror of k_step_cta (one tile shared by W warps, bodies dealt to the warps): the phases below are
-// the kernel's, each CTA barrier becomes the end of a loop over (warp, lane).
+// Mirror of k_step_cta (one tile shared by NW warps: W = NW - 1 body warps with the bodies dealt to them,
+// and a helper warp that computes the resets speculatively into shadow columns): the phases below are the
+// kernel's, each CTA barrier becomes the end of a loop over (warp, lane).
 template <int VIEW, bool INJECT>
-static void emu_step_cta_t(const StepArgs& a, const DevParams& P, int W) {
+static void emu_step_cta_t(const StepArgs& a, const DevParams& P, int NW) {
   constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
+  const int W = NW - 1;
   const long long tiles = (a.n + 31) / 32;
 #pragma omp parallel for schedule(static)
   for (long long tile = 0; tile < tiles; ++tile) {
@@ -74,9 +76,10 @@ static void emu_step_cta_t(const StepArgs& a, const DevParams& P, int W) {
     float* T = Tbuf.data();
     const long long env0 = tile * 32;
     const int valid = (int)std::min(32LL, a.n - env0);
-#define EACH_THREAD for (int warp = 0; warp < W; ++warp) for (int lane = 0; lane < valid; ++lane)
-    EACH_THREAD load_state_words(T + lane, a.state, a.ld, env0 + lane, warp, W);
-    EACH_THREAD {
+#define EACH_THREAD for (int warp = 0; warp < NW; ++warp) for (int lane = 0; lane < valid; ++lane)
+#define EACH_BODY_THREAD for (int warp = 0; warp < W; ++warp) for (int lane = 0; lane < valid; ++lane)
+    EACH_THREAD load_state_words(T + lane, a.state, a.ld, env0 + lane, warp, NW);
+    EACH_BODY_THREAD {
       float* S = T + lane;
       const long long env = env0 + lane;
       const RngKey key = make_key(a, env);
@@ -84,51 +87,64 @@ static void emu_step_cta_t(const StepArgs& a, const DevParams& P, int W) {
       if (warp == 3 % W && a.reset_buf[env] != 0) S[VSS_W_PROGRESS * LDS] = bitsf(0u);
       for (int b = warp; b < 7; b += W) prev_term_body(S, b, P);
     }
+    for (int lane = 0; lane < valid; ++lane) {  // the helper warp
+      float* S = T + lane;
+      float* Sh = S + W_SHADOW * LDS;
+      Sh[VSS_W_EPISODE * LDS] = S[VSS_W_EPISODE * LDS];
+      reset_lane(Sh, P, make_key(a, env0 + lane));
+    }
     if (INJECT) {
       for (int lane = 0; lane < valid; ++lane) lane_inject(T + lane, env0 + lane, a);
     } else {
       for (int it = 0; it < P.substeps; ++it) {
-        EACH_THREAD for (int b = warp; b < 7; b += W) { if (b < 6) integrate_robot(T + lane, b, P); else integrate_ball(T + lane, P); }
-        EACH_THREAD {
+        EACH_BODY_THREAD for (int b = warp; b < 7; b += W) { if (b < 6) integrate_robot(T + lane, b, P); else integrate_ball(T + lane, P); }
+        EACH_BODY_THREAD {
           uint32_t m = 0u;
           for (int q = warp; q < 21; q += W) m |= broadphase_pair(T + lane, q, P);
           T[(W_SCR + warp) * LDS + lane] = bitsf(m);
         }
-        EACH_THREAD if (lane % W == warp) {
+        EACH_BODY_THREAD if (lane % W == warp) {
           uint32_t m = 0u;
           for (int j = 0; j < W; ++j) m |= fbits(T[(W_SCR + j) * LDS + lane]);
           if (m) contacts_task(T + lane, m, P);
         }
-        EACH_THREAD for (int b = warp; b < 7; b += W) walls_body(T + lane, b, P);
+        EACH_BODY_THREAD for (int b = warp; b < 7; b += W) walls_body(T + lane, b, P);
       }
     }
-    uint32_t done_mask = 0, ended_mask = 0;
+    bool finite[32];
     for (int lane = 0; lane < valid; ++lane) {
-      const int code = lane_phase1d<VIEW>(T + lane, env0 + lane, a, P, make_key(a, env0 + lane));
-      if (code == LANE_DONE) done_mask |= 1u << lane;
-      if (code != LANE_RUNNING) ended_mask |= 1u << lane;
+      finite[lane] = state_finite(T + lane);
+      if (!finite[lane]) lane_sanitise(T + lane, a, P, make_key(a, env0 + lane));
     }
     float* ob = a.obs + env0 * (PER_FIELD * 4);
     float* tob = a.term_obs ? a.term_obs + env0 * (PER_FIELD * 4) : nullptr;
     void* pk = (VIEW != VIEW_FULL && a.packed)
                    ? static_cast<void*>(static_cast<char*>(a.packed) + env0 * (ViewShape<VIEW>::AGENTS * VSS_PACKED_ROW_BYTES))
                    : nullptr;
-    for (int warp = 0; warp < W; ++warp)
+    // warps 1 .. NW-1 write the rows of ALL fields (before warp 0's outputs are known) ...
+    for (int warp = 1; warp < NW; ++warp)
       for (int lane = 0; lane < 32; ++lane) {
-        if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD, true>(T, g_tab.v, lane, valid, tob, ob, done_mask, nullptr, pk, warp, W);
-        else write_obs_tile(T, g_tab.v, lane, valid, PER_FIELD, tob, ob, done_mask, nullptr, pk, warp, W);
+        if (PER_FIELD >= 32) write_obs_tile_rows<PER_FIELD, true>(T, g_tab.v, lane, valid, tob, ob, 0u, nullptr, pk, warp - 1, NW - 1);
+        else write_obs_tile(T, g_tab.v, lane, valid, PER_FIELD, tob, ob, 0u, nullptr, pk, warp - 1, NW - 1);
       }
-    EACH_THREAD if ((done_mask >> lane) & 1u) {
-      const int k = __builtin_popcount(done_mask & ((1u << lane) - 1u));
-      if (k % W == warp) reset_lane(T + lane, P, make_key(a, env0 + lane));
+    // ... while warp 0 computes them
+    uint32_t done_mask = 0, ended_mask = 0;
+    for (int lane = 0; lane < valid; ++lane) {
+      const int code = lane_outputs<VIEW>(T + lane, env0 + lane, a, P, finite[lane]);
+      if (code == LANE_DONE) done_mask |= 1u << lane;
+      if (code != LANE_RUNNING) ended_mask |= 1u << lane;
     }
-    for (int warp = 0; warp < W; ++warp)
-      for (int lane = 0; lane < 32; ++lane) write_obs_fields(T, g_tab.v, lane, PER_FIELD, ob, done_mask, nullptr, pk, warp, W);
-    EACH_THREAD store_state_words(T + lane, a.state, a.ld, env0 + lane, warp, W);
+    EACH_THREAD if ((done_mask >> lane) & 1u)
+      for (int w = warp; w < VSS_STATE_WORDS; w += NW)
+        if (w != VSS_W_PROGRESS) T[w * LDS + lane] = T[(W_SHADOW + w) * LDS + lane];
+    for (int warp = 0; warp < NW; ++warp)
+      for (int lane = 0; lane < 32; ++lane) write_obs_fields(T, g_tab.v, lane, PER_FIELD, ob, done_mask, nullptr, pk, warp, NW);
+    EACH_THREAD store_state_words(T + lane, a.state, a.ld, env0 + lane, warp, NW);
     if (VIEW != VIEW_FULL)
       for (int lane = 0; lane < valid; ++lane)
         if ((ended_mask >> lane) & 1u) zero_action_row(env0 + lane, a);
 #undef EACH_THREAD
+#undef EACH_BODY_THREAD
   }
 }
 
