@@ -580,13 +580,21 @@ VSS_HD void integrate_ball(float* S, const DevParams& P) {
   S[0] += vx * P.h; S[LDS] += vy * P.h;
 }
 // C. broadphase of pair q (0-5: ball-robot q; 6-20: robot pairs in lexicographic order): the bit of the
-// candidate mask, from the post-integration positions.
-VSS_HD uint32_t broadphase_pair(const float* S, int q, const DevParams& P) {
-  // x word of the two bodies of pair q (the y word is the next one): ball = word 0, robot r = word 4 + 9 r
-  constexpr unsigned char A[21] = {0, 0, 0, 0, 0, 0, 4, 4, 4, 4, 4, 13, 13, 13, 13, 22, 22, 22, 31, 31, 40};
-  constexpr unsigned char B[21] = {4, 13, 22, 31, 40, 49, 13, 22, 31, 40, 49, 22, 31, 40, 49, 31, 40, 49, 40, 49, 49};
-  const float* pa = S + A[q] * LDS;
-  const float* pb = S + B[q] * LDS;
+// candidate mask, from the post-integration positions. PAIR_A / PAIR_B: x word of the two bodies of pair
+// q (the y word is the next one): ball = word 0, robot r = word 4 + 9 r. (Constant memory on the device: a
+// local constexpr array indexed at run time is rebuilt on the stack at every call.)
+#if defined(__CUDACC__)
+#define VSS_D __device__ __forceinline__
+#define VSS_TABLE __constant__ const
+#else
+#define VSS_D inline
+#define VSS_TABLE static const
+#endif
+VSS_TABLE unsigned char PAIR_A[21] = {0, 0, 0, 0, 0, 0, 4, 4, 4, 4, 4, 13, 13, 13, 13, 22, 22, 22, 31, 31, 40};
+VSS_TABLE unsigned char PAIR_B[21] = {4, 13, 22, 31, 40, 49, 13, 22, 31, 40, 49, 22, 31, 40, 49, 31, 40, 49, 40, 49, 49};
+VSS_D uint32_t broadphase_pair(const float* S, int q, const DevParams& P) {
+  const float* pa = S + PAIR_A[q] * LDS;
+  const float* pb = S + PAIR_B[q] * LDS;
   const float dx = pa[0] - pb[0], dy = pa[LDS] - pb[LDS];
   return dx * dx + dy * dy < (q < 6 ? P.br_reach2 : P.rr_reach2) ? 1u << q : 0u;
 }

@@ -193,6 +193,12 @@ k_step(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) 
 // observation rows by field groups — are dealt to all NW warps.
 // Results are bit-identical to k_step: the same per-body code in the same order per field.
 // ----------------------------------------------------------------------------------------
+// Barrier over the W body warps of a k_step_cta CTA only (named barrier 1): the helper warp runs its
+// speculative resets meanwhile and joins the others at the next __syncthreads().
+__device__ __forceinline__ void body_barrier(int W) {
+  asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
+}
+
 template <int VIEW, bool INJECT>
 __global__ void __launch_bounds__(32 * MAX_WPT)
 k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) {
@@ -222,8 +228,8 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
     for (int b = warp; b < 7; b += W) prev_term_body(S, b, P);
   }
   __syncthreads();
-  // physics (replaces gym.simulate) on the body warps; speculative resets on the helper warp. The helper
-  // takes part in every barrier of the substep loop (the barrier counts all threads of the CTA).
+  // physics (replaces gym.simulate) on the body warps, which synchronise among themselves (body_barrier);
+  // speculative resets on the helper warp meanwhile.
   if (helper && active) {
     Sh[VSS_W_EPISODE * LDS] = S[VSS_W_EPISODE * LDS];
     reset_lane(Sh, P, key);
@@ -231,26 +237,28 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
   if (INJECT) {
     if (warp == 0 && active) lane_inject(S, env, a);
   } else {
+    if (!helper) {
 #pragma unroll 1
-    for (int it = 0; it < P.substeps; ++it) {
-      if (active && !helper)
-        for (int b = warp; b < 7; b += W) { if (b < 6) integrate_robot(S, b, P); else integrate_ball(S, P); }
-      __syncthreads();
-      if (!helper) {
-        uint32_t m = 0u;
+      for (int it = 0; it < P.substeps; ++it) {
         if (active)
-          for (int q = warp; q < 21; q += W) m |= broadphase_pair(S, q, P);
-        S[(W_SCR + warp) * LDS] = bitsf(m);
+          for (int b = warp; b < 7; b += W) { if (b < 6) integrate_robot(S, b, P); else integrate_ball(S, P); }
+        body_barrier(W);
+        {
+          uint32_t m = 0u;
+          if (active)
+            for (int q = warp; q < 21; q += W) m |= broadphase_pair(S, q, P);
+          S[(W_SCR + warp) * LDS] = bitsf(m);
+        }
+        body_barrier(W);
+        if (active && lane % W == warp) {
+          uint32_t m = 0u;
+          for (int j = 0; j < W; ++j) m |= fbits(S[(W_SCR + j) * LDS]);
+          if (m) contacts_task(S, m, P);
+        }
+        body_barrier(W);
+        if (active)
+          for (int b = warp; b < 7; b += W) walls_body(S, b, P);  // (the next integrate of a body is by the same thread)
       }
-      __syncthreads();
-      if (active && !helper && lane % W == warp) {
-        uint32_t m = 0u;
-        for (int j = 0; j < W; ++j) m |= fbits(S[(W_SCR + j) * LDS]);
-        if (m) contacts_task(S, m, P);
-      }
-      __syncthreads();
-      if (active && !helper)
-        for (int b = warp; b < 7; b += W) walls_body(S, b, P);  // (the next integrate of a body is by the same thread)
     }
   }
   __syncthreads();
