@@ -476,7 +476,10 @@ struct LaunchShape {
 
 static int auto_wpt(int64_t n) {
   const int64_t tiles = (n + 31) / 32;
-  return tiles <= 512 ? 8 : 1;
+  // measured (profiles/r02_g_step_shapes.txt, us per launch, sa view, 1 / 8 warps per tile): 1 024 fields 31.0 / 29.0;
+  // 4 096: 32.5 / 30.3; 8 192: 36.2 / 33.2; 16 384: 39.5 / 45+: from ~3 CTAs per SM on, the idle lanes of the
+  // one-warp shape (8 or 16 fields per warp) are the cheaper way to shorten the critical path
+  return tiles <= 256 ? 8 : 1;
 }
 
 static LaunchShape launch_shape(int64_t n, bool step_kernel = true, int wpt_override = 0) {
