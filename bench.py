@@ -399,13 +399,13 @@ def run_native(args):
     achieved = BYTES_PER_FIELD_STEP * n / (ms * 1e-3 / args.steps) / 1e9
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, scaled per field
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_step_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_step_traffic.json")))
         traffic = tr["dram_bytes_per_field_step"] * n
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
-                "traffic_source": "ncu capture profiles/r01_step_traffic.json (per field-step x fields), not re-measured in this run",
+                "traffic_source": "ncu capture profiles/r02_step_traffic.json (per field-step x fields), not re-measured in this run",
                 "kernel": "k_step<full>", "algorithmic_bytes_per_launch": BYTES_PER_FIELD_STEP * n,
                 "region": f"{args.steps} back-to-back launches" + (" (burst: shorter than the power-cap time constant)"
                                                                    if args.steps < 200 else " (sustained)"),
