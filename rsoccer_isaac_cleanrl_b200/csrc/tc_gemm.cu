@@ -137,6 +137,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// Bulk tensor store shared -> global (the epilogue's output tile; rows / columns outside the tensor are clipped)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// The same load without the wait: the caller overlaps it with work on registers it already holds and
+// calls tmem_ld_wait() before touching v.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -502,19 +526,21 @@ constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
 struct SmemWS {
   static constexpr int A_BYTES = BM * BK * 2;                    // 16 KB per stage
   static constexpr int KB_BYTES = 128 * BK * 2;                  // 16 KB of resident weights per k-block
-  static constexpr int TAIL = 1024 + 256 + 2048 + WS_EPI_WARPS * 32 * 80;  // align slack, barriers, bias, staging
+  static constexpr int OUT_STAGE = 32 * 128;                     // per epilogue warp: 32 rows x 64 bf16, 128B-swizzled TMA box
+  static constexpr int TAIL = 1024 + 256 + 2048 + WS_EPI_WARPS * OUT_STAGE;  // align slack, barriers, bias, output staging
   static constexpr int BUDGET = 226 * 1024;                      // dynamic shared memory per CTA (227 KB max)
   // Depth of the activation ring. Measured at M = 131072, N = 512: K = 256 -> 74 us with 4 stages,
   // 69 us with 9; K = 512 -> 93 us with 4 stages, 104 us with 5 (the last 16 KB of shared memory
   // are better left to L1). So: as deep as fits below ~208 KB.
-  static int stages(int nkb) { return std::min(WS_MAX_STAGES, (208 * 1024 - TAIL - nkb * KB_BYTES) / A_BYTES); }
+  // (212 KB: K = 512 keeps its 4 stages beside the 16 KB of output staging)
+  static int stages(int nkb) { return std::min(WS_MAX_STAGES, (212 * 1024 - TAIL - nkb * KB_BYTES) / A_BYTES); }
   static int total(int nkb) { return nkb * KB_BYTES + stages(nkb) * A_BYTES + TAIL; }
 };
 
 template <int EPI>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-          const __grid_constant__ GemmArgs g) {
+          const __grid_constant__ CUtensorMap map_o, const __grid_constant__ GemmArgs g) {
   constexpr int BN = 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -522,7 +548,8 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const uint32_t nst = (uint32_t)g.ws_stages;   // depth of the activation ring (host: SmemWS::stages)
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + nkb * SmemWS::KB_BYTES;
-  uint8_t* tail = smem_a + nst * SmemWS::A_BYTES;
+  uint8_t* out_stage = smem_a + nst * SmemWS::A_BYTES;   // 1024-byte aligned: the swizzle pattern is address-based
+  uint8_t* tail = out_stage + WS_EPI_WARPS * SmemWS::OUT_STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + WS_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + WS_MAX_STAGES;
@@ -530,7 +557,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* b_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
   float* bias_s = reinterpret_cast<float*>(tail + 256);
-  uint8_t* stage = tail + 256 + 2048 + (((threadIdx.x >> 5) + WS_EPI_WARPS - 2) % WS_EPI_WARPS) * STAGE_BYTES_PER_WARP;
+  uint8_t* stage = out_stage + (((threadIdx.x >> 5) + WS_EPI_WARPS - 2) % WS_EPI_WARPS) * SmemWS::OUT_STAGE;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
@@ -600,16 +627,58 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
       mbar_wait(&tfull_bar[buf], bph);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = c_begin; c < c_begin + COLS_PER_WARP; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c, v);
-        epilogue_chunk<EPI>(v, mt * BM + q * 32, lane, n0 + c, g, bias_s, bias_in_smem, stage);
+      // The four 32-column chunks of this warp's rows, software-pipelined: the TMEM load of chunk c + 1 is in
+      // flight while chunk c goes through bias + tanh + stores (with one load at a time every chunk exposed the
+      // full tcgen05.ld latency: with one CTA per SM nothing else runs on the epilogue warps' schedulers).
+      static_assert(COLS_PER_WARP == 128, "four chunks per warp");
+      uint32_t v[2][32];
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c_begin;
+      tmem_ld32_issue(t0, v[0]);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        tmem_ld_wait();
+        if (ci + 1 < 4) tmem_ld32_issue(t0 + 32u * (ci + 1), v[(ci + 1) & 1]);
+        if (EPI == EPI_BIAS_TANH_BF16) {
+          // bias + tanh -> bf16 -> this warp's 32 x 64 staging box (128-byte rows, 16-byte chunk k of row r at
+          // position k ^ (r & 7): the layout of a SWIZZLE_128B tensor-map box, and conflict-free for STS.128);
+          // after two chunks ONE bulk tensor store writes the 32 x 128-byte box. (Direct 16-byte stores of one
+          // row per lane sent every 32-byte sector to L2 twice and kept L1TEX 70 % busy: ncu, profiles/r02_k.)
+          if ((ci & 1) == 0) {  // the previous box must have been read out of shared memory
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+          const int col = n0 + c_begin + 32 * ci;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j + 4);
+            const uint32_t* x = &v[ci & 1][8 * j];
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[0]) + b0.x), tanh_fast(__uint_as_float(x[1]) + b0.y));
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[2]) + b0.z), tanh_fast(__uint_as_float(x[3]) + b0.w));
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[4]) + b1.x), tanh_fast(__uint_as_float(x[5]) + b1.y));
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[6]) + b1.z), tanh_fast(__uint_as_float(x[7]) + b1.w));
+            const int k = (ci & 1) * 4 + j;
+            *reinterpret_cast<uint4*>(stage + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+                make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                           *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+          }
+          if (ci & 1) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_o, stage, n0 + c_begin + 32 * (ci - 1), mt * BM + q * 32);
+              tma_store_commit();
+            }
+          }
+        } else {
+          epilogue_chunk<EPI>(v[ci & 1], mt * BM + q * 32, lane, n0 + c_begin + 32 * ci, g, bias_s, bias_in_smem, stage);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
+    if (EPI == EPI_BIAS_TANH_BF16 && lane == 0) tma_store_wait_all();  // the last boxes have left shared memory and landed
   }
   tc_fence_before();
   __syncthreads();
@@ -652,7 +721,7 @@ static bool make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int 
 }
 
 template <int EPI>
-static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, GemmArgs g, cudaStream_t st) {
+static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, GemmArgs g, cudaStream_t st) {
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
@@ -667,7 +736,7 @@ static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, GemmA
   int per_slice = std::min(std::max(sms / n_tiles, 1), m_tiles);   // CTAs per column slice
   const int nkb = g.K / BK;
   g.ws_stages = SmemWS::stages(nkb);
-  k_gemm_ws<EPI><<<per_slice * n_tiles, WS_THREADS, SmemWS::total(nkb), st>>>(ma, mb, g);
+  k_gemm_ws<EPI><<<per_slice * n_tiles, WS_THREADS, SmemWS::total(nkb), st>>>(ma, mb, mo, g);
   return cudaGetLastError();
 }
 
@@ -964,10 +1033,12 @@ VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int l
   // MLP at M = 131072; dgrad, whose epilogue also streams the aux tile, is 8 % slower with it and
   // stays on the streaming kernel). VSS_GEMM_WS=0/2 disables it / also enables it for dgrad (tuning).
   static const int ws_mode = getenv("VSS_GEMM_WS") ? atoi(getenv("VSS_GEMM_WS")) : 1;
-  if (ws_mode && !colsum && !mn_major && splits == 1 && bn == 128 && K <= 512 && M >= 128 * 148 &&
+  if (ws_mode && !colsum && !mn_major && splits == 1 && bn == 128 && K <= 512 && N <= 512 && M >= 128 * 148 &&
       (epilogue == EPI_BIAS_TANH_BF16 || (ws_mode == 2 && epilogue == EPI_DTANH_BF16))) {
-    e = epilogue == EPI_BIAS_TANH_BF16 ? launch_ws<EPI_BIAS_TANH_BF16>(ma, mb, g, st)
-                                       : launch_ws<EPI_DTANH_BF16>(ma, mb, g, st);
+    CUtensorMap mo;  // the bf16 output as 32-row x 64-column boxes for the epilogue's bulk tensor stores
+    if (!make_map(&mo, out, M, N, ldo, 32)) { g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled (output) failed"; return VSS_E_CUDA; }
+    e = epilogue == EPI_BIAS_TANH_BF16 ? launch_ws<EPI_BIAS_TANH_BF16>(ma, mb, mo, g, st)
+                                       : launch_ws<EPI_DTANH_BF16>(ma, mb, mo, g, st);
     if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
     return VSS_OK;
   }
