@@ -688,6 +688,209 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA-pair kernel for the forward GEMMs (K-major, N % 256 == 0): tcgen05 `cta_group::2`.
+// Two CTAs on the two SMs of a TPC (a cluster of 2) compute one 256 x 256 output tile: each CTA
+// stages ITS 128 rows of A and ITS 128 of the 256 B rows (N) per k-block — 32 KB per stage for 4.2 MFLOP
+// of its tensor core, 131 FLOP per staged byte like the weight-stationary kernel, but without the
+// 128 KB resident weight slice, so the ring is 6 x 32 KB deep instead of 4 x 16 KB: the streaming of
+// the activation tiles was latency-bound by the bytes in flight (K = 512: 767 TFLOP/s with 64 KB in
+// flight per SM). One thread of the leader CTA (cluster rank 0) issues the MMAs for both tensor
+// cores (M = 256: rows 0-127 accumulate in the leader's TMEM, rows 128-255 in the peer's, same
+// columns); both CTAs' TMA loads complete on the LEADER's full barrier (the leader arms it for
+// both halves); tcgen05.commit multicasts the "stage free" and "accumulator ready" arrivals to both
+// CTAs; the peer's epilogue warps hand the accumulator buffer back by arriving on the leader's
+// barrier across the cluster. Epilogue as in k_gemm_ws: bias + tanh -> bf16 -> swizzled staging box
+// -> bulk tensor store, TMEM loads software-pipelined; accumulators double-buffered (2 x 256 columns).
+// ---------------------------------------------------------------------------------------------
+constexpr int P2_BN = 256, P2_STAGES = 5;   // 5 x 32 KB ring + 2 x 16 KB of output staging
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: the leader's copy
+struct SmemPair {
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = 128 * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_STAGE = 2 * 32 * 128;   // per epilogue warp: two 32 x 64 boxes (one being stored, one being filled)
+  static constexpr int TOTAL = P2_STAGES * STAGE_BYTES + EPI_WARPS * OUT_STAGE + 256 + 2048 + 1024;
+};
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & PEER_BIT_MASK), "r"(c_inner), "r"(c_outer) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on `bar` of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ CUtensorMap map_o, const __grid_constant__ GemmArgs g) {
+  static_assert(EPI == EPI_BIAS_TANH_BF16, "forward epilogue");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* out_stage = smem + P2_STAGES * SmemPair::STAGE_BYTES;  // 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + EPI_WARPS * SmemPair::OUT_STAGE);
+  uint64_t* empty_bar = full_bar + P2_STAGES;
+  uint64_t* tfull_bar = empty_bar + P2_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_tiles = g.N / P2_BN, m_tiles = (g.M + 2 * BM - 1) / (2 * BM);
+  const int total_tiles = n_tiles * m_tiles, nkb = g.K / BK;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // the same warp of both CTAs allocates all 512 columns of the pair's tensor memory
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < g.N; i += THREADS) bias_s[i] = __ldg(g.bias + i);   // N <= 512 (checked by the host)
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // the peer's barriers are initialised before anything is signalled to them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer (both CTAs): own 128 rows of A, own 128 rows of B
+      uint32_t s = 0, ph = 0;
+      for (int t = pair; t < total_tiles; t += npairs) {
+        const int m0 = (t / n_tiles) * (2 * BM) + rank * BM, n0 = (t % n_tiles) * P2_BN + rank * 128;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * SmemPair::STAGE_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * SmemPair::STAGE_BYTES);  // both CTAs' halves land on this barrier
+          tma_load_2d_pair(sa, &map_a, &full_bar[s], kb * BK, m0);
+          tma_load_2d_pair(sa + SmemPair::A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
+          if (++s == P2_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {  // ---- MMA issuer: one thread for both tensor cores
+      constexpr uint32_t idesc = make_idesc(2 * BM, P2_BN, false);
+      uint32_t s = 0, ph = 0, lt = 0;
+      for (int t = pair; t < total_tiles; t += npairs, ++lt) {
+        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], bph ^ 1);  // both CTAs' epilogues have drained this buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * P2_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SmemPair::STAGE_BYTES);
+          const uint64_t adesc = make_desc_k128(sa), bdesc = make_desc_k128(sa + SmemPair::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[s]);  // the stage is free in both CTAs when these MMAs retire
+          if (++s == P2_STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[buf]);  // accumulator complete, in both CTAs
+      }
+    }
+  } else {
+    // ---- epilogue (both CTAs): this CTA's 128 rows x 256 columns, warp q = TMEM lane quarter
+    const int q = warp & 3;
+    uint8_t* stage = out_stage + q * SmemPair::OUT_STAGE;
+    uint32_t lt = 0;
+    for (int t = pair; t < total_tiles; t += npairs, ++lt) {
+      const int m0 = (t / n_tiles) * (2 * BM) + rank * BM + q * 32, n0 = (t % n_tiles) * P2_BN;
+      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+      mbar_wait(&tfull_bar[buf], bph);
+      tc_fence_after();
+      uint32_t v[2][32];
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * P2_BN;
+      tmem_ld32_issue(t0, v[0]);
+#pragma unroll
+      for (int ci = 0; ci < P2_BN / 32; ++ci) {
+        tmem_ld_wait();
+        if (ci + 1 < P2_BN / 32) tmem_ld32_issue(t0 + 32u * (ci + 1), v[(ci + 1) & 1]);
+        uint8_t* box = stage + ((ci >> 1) & 1) * (32 * 128);   // the two boxes alternate
+        if ((ci & 1) == 0) {  // the store that last used this box (two boxes ago) has read it out of shared memory
+          if (lane == 0) tma_store_wait_read1();
+          __syncwarp();
+        }
+        const int col = n0 + 32 * ci;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j + 4);
+          const uint32_t* x = &v[ci & 1][8 * j];
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[0]) + b0.x), tanh_fast(__uint_as_float(x[1]) + b0.y));
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[2]) + b0.z), tanh_fast(__uint_as_float(x[3]) + b0.w));
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[4]) + b1.x), tanh_fast(__uint_as_float(x[5]) + b1.y));
+          __nv_bfloat162 p3 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[6]) + b1.z), tanh_fast(__uint_as_float(x[7]) + b1.w));
+          const int k = (ci & 1) * 4 + j;
+          *reinterpret_cast<uint4*>(box + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+              make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                         *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+        }
+        if (ci & 1) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_o, box, n0 + 32 * (ci - 1), m0);
+            tma_store_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[buf]);  // (the leader's own warps arrive locally through the same address)
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // no CTA leaves while its peer can still signal it or read its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+template <int EPI>
+static cudaError_t launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmArgs& g,
+                               cudaStream_t st) {
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_pair<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPair::TOTAL);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const long long tiles = (long long)((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / P2_BN);
+  unsigned grid = (unsigned)std::min<long long>(2 * tiles, sms & ~1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SmemPair::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_gemm_pair<EPI>, ma, mb, mo, g);
+}
+
 // ------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1033,6 +1236,18 @@ VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int l
   // MLP at M = 131072; dgrad, whose epilogue also streams the aux tile, is 8 % slower with it and
   // stays on the streaming kernel). VSS_GEMM_WS=0/2 disables it / also enables it for dgrad (tuning).
   static const int ws_mode = getenv("VSS_GEMM_WS") ? atoi(getenv("VSS_GEMM_WS")) : 1;
+#ifndef VSS_NO_PAIR
+  // forward with N a multiple of 256 and enough row tiles: the CTA-pair kernel (tcgen05 cta_group::2)
+  if (epilogue == EPI_BIAS_TANH_BF16 && !mn_major && splits == 1 && N % 256 == 0 && N <= 512 && M >= 256 * 74) {
+    CUtensorMap ma2, mb2, mo2;  // A: 128-row boxes; B: 128-row boxes (this CTA's half of the 256 columns); out: 32 x 64 boxes
+    if (!make_map(&ma2, A, M, K, lda, BM) || !make_map(&mb2, B, N, K, ldb, 128) || !make_map(&mo2, out, M, N, ldo, 32)) {
+      g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA;
+    }
+    e = launch_pair<EPI_BIAS_TANH_BF16>(ma2, mb2, mo2, g, st);
+    if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn (pair): ") + cudaGetErrorString(e); return VSS_E_CUDA; }
+    return VSS_OK;
+  }
+#endif
   if (ws_mode && !colsum && !mn_major && splits == 1 && bn == 128 && K <= 512 && N <= 512 && M >= 128 * 148 &&
       (epilogue == EPI_BIAS_TANH_BF16 || (ws_mode == 2 && epilogue == EPI_DTANH_BF16))) {
     CUtensorMap mo;  // the bf16 output as 32-row x 64-column boxes for the epilogue's bulk tensor stores

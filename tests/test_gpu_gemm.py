@@ -19,8 +19,11 @@ def _rand(shape, seed, scale=1.0):
     return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
 
 
+# (M >= 18 944 with N a multiple of 256 takes the CTA-pair kernel, tcgen05 cta_group::2: ragged M, one and two
+# column tiles, every K of the MLP)
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 64), (4096, 512, 256), (300, 256, 512), (131072, 512, 512),
-                                   (1000, 64, 256)])
+                                   (1000, 64, 256), (19001, 256, 64), (40000, 512, 256), (131072, 256, 512),
+                                   (18944, 512, 512)])
 def test_forward_bias_tanh(M, N, K):
     from rsoccer_isaac_cleanrl_b200.engine import EPI_BIAS_TANH_BF16, gemm_bf16
     a, w = _rand((M, K), 1), _rand((N, K), 2, K ** -0.5)
