@@ -703,12 +703,18 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // barrier across the cluster. Epilogue as in k_gemm_ws: bias + tanh -> bf16 -> swizzled staging box
 // -> bulk tensor store, TMEM loads software-pipelined; accumulators double-buffered (2 x 256 columns).
 // ---------------------------------------------------------------------------------------------
-constexpr int P2_BN = 256, P2_STAGES = 5;   // 5 x 32 KB ring + 2 x 16 KB of output staging
+constexpr int P2_BN = 256;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: the leader's copy
+// forward: 5 x 32 KB ring + 2 x 16 KB of output boxes; dgrad: 4 x 32 KB ring + 2 x 16 KB of output boxes + 2 x 16 KB
+// of boxes for the tanh' operand (the activations of the layer below, fetched by TMA one box ahead)
+template <int EPI>
 struct SmemPair {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = 128 * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_STAGE = 2 * 32 * 128;   // per epilogue warp: two 32 x 64 boxes (one being stored, one being filled)
-  static constexpr int TOTAL = P2_STAGES * STAGE_BYTES + EPI_WARPS * OUT_STAGE + 256 + 2048 + 1024;
+  static constexpr int STAGES = EPI == EPI_DTANH_BF16 ? 4 : 5;
+  static constexpr int BOX = 32 * 128;             // 32 rows x 64 bf16: one 128B-swizzled tensor-map box
+  static constexpr int OUT_STAGE = 2 * BOX;        // per epilogue warp: one box being stored, one being filled
+  static constexpr int AUX_STAGE = EPI == EPI_DTANH_BF16 ? 2 * BOX : 0;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_WARPS * (OUT_STAGE + AUX_STAGE) + 256 + 2048 + 1024;
 };
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c_inner, int c_outer) {
@@ -734,17 +740,22 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive o
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-            const __grid_constant__ CUtensorMap map_o, const __grid_constant__ GemmArgs g) {
-  static_assert(EPI == EPI_BIAS_TANH_BF16, "forward epilogue");
+            const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_x,
+            const __grid_constant__ GemmArgs g) {
+  static_assert(EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16, "forward or dgrad epilogue");
+  using SM = SmemPair<EPI>;
+  constexpr int P2_STAGES = SM::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* out_stage = smem + P2_STAGES * SmemPair::STAGE_BYTES;  // 1024-byte aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + EPI_WARPS * SmemPair::OUT_STAGE);
+  uint8_t* out_stage = smem + P2_STAGES * SM::STAGE_BYTES;  // 1024-byte aligned (and so is every box after it)
+  uint8_t* aux_stage = out_stage + EPI_WARPS * SM::OUT_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux_stage + EPI_WARPS * SM::AUX_STAGE);
   uint64_t* empty_bar = full_bar + P2_STAGES;
   uint64_t* tfull_bar = empty_bar + P2_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+  uint64_t* aux_bar = tempty_bar + 2;   // [EPI_WARPS][2] tanh'-operand box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * EPI_WARPS);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // forward: bias; dgrad: column sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const bool leader = rank == 0;
@@ -755,13 +766,15 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (threadIdx.x == 0) {
     for (int s = 0; s < P2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }
+    for (int b = 0; b < 2 * EPI_WARPS; ++b) mbar_init(&aux_bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // the same warp of both CTAs allocates all 512 columns of the pair's tensor memory
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < g.N; i += THREADS) bias_s[i] = __ldg(g.bias + i);   // N <= 512 (checked by the host)
+  for (int i = threadIdx.x; i < g.N; i += THREADS)   // N <= 512 (checked by the host)
+    bias_s[i] = EPI == EPI_BIAS_TANH_BF16 ? __ldg(g.bias + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
   cluster_sync();  // the peer's barriers are initialised before anything is signalled to them
@@ -775,10 +788,10 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const int m0 = (t / n_tiles) * (2 * BM) + rank * BM, n0 = (t % n_tiles) * P2_BN + rank * 128;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * SmemPair::STAGE_BYTES;
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * SmemPair::STAGE_BYTES);  // both CTAs' halves land on this barrier
+          uint8_t* sa = smem + s * SM::STAGE_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * SM::STAGE_BYTES);  // both CTAs' halves land on this barrier
           tma_load_2d_pair(sa, &map_a, &full_bar[s], kb * BK, m0);
-          tma_load_2d_pair(sa + SmemPair::A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
+          tma_load_2d_pair(sa + SM::A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
           if (++s == P2_STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -795,8 +808,8 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * SmemPair::STAGE_BYTES);
-          const uint64_t adesc = make_desc_k128(sa), bdesc = make_desc_k128(sa + SmemPair::A_BYTES);
+          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+          const uint64_t adesc = make_desc_k128(sa), bdesc = make_desc_k128(sa + SM::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
@@ -809,8 +822,14 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   } else {
     // ---- epilogue (both CTAs): this CTA's 128 rows x 256 columns, warp q = TMEM lane quarter
     const int q = warp & 3;
-    uint8_t* stage = out_stage + q * SmemPair::OUT_STAGE;
-    uint32_t lt = 0;
+    uint8_t* stage = out_stage + q * SM::OUT_STAGE;
+    uint8_t* xstage = aux_stage + q * SM::AUX_STAGE;
+    uint64_t* xbar = aux_bar + 2 * q;
+    uint32_t lt = 0, xbox = 0;   // xbox: boxes of the tanh' operand consumed so far (buffer = xbox & 1, phase = (xbox >> 1) & 1)
+    if (EPI == EPI_DTANH_BF16 && lane == 0 && pair < total_tiles) {   // the first box of the first tile
+      mbar_expect_tx(&xbar[0], SM::BOX);
+      tma_load_2d(xstage, &map_x, &xbar[0], (pair % n_tiles) * P2_BN, (pair / n_tiles) * (2 * BM) + rank * BM + q * 32);
+    }
     for (int t = pair; t < total_tiles; t += npairs, ++lt) {
       const int m0 = (t / n_tiles) * (2 * BM) + rank * BM + q * 32, n0 = (t % n_tiles) * P2_BN;
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
@@ -829,21 +848,64 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           __syncwarp();
         }
         const int col = n0 + 32 * ci;
+        const uint8_t* xb = xstage + (xbox & 1) * SM::BOX;   // (dgrad) the box of the tanh' operand for these 64 columns
+        if (EPI == EPI_DTANH_BF16 && (ci & 1) == 0) {
+          // request the NEXT box (same tile, or the first box of this warp's next tile) into the other buffer —
+          // its previous contents were consumed one box ago — then wait for this one
+          const bool last = ci + 2 >= P2_BN / 32;
+          const int tn = last ? t + npairs : t;
+          if (lane == 0 && tn < total_tiles) {
+            const int cn = last ? (tn % n_tiles) * P2_BN : col + 64;
+            const int rn = last ? (tn / n_tiles) * (2 * BM) + rank * BM + q * 32 : m0;
+            mbar_expect_tx(&xbar[(xbox + 1) & 1], SM::BOX);
+            tma_load_2d(xstage + ((xbox + 1) & 1) * SM::BOX, &map_x, &xbar[(xbox + 1) & 1], cn, rn);
+          }
+          mbar_wait(&xbar[xbox & 1], (xbox >> 1) & 1);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j);
-          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j + 4);
           const uint32_t* x = &v[ci & 1][8 * j];
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[0]) + b0.x), tanh_fast(__uint_as_float(x[1]) + b0.y));
-          __nv_bfloat162 p1 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[2]) + b0.z), tanh_fast(__uint_as_float(x[3]) + b0.w));
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[4]) + b1.x), tanh_fast(__uint_as_float(x[5]) + b1.y));
-          __nv_bfloat162 p3 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[6]) + b1.z), tanh_fast(__uint_as_float(x[7]) + b1.w));
           const int k = (ci & 1) * 4 + j;
+          float o[8];
+          if (EPI == EPI_BIAS_TANH_BF16) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = tanh_fast(__uint_as_float(x[i]) + bb[i]);
+          } else {  // acc * (1 - y^2), y = this row's activations of the layer below (same swizzled box layout)
+            const uint4 y4 = *reinterpret_cast<const uint4*>(xb + lane * 128 + ((k ^ (lane & 7)) << 4));
+            const uint32_t yy[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yy[i]);
+              const float ya = __bfloat162float(y2.x), yb = __bfloat162float(y2.y);
+              o[2 * i] = __uint_as_float(x[2 * i]) * (1.0f - ya * ya);
+              o[2 * i + 1] = __uint_as_float(x[2 * i + 1]) * (1.0f - yb * yb);
+            }
+          }
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
           *reinterpret_cast<uint4*>(box + lane * 128 + ((k ^ (lane & 7)) << 4)) =
               make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
                          *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
         }
         if (ci & 1) {
+          if (EPI == EPI_DTANH_BF16) {
+            __syncwarp();
+            if (g.colsum != nullptr) {
+              // bias gradient of the layer below: column sums of the (bf16-rounded) box, two columns per lane
+              float s0 = 0.0f, s1 = 0.0f;  // (rows past M were computed from zero-filled operands and hold zeros)
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const __nv_bfloat162 e = *reinterpret_cast<const __nv_bfloat162*>(box + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + 4 * (lane & 3));
+                s0 += __bfloat162float(e.x); s1 += __bfloat162float(e.y);
+              }
+              atomicAdd(bias_s + n0 + 32 * (ci - 1) + 2 * lane, s0);
+              atomicAdd(bias_s + n0 + 32 * (ci - 1) + 2 * lane + 1, s1);
+            }
+            ++xbox;
+          }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -860,6 +922,8 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if (EPI == EPI_DTANH_BF16 && g.colsum != nullptr)
+    for (int i = threadIdx.x; i < g.N; i += THREADS) atomicAdd(g.colsum + i, bias_s[i]);
   cluster_sync();  // no CTA leaves while its peer can still signal it or read its shared memory
   if (warp == 1) {
     tc_fence_after();
@@ -868,12 +932,12 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 }
 
 template <int EPI>
-static cudaError_t launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmArgs& g,
-                               cudaStream_t st) {
+static cudaError_t launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mx,
+                               const GemmArgs& g, cudaStream_t st) {
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_pair<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPair::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_pair<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPair<EPI>::TOTAL);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -883,12 +947,12 @@ static cudaError_t launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, con
   const long long tiles = (long long)((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / P2_BN);
   unsigned grid = (unsigned)std::min<long long>(2 * tiles, sms & ~1);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SmemPair::TOTAL; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SmemPair<EPI>::TOTAL; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_gemm_pair<EPI>, ma, mb, mo, g);
+  return cudaLaunchKernelEx(&cfg, k_gemm_pair<EPI>, ma, mb, mo, mx, g);
 }
 
 // ------------------------------------------------------------------------------- host side
@@ -1236,18 +1300,19 @@ VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int l
   // MLP at M = 131072; dgrad, whose epilogue also streams the aux tile, is 8 % slower with it and
   // stays on the streaming kernel). VSS_GEMM_WS=0/2 disables it / also enables it for dgrad (tuning).
   static const int ws_mode = getenv("VSS_GEMM_WS") ? atoi(getenv("VSS_GEMM_WS")) : 1;
-#ifndef VSS_NO_PAIR
-  // forward with N a multiple of 256 and enough row tiles: the CTA-pair kernel (tcgen05 cta_group::2)
-  if (epilogue == EPI_BIAS_TANH_BF16 && !mn_major && splits == 1 && N % 256 == 0 && N <= 512 && M >= 256 * 74) {
-    CUtensorMap ma2, mb2, mo2;  // A: 128-row boxes; B: 128-row boxes (this CTA's half of the 256 columns); out: 32 x 64 boxes
-    if (!make_map(&ma2, A, M, K, lda, BM) || !make_map(&mb2, B, N, K, ldb, 128) || !make_map(&mo2, out, M, N, ldo, 32)) {
-      g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA;
-    }
-    e = launch_pair<EPI_BIAS_TANH_BF16>(ma2, mb2, mo2, g, st);
+  // forward and dgrad with N a multiple of 256 and enough row tiles: the CTA-pair kernel (tcgen05 cta_group::2)
+  if ((epilogue == EPI_BIAS_TANH_BF16 || epilogue == EPI_DTANH_BF16) && !mn_major && splits == 1 && N % 256 == 0 &&
+      N <= 512 && M >= 256 * 74 && (epilogue != EPI_DTANH_BF16 || ld_aux % 8 == 0)) {
+    // A: 128-row boxes; B: 128-row boxes (this CTA's half of the 256 columns); out / tanh' operand: 32 x 64 boxes
+    CUtensorMap ma2, mb2, mo2, mx2;
+    bool ok2 = make_map(&ma2, A, M, K, lda, BM) && make_map(&mb2, B, N, K, ldb, 128) && make_map(&mo2, out, M, N, ldo, 32);
+    if (ok2) { if (epilogue == EPI_DTANH_BF16) ok2 = make_map(&mx2, aux, M, N, ld_aux, 32); else mx2 = mo2; }
+    if (!ok2) { g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA; }
+    e = epilogue == EPI_BIAS_TANH_BF16 ? launch_pair<EPI_BIAS_TANH_BF16>(ma2, mb2, mo2, mx2, g, st)
+                                       : launch_pair<EPI_DTANH_BF16>(ma2, mb2, mo2, mx2, g, st);
     if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn (pair): ") + cudaGetErrorString(e); return VSS_E_CUDA; }
     return VSS_OK;
   }
-#endif
   if (ws_mode && !colsum && !mn_major && splits == 1 && bn == 128 && K <= 512 && N <= 512 && M >= 128 * 148 &&
       (epilogue == EPI_BIAS_TANH_BF16 || (ws_mode == 2 && epilogue == EPI_DTANH_BF16))) {
     CUtensorMap mo;  // the bf16 output as 32-row x 64-column boxes for the epilogue's bulk tensor stores

@@ -61,11 +61,10 @@ def test_dgrad_fused_tanh_derivative():
 
 
 @pytest.mark.parametrize("M,N_out,K_in", [(131072, 512, 512), (128 * 148 + 77, 256, 512), (40000, 512, 256)])
-def test_dgrad_cluster_multicast_path(M, N_out, K_in, monkeypatch):
-    """VSS_GEMM_CLUSTER=1, M >= 128 * 148 and k_in % 256 == 0: pairs of CTAs share the dZ tile through
-    TMA multicast (the knob is read on every call)."""
+def test_dgrad_cta_pair_path(M, N_out, K_in):
+    """M >= 18 944 and k_in % 256 == 0: the CTA-pair kernel (tcgen05 cta_group::2) with the tanh' operand fetched
+    by TMA and the bias gradient of the layer below (column sums of the bf16 output) from the epilogue."""
     from rsoccer_isaac_cleanrl_b200.engine import EPI_DTANH_BF16, gemm_bf16
-    monkeypatch.setenv("VSS_GEMM_CLUSTER", "1")
     dz, wt = _rand((M, N_out), 15), _rand((K_in, N_out), 16, N_out ** -0.5)
     y = torch.tanh(_rand((M, K_in), 17).float()).to(torch.bfloat16)
     out = torch.empty((M, K_in), device="cuda", dtype=torch.bfloat16)
@@ -73,8 +72,11 @@ def test_dgrad_cluster_multicast_path(M, N_out, K_in, monkeypatch):
     ref = (dz.float() @ wt.float().t()) * (1 - y.float() ** 2)
     assert (out.float() - ref).abs().max().item() < 3e-2
     out2 = torch.empty_like(out)
-    gemm_bf16(dz, wt, out2, EPI_DTANH_BF16, aux=y)
+    colsum = torch.zeros(K_in, device="cuda")
+    gemm_bf16(dz, wt, out2, EPI_DTANH_BF16, aux=y, colsum=colsum)
     assert torch.equal(out, out2)
+    want = out.double().sum(0)
+    assert (colsum.double() - want).abs().max().item() < 2e-3 * want.abs().max().item() + 1e-2
 
 
 @pytest.mark.parametrize("batch,N_out,K_in,splits", [(4096, 256, 64, 8), (8192, 512, 256, 16), (4000, 512, 512, 7),
