@@ -79,8 +79,11 @@ def test_dgrad_cta_pair_path(M, N_out, K_in):
     assert (colsum.double() - want).abs().max().item() < 2e-3 * want.abs().max().item() + 1e-2
 
 
+# (batch >= 18 944 with both sides of dW multiples of 256 takes the CTA-pair wgrad kernel, which chooses its own
+# batch slices: ragged batch, 1 x 2, 2 x 1 and 2 x 2 blocks of dW)
 @pytest.mark.parametrize("batch,N_out,K_in,splits", [(4096, 256, 64, 8), (8192, 512, 256, 16), (4000, 512, 512, 7),
-                                                     (131072, 256, 512, 32)])
+                                                     (131072, 256, 512, 32), (131072, 512, 512, 18), (40003, 512, 256, 9),
+                                                     (131072, 256, 64, 49)])
 @pytest.mark.parametrize("cluster,bn256", [("0", "2"), ("1", "0"), ("0", "0")])
 def test_wgrad_mn_major_split_k(batch, N_out, K_in, splits, cluster, bn256, monkeypatch):
     """Default 128x256 tiles, the 2-CTA multicast variant and plain 128x128 tiles."""
