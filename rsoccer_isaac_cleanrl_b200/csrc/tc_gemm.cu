@@ -84,15 +84,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
 }
-// The same load delivered to the same shared-memory offset of every CTA of the cluster whose bit is
-// set in cta_mask; each destination CTA's mbarrier (same offset) receives the complete_tx.
-__device__ __forceinline__ void tma_load_2d_multicast(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
-                                                      int c_outer, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "h"(cta_mask) : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -119,11 +110,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// commit that arrives on the mbarrier at the same offset in every CTA of cta_mask
-__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -341,18 +327,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m_ba
 // CTAs working at the same time share A rows through L2). The accumulator is double-buffered in TMEM
 // (2 x BN columns): the MMA warp fills buffer (i+1)&1 while the epilogue warps drain buffer i&1, and the
 // TMA producer runs ahead across tile boundaries through the smem ring.
-//
-// CL = 2: the CTAs are launched as clusters of two that work on horizontally adjacent tiles (same rows
-// of A, neighbouring column blocks of B). Each CTA fetches HALF of the A tile and multicasts it into
-// both CTAs' shared memory, so a CTA pulls 24 KB instead of 32 KB per k-block through L2 — the kernel
-// is bound by that feed (~42 B/clk/SM), not by the tensor pipe. A stage may be refilled only when
-// BOTH CTAs' MMAs have read it: the MMA issuer's tcgen05.commit arrives on the empty barrier of both
-// CTAs (multicast), and the barrier counts two arrivals.
-template <int BN, int EPI, bool MN, int CL>
+template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(THREADS, 2)
 k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ GemmArgs g) {
-  static_assert(CL == 1 || CL == 2, "cluster of one or two CTAs");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Smem<BN>::NSTAGES * Smem<BN>::STAGE_BYTES);
@@ -368,14 +346,10 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const int tiles_per_split = n_tiles * m_tiles;
   const int total_tiles = tiles_per_split * g.splits;
   const int total_kb = g.K / BK;
-  // tile walk: cluster c takes tile groups c, c + #clusters, ...; rank r of the cluster takes tile CL * group + r
-  // (n-tile fastest and n_tiles % CL == 0, so a group shares its A rows and its K-split)
-  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-  const int t_begin = (blockIdx.x / CL) * CL + crank, t_step = (gridDim.x / CL) * CL;
-  constexpr uint16_t CL_MASK = (1u << CL) - 1u;
+  const int t_begin = blockIdx.x, t_step = gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Smem<BN>::NSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
+    for (int s = 0; s < Smem<BN>::NSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -389,7 +363,6 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     for (int i = threadIdx.x; i < g.N; i += THREADS) colsum_s[i] = 0.0f;
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -405,19 +378,13 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Smem<BN>::STAGE_BYTES;
           uint8_t* sb = sa + Smem<BN>::A_BYTES;
-          mbar_expect_tx(&full_bar[s], Smem<BN>::STAGE_BYTES);  // (CL = 2: half of the A bytes come from the peer)
+          mbar_expect_tx(&full_bar[s], Smem<BN>::STAGE_BYTES);
           if (!MN) {
-            if (CL == 1) tma_load_2d(sa, &map_a, &full_bar[s], (kb0 + kb) * BK, m0);
-            else  // rows [64 r, 64 r + 64) of the A tile (the map's box is 64 rows) into both CTAs
-              tma_load_2d_multicast(sa + crank * 8192, &map_a, &full_bar[s], (kb0 + kb) * BK, m0 + 64 * crank, CL_MASK);
+            tma_load_2d(sa, &map_a, &full_bar[s], (kb0 + kb) * BK, m0);
             tma_load_2d(sb, &map_b, &full_bar[s], (kb0 + kb) * BK, n0);
           } else {  // source tensors are [K, M] / [K, N]: 64 x 64 boxes, inner coordinate = m / n
-            if (CL == 1) {
 #pragma unroll
-              for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &map_a, &full_bar[s], m0 + 64 * i, (kb0 + kb) * BK);
-            } else {
-              tma_load_2d_multicast(sa + crank * 8192, &map_a, &full_bar[s], m0 + 64 * crank, (kb0 + kb) * BK, CL_MASK);
-            }
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &map_a, &full_bar[s], m0 + 64 * i, (kb0 + kb) * BK);
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &map_b, &full_bar[s], n0 + 64 * i, (kb0 + kb) * BK);
           }
@@ -448,8 +415,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_bf16(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
-          // frees the smem stage when these MMAs retire (in both CTAs of a cluster: the peer fills half of it)
-          if (CL == 1) umma_commit(&empty_bar[s]); else umma_commit_multicast(&empty_bar[s], CL_MASK);
+          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
           if (++s == Smem<BN>::NSTAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[buf]);  // accumulator complete
@@ -508,185 +474,6 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   __syncthreads();
   if (colsum_s)
     for (int i = threadIdx.x; i < g.N; i += THREADS) atomicAdd(g.colsum + i, colsum_s[i]);
-  if (CL > 1) cluster_sync();  // no CTA leaves while its peer can still multicast data or arrivals into it
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
-  }
-}
-
-// Weight-stationary variant for the forward / dgrad GEMMs (K-major, K <= 512, N % 128 == 0).
-// With the B tile streamed per k-block the kernel above moves 32 KB of shared memory per 2 MFLOP
-// (64 FLOP/B) and saturates the ~42 B/clk/SM that L2 can deliver long before the tensor core.
-// Here one CTA per SM owns one 128-column slice of the weights, loads it ONCE (K/64 x 16 KB, stays
-// resident), and streams only the activation tiles (16 KB per k-block = 128 FLOP/B) through a 4-stage
-// ring while walking its share of the M tiles; accumulators are double-buffered in TMEM as above.
-constexpr int WS_MAX_KB = 8;        // K <= 512
-constexpr int WS_MAX_STAGES = 12;
-// Epilogue warps of the weight-stationary kernel (one CTA per SM). 8 (two per TMEM lane quarter, half
-// of the 128 columns each) was measured slower: K = 512 105 vs 93 us, K = 256 72 vs 70 us — their 10 KB
-// of extra staging cost one stage of the activation ring, and the epilogue is not issue-bound.
-constexpr int WS_EPI_WARPS = 4;
-constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
-struct SmemWS {
-  static constexpr int A_BYTES = BM * BK * 2;                    // 16 KB per stage
-  static constexpr int KB_BYTES = 128 * BK * 2;                  // 16 KB of resident weights per k-block
-  static constexpr int OUT_STAGE = 32 * 128;                     // per epilogue warp: 32 rows x 64 bf16, 128B-swizzled TMA box
-  static constexpr int TAIL = 1024 + 256 + 2048 + WS_EPI_WARPS * OUT_STAGE;  // align slack, barriers, bias, output staging
-  static constexpr int BUDGET = 226 * 1024;                      // dynamic shared memory per CTA (227 KB max)
-  // Depth of the activation ring. Measured at M = 131072, N = 512: K = 256 -> 74 us with 4 stages,
-  // 69 us with 9; K = 512 -> 93 us with 4 stages, 104 us with 5 (the last 16 KB of shared memory
-  // are better left to L1). So: as deep as fits below ~208 KB.
-  // (212 KB: K = 512 keeps its 4 stages beside the 16 KB of output staging)
-  static int stages(int nkb) { return std::min(WS_MAX_STAGES, (212 * 1024 - TAIL - nkb * KB_BYTES) / A_BYTES); }
-  static int total(int nkb) { return nkb * KB_BYTES + stages(nkb) * A_BYTES + TAIL; }
-};
-
-template <int EPI>
-__global__ void __launch_bounds__(WS_THREADS, 1)
-k_gemm_ws(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-          const __grid_constant__ CUtensorMap map_o, const __grid_constant__ GemmArgs g) {
-  constexpr int BN = 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int nkb = g.K / BK;
-  const uint32_t nst = (uint32_t)g.ws_stages;   // depth of the activation ring (host: SmemWS::stages)
-  uint8_t* smem_b = smem;
-  uint8_t* smem_a = smem + nkb * SmemWS::KB_BYTES;
-  uint8_t* out_stage = smem_a + nst * SmemWS::A_BYTES;   // 1024-byte aligned: the swizzle pattern is address-based
-  uint8_t* tail = out_stage + WS_EPI_WARPS * SmemWS::OUT_STAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_bar = full_bar + WS_MAX_STAGES;
-  uint64_t* tfull_bar = empty_bar + WS_MAX_STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* b_bar = tempty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
-  float* bias_s = reinterpret_cast<float*>(tail + 256);
-  uint8_t* stage = out_stage + (((threadIdx.x >> 5) + WS_EPI_WARPS - 2) % WS_EPI_WARPS) * SmemWS::OUT_STAGE;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = g.N / BN, m_tiles = (g.M + BM - 1) / BM;
-  // CTA c owns column slice c % n_tiles and the M tiles c / n_tiles, + gridDim.x / n_tiles, ...
-  const int n0 = (blockIdx.x % n_tiles) * BN;
-  const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
-
-  if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], WS_EPI_WARPS); }
-    mbar_init(b_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
-  const bool bias_in_smem = (EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_BIAS_F32) && g.bias != nullptr && g.N <= 512;
-  if (bias_in_smem)
-    for (int i = threadIdx.x; i < g.N; i += WS_THREADS) bias_s[i] = __ldg(g.bias + i);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer: the weight slice once, then activation tiles
-      mbar_expect_tx(b_bar, (uint32_t)nkb * SmemWS::KB_BYTES);
-      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem_b + kb * SmemWS::KB_BYTES, &map_b, b_bar, kb * BK, n0);
-      uint32_t s = 0, ph = 0;  // ring position and phase, advanced without divisions
-      for (int mt = m_first; mt < m_tiles; mt += m_step) {
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], SmemWS::A_BYTES);
-          tma_load_2d(smem_a + s * SmemWS::A_BYTES, &map_a, &full_bar[s], kb * BK, mt * BM);
-          if (++s == nst) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer
-      constexpr uint32_t idesc = make_idesc(BM, BN, false);
-      mbar_wait(b_bar, 0);
-      uint32_t s = 0, ph = 0, lt = 0;
-      for (int mt = m_first; mt < m_tiles; mt += m_step, ++lt) {
-        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-        mbar_wait(&tempty_bar[buf], bph ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint64_t adesc = make_desc_k128(smem_u32(smem_a + s * SmemWS::A_BYTES));
-          const uint64_t bdesc = make_desc_k128(smem_u32(smem_b + kb * SmemWS::KB_BYTES));
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty_bar[s]);
-          if (++s == nst) { s = 0; ph ^= 1; }
-        }
-        umma_commit(&tfull_bar[buf]);
-      }
-    }
-  } else {  // ---- epilogue
-    const int q = warp & 3;                              // TMEM lane quarter this warp may touch
-    constexpr int COLS_PER_WARP = BN / (WS_EPI_WARPS / 4);  // column share of this warp within the quarter
-    const int c_begin = ((warp - 2) >> 2) * COLS_PER_WARP;
-    uint32_t lt = 0;
-    for (int mt = m_first; mt < m_tiles; mt += m_step, ++lt) {
-      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-      mbar_wait(&tfull_bar[buf], bph);
-      tc_fence_after();
-      // The four 32-column chunks of this warp's rows, software-pipelined: the TMEM load of chunk c + 1 is in
-      // flight while chunk c goes through bias + tanh + stores (with one load at a time every chunk exposed the
-      // full tcgen05.ld latency: with one CTA per SM nothing else runs on the epilogue warps' schedulers).
-      static_assert(COLS_PER_WARP == 128, "four chunks per warp");
-      uint32_t v[2][32];
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c_begin;
-      tmem_ld32_issue(t0, v[0]);
-#pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        tmem_ld_wait();
-        if (ci + 1 < 4) tmem_ld32_issue(t0 + 32u * (ci + 1), v[(ci + 1) & 1]);
-        if (EPI == EPI_BIAS_TANH_BF16) {
-          // bias + tanh -> bf16 -> this warp's 32 x 64 staging box (128-byte rows, 16-byte chunk k of row r at
-          // position k ^ (r & 7): the layout of a SWIZZLE_128B tensor-map box, and conflict-free for STS.128);
-          // after two chunks ONE bulk tensor store writes the 32 x 128-byte box. (Direct 16-byte stores of one
-          // row per lane sent every 32-byte sector to L2 twice and kept L1TEX 70 % busy: ncu, profiles/r02_k.)
-          if ((ci & 1) == 0) {  // the previous box must have been read out of shared memory
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-          }
-          const int col = n0 + c_begin + 32 * ci;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j + 4);
-            const uint32_t* x = &v[ci & 1][8 * j];
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[0]) + b0.x), tanh_fast(__uint_as_float(x[1]) + b0.y));
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[2]) + b0.z), tanh_fast(__uint_as_float(x[3]) + b0.w));
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[4]) + b1.x), tanh_fast(__uint_as_float(x[5]) + b1.y));
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(tanh_fast(__uint_as_float(x[6]) + b1.z), tanh_fast(__uint_as_float(x[7]) + b1.w));
-            const int k = (ci & 1) * 4 + j;
-            *reinterpret_cast<uint4*>(stage + lane * 128 + ((k ^ (lane & 7)) << 4)) =
-                make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                           *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-          }
-          if (ci & 1) {
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&map_o, stage, n0 + c_begin + 32 * (ci - 1), mt * BM + q * 32);
-              tma_store_commit();
-            }
-          }
-        } else {
-          epilogue_chunk<EPI>(v[ci & 1], mt * BM + q * 32, lane, n0 + c_begin + 32 * ci, g, bias_s, bias_in_smem, stage);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-    }
-    if (EPI == EPI_BIAS_TANH_BF16 && lane == 0) tma_store_wait_all();  // the last boxes have left shared memory and landed
-  }
-  tc_fence_before();
-  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
@@ -1130,31 +917,11 @@ static bool make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int EPI>
-static cudaError_t launch_ws(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, GemmArgs g, cudaStream_t st) {
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemWS::BUDGET);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
-  }
-  const int n_tiles = g.N / 128, m_tiles = (g.M + BM - 1) / BM;
-  int per_slice = std::min(std::max(sms / n_tiles, 1), m_tiles);   // CTAs per column slice
-  const int nkb = g.K / BK;
-  g.ws_stages = SmemWS::stages(nkb);
-  k_gemm_ws<EPI><<<per_slice * n_tiles, WS_THREADS, SmemWS::total(nkb), st>>>(ma, mb, mo, g);
-  return cudaGetLastError();
-}
-
-template <int BN, int EPI, bool MN, int CL = 1>
+template <int BN, int EPI, bool MN>
 static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tn<BN, EPI, MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tn<BN, EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Smem<BN>::TOTAL);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -1169,18 +936,8 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Ge
   const int resident = BN == 256 ? max_ctas / 2 : max_ctas;  // 128x256 tiles: 144 KB smem + all 512 TMEM columns
   const long long tiles = (long long)((g.M + BM - 1) / BM) * (g.N / BN) * splits;
   unsigned grid = (unsigned)std::min<long long>(tiles, resident);
-  if (CL == 1) {
-    k_gemm_tn<BN, EPI, MN, 1><<<grid, THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
-    return cudaGetLastError();
-  }
-  grid -= grid % CL;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Smem<BN>::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_gemm_tn<BN, EPI, MN, CL>, ma, mb, g);
+  k_gemm_tn<BN, EPI, MN><<<grid, THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
+  return cudaGetLastError();
 }
 
 }  // namespace tc
@@ -1405,26 +1162,13 @@ VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int l
   if ((epilogue == EPI_BIAS_TANH_BF16 && !bias) || (epilogue == EPI_DTANH_BF16 && !aux)) {
     g_tc_error = "vss_gemm_bf16_tn: missing bias/aux"; return VSS_E_INVALID;
   }
-  // tile width: 256 (tuning knob VSS_GEMM_BN256, bit 0 = dgrad, bit 1 = wgrad) raises the FLOP per
-  // operand byte from 64 to 85 at the price of one CTA per SM. Measured at minibatch 131072: wgrad
-  // 512x512 79 us vs 87 us with 128x128 tiles (default: on); dgrad 131 vs 107 us (default: off)
-  const char* bn_env = getenv("VSS_GEMM_BN256");
-  const int bn256 = bn_env ? atoi(bn_env) : 2;
+  // tile width of the one-CTA kernel: 128 x 256 for the split-K wgrad shapes that do not reach the CTA-pair kernel
+  // (short reductions), else 128 x 128 / 128 x 64
   int bn = (N % 128 == 0) ? 128 : 64;
-  if (N % 256 == 0 && (((bn256 & 1) && epilogue == EPI_DTANH_BF16 && !mn_major && M >= 128 * 148) ||
-                       ((bn256 & 2) && epilogue == EPI_ATOMIC_F32 && mn_major)))
-    bn = 256;
-  // VSS_GEMM_CLUSTER=1: clusters of two CTAs sharing the A tile by TMA multicast (dgrad and wgrad of
-  // the 512-wide layers). Off by default: measured equal to unicast at minibatch 131072 (dgrad 108.7
-  // vs 108.6 us) — L2 already merges the same line requested by up to ~4 CTAs close in time, so a
-  // pair saves no L2 bandwidth. Read per call so that tests can switch it.
-  const char* cluster_env = getenv("VSS_GEMM_CLUSTER");
-  const int cluster_mode = cluster_env ? atoi(cluster_env) : 0;
-  const bool clustered = cluster_mode && bn == 128 && N % 256 == 0 && M >= (mn_major ? 128 : 128 * 148) &&
-                         ((epilogue == EPI_DTANH_BF16 && !mn_major) || (epilogue == EPI_ATOMIC_F32 && mn_major));
+  if (N % 256 == 0 && epilogue == EPI_ATOMIC_F32 && mn_major) bn = 256;
   CUtensorMap ma, mb;
   const bool ok = mn_major ? (make_map(&ma, A, K, M, lda, BK) && make_map(&mb, B, K, N, ldb, BK))
-                           : (make_map(&ma, A, M, K, lda, clustered ? BM / 2 : BM) && make_map(&mb, B, N, K, ldb, bn));
+                           : (make_map(&ma, A, M, K, lda, BM) && make_map(&mb, B, N, K, ldb, bn));
   if (!ok) {
     g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA;
   }
@@ -1439,53 +1183,6 @@ VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int l
   g.colsum = colsum;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-  // forward with enough M tiles per SM: weight-stationary kernel (measured: forward 257 -> 244 us per
-  // MLP at M = 131072; dgrad, whose epilogue also streams the aux tile, is 8 % slower with it and
-  // stays on the streaming kernel). VSS_GEMM_WS=0/2 disables it / also enables it for dgrad (tuning).
-  static const int ws_mode = getenv("VSS_GEMM_WS") ? atoi(getenv("VSS_GEMM_WS")) : 1;
-  // wgrad with 256-multiples on both sides of dW and a long reduction: the CTA-pair kernel; the batch is cut into
-  // as many slices as there are CTA pairs per 256 x 256 block of dW (one wave)
-  if (epilogue == EPI_ATOMIC_F32 && mn_major && M % 256 == 0 && N % 256 == 0 && K >= 64 * 74 * 4) {
-    CUtensorMap ma2, mb2;
-    if (!make_map(&ma2, A, K, M, lda, BK) || !make_map(&mb2, B, K, N, ldb, BK)) {
-      g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA;
-    }
-    const int blocks = (M / 256) * (N / 256);
-    const int want = std::max(1, 74 / blocks);
-    g.k_blocks_per_split = (total_kb + want - 1) / want;
-    g.splits = (total_kb + g.k_blocks_per_split - 1) / g.k_blocks_per_split;
-    e = launch_pair_wgrad(ma2, mb2, g, st);
-    if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn (pair wgrad): ") + cudaGetErrorString(e); return VSS_E_CUDA; }
-    return VSS_OK;
-  }
-  // forward and dgrad with N a multiple of 256 and enough row tiles: the CTA-pair kernel (tcgen05 cta_group::2)
-  if ((epilogue == EPI_BIAS_TANH_BF16 || epilogue == EPI_DTANH_BF16) && !mn_major && splits == 1 && N % 256 == 0 &&
-      N <= 512 && M >= 256 * 74 && (epilogue != EPI_DTANH_BF16 || ld_aux % 8 == 0)) {
-    // A: 128-row boxes; B: 128-row boxes (this CTA's half of the 256 columns); out / tanh' operand: 32 x 64 boxes
-    CUtensorMap ma2, mb2, mo2, mx2;
-    bool ok2 = make_map(&ma2, A, M, K, lda, BM) && make_map(&mb2, B, N, K, ldb, 128) && make_map(&mo2, out, M, N, ldo, 32);
-    if (ok2) { if (epilogue == EPI_DTANH_BF16) ok2 = make_map(&mx2, aux, M, N, ld_aux, 32); else mx2 = mo2; }
-    if (!ok2) { g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA; }
-    e = epilogue == EPI_BIAS_TANH_BF16 ? launch_pair<EPI_BIAS_TANH_BF16>(ma2, mb2, mo2, mx2, g, st)
-                                       : launch_pair<EPI_DTANH_BF16>(ma2, mb2, mo2, mx2, g, st);
-    if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn (pair): ") + cudaGetErrorString(e); return VSS_E_CUDA; }
-    return VSS_OK;
-  }
-  if (ws_mode && !colsum && !mn_major && splits == 1 && bn == 128 && K <= 512 && N <= 512 && M >= 128 * 148 &&
-      (epilogue == EPI_BIAS_TANH_BF16 || (ws_mode == 2 && epilogue == EPI_DTANH_BF16))) {
-    CUtensorMap mo;  // the bf16 output as 32-row x 64-column boxes for the epilogue's bulk tensor stores
-    if (!make_map(&mo, out, M, N, ldo, 32)) { g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled (output) failed"; return VSS_E_CUDA; }
-    e = epilogue == EPI_BIAS_TANH_BF16 ? launch_ws<EPI_BIAS_TANH_BF16>(ma, mb, mo, g, st)
-                                       : launch_ws<EPI_DTANH_BF16>(ma, mb, mo, g, st);
-    if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
-    return VSS_OK;
-  }
-  if (clustered) {
-    e = mn_major ? launch<128, EPI_ATOMIC_F32, true, 2>(ma, mb, g, splits, st)
-                 : launch<128, EPI_DTANH_BF16, false, 2>(ma, mb, g, splits, st);
-    if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }
-    return VSS_OK;
-  }
 #define TC_CASE(BNV, EPIV, MNV) \
   if (bn == BNV && epilogue == EPIV && (mn_major != 0) == MNV) e = launch<BNV, EPIV, MNV>(ma, mb, g, splits, st); else
   TC_CASE(128, EPI_BIAS_TANH_BF16, false) TC_CASE(64, EPI_BIAS_TANH_BF16, false)
@@ -1493,7 +1190,7 @@ VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int l
   TC_CASE(128, EPI_ATOMIC_F32, false) TC_CASE(64, EPI_ATOMIC_F32, false)
   TC_CASE(128, EPI_BIAS_F32, false) TC_CASE(64, EPI_BIAS_F32, false)
   TC_CASE(128, EPI_ATOMIC_F32, true) TC_CASE(64, EPI_ATOMIC_F32, true)
-  TC_CASE(256, EPI_DTANH_BF16, false) TC_CASE(256, EPI_ATOMIC_F32, true)
+  TC_CASE(256, EPI_ATOMIC_F32, true)
   { g_tc_error = "vss_gemm_bf16_tn: unsupported epilogue / layout combination"; return VSS_E_INVALID; }
 #undef TC_CASE
   if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn: ") + cudaGetErrorString(e); return VSS_E_CUDA; }

@@ -345,7 +345,7 @@ def train(args, log=print, hook=None):
         k0 = mw_actor.k0
         # the critic runs beside the actor on a second stream (fork/join inside the captured graphs): at
         # 4096 rows one network's GEMMs fill less than half of the SMs
-        side = torch.cuda.Stream(device=device) if os.environ.get("VSS_PPO_TWO_STREAMS", "1") != "0" else None
+        side = torch.cuda.Stream(device=device)
 
     def on_side(fn):
         """Run fn() on the side stream, ordered after everything queued so far on the current one.
