@@ -148,8 +148,13 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // fp32 reduction of four consecutive floats (16-byte aligned) in one L2 operation: split-K partial sums
+// (p not 16-byte aligned — a gradient view at an odd offset of a flat buffer — falls back to four scalar reductions)
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  } else {
+    atomicAdd(p, a); atomicAdd(p + 1, b); atomicAdd(p + 2, c); atomicAdd(p + 3, d);
+  }
 }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -1183,6 +1188,19 @@ VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int l
   g.colsum = colsum;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
+  // forward and dgrad with N a multiple of 256 and enough row tiles: the CTA-pair kernel (tcgen05 cta_group::2)
+  if ((epilogue == EPI_BIAS_TANH_BF16 || epilogue == EPI_DTANH_BF16) && !mn_major && splits == 1 && N % 256 == 0 &&
+      N <= 512 && M >= 256 * 74 && (epilogue != EPI_DTANH_BF16 || ld_aux % 8 == 0)) {
+    // A: 128-row boxes; B: 128-row boxes (this CTA's half of the 256 columns); out / tanh' operand: 32 x 64 boxes
+    CUtensorMap ma2, mb2, mo2, mx2;
+    bool ok2 = make_map(&ma2, A, M, K, lda, BM) && make_map(&mb2, B, N, K, ldb, 128) && make_map(&mo2, out, M, N, ldo, 32);
+    if (ok2) { if (epilogue == EPI_DTANH_BF16) ok2 = make_map(&mx2, aux, M, N, ld_aux, 32); else mx2 = mo2; }
+    if (!ok2) { g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA; }
+    e = epilogue == EPI_BIAS_TANH_BF16 ? launch_pair<EPI_BIAS_TANH_BF16>(ma2, mb2, mo2, mx2, g, st)
+                                       : launch_pair<EPI_DTANH_BF16>(ma2, mb2, mo2, mx2, g, st);
+    if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn (pair): ") + cudaGetErrorString(e); return VSS_E_CUDA; }
+    return VSS_OK;
+  }
 #define TC_CASE(BNV, EPIV, MNV) \
   if (bn == BNV && epilogue == EPIV && (mn_major != 0) == MNV) e = launch<BNV, EPIV, MNV>(ma, mb, g, splits, st); else
   TC_CASE(128, EPI_BIAS_TANH_BF16, false) TC_CASE(64, EPI_BIAS_TANH_BF16, false)

@@ -146,16 +146,20 @@ def flatten_parameters(module):
     """Re-home every parameter (and its .grad) as a view of one flat buffer, so the gradient
     all-reduce, the norm clip and Adam each touch ONE tensor."""
     params = list(module.parameters())
-    total = sum(p.numel() for p in params)
-    flat = torch.zeros(total, device=params[0].device, dtype=params[0].dtype)
-    flat_grad = torch.zeros_like(flat)
-    off = 0
+    # every tensor starts on a 16-byte boundary (the 1-element biases of the value head would otherwise leave all
+    # later tensors at odd offsets: the split-K wgrad reduces with 16-byte vector atomics); the padding words stay
+    # zero in the parameters, the gradient and the Adam moments
+    starts, off = [], 0
     for p in params:
+        starts.append(off)
+        off += (p.numel() + 3) // 4 * 4
+    flat = torch.zeros(off, device=params[0].device, dtype=params[0].dtype)
+    flat_grad = torch.zeros_like(flat)
+    for p, o in zip(params, starts):
         n = p.numel()
-        flat[off:off + n].copy_(p.data.view(-1))
-        p.data = flat[off:off + n].view_as(p.data)
-        p.grad = flat_grad[off:off + n].view_as(p.data)
-        off += n
+        flat[o:o + n].copy_(p.data.view(-1))
+        p.data = flat[o:o + n].view_as(p.data)
+        p.grad = flat_grad[o:o + n].view_as(p.data)
     return flat, flat_grad
 
 
