@@ -360,6 +360,7 @@ def run_ppo_leg(torch, world, env_id, agents, updates):
                        f"{st['updates']} updates, defaults of ppo…:71-108",
            "rollout_s": st["rollout_s"], "update_s": st["update_s"], "wall_s": st["wall"],
            "mlp_backend": st.get("mlp_backend", "torch-fp32"), "nccl_in_graph": st.get("nccl_in_graph"),
+           "grad_allreduce": st.get("grad_allreduce"),
            "sanitised_fields": st.get("sanitised_fields"), "n_gpus": world}
     del st
     torch.cuda.empty_cache()

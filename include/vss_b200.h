@@ -331,6 +331,32 @@ VSS_API int vss_clip_adam(float* params, float* grads, float* exp_avg, float* ex
                           float grad_scale, float max_grad_norm, float beta1, float beta2, float eps, void* stream);
 VSS_API const char* vss_ppo_last_error(void);
 
+/* ---- the PPO gradient all-reduce over NVLink peer memory (csrc/peer_reduce.cu) -----------------------
+ * Replaces `torch.distributed.all_reduce(flat_grad)` — the data-parallel form of the reference's
+ * single-GPU `loss.backward(); clip_grad_norm_; optimizer.step()` (ppo…:352-354) — for the ranks of ONE
+ * node: one process per GPU, every rank keeps its flat gradient in a buffer of its vss_peer group that
+ * the other ranks map through CUDA IPC, and vss_peer_allreduce is ONE kernel per rank that synchronises
+ * with the peers through flag words in those buffers and sums all P gradients in rank order (bit-
+ * identical results on all ranks), with no host involvement; graph-capturable.
+ *   vss_peer_create      allocates the group's buffer on `device` (num_floats floats, rounded up to 4)
+ *   vss_peer_ipc_handle  64 opaque bytes to hand to the other ranks (any host-side exchange, e.g.
+ *                        torch.distributed.all_gather)
+ *   vss_peer_connect     all_handles = world x 64 bytes in rank order (own entry ignored)
+ *   vss_peer_buffer      the rank's gradient buffer (device pointer): the backward pass accumulates here
+ *   vss_peer_allreduce   out_sum[i] = sum over ranks of buffer_rank[i]; when it has completed on the
+ *                        stream the rank's buffer may be overwritten. Collective: every rank must
+ *                        call it the same number of times. */
+typedef struct vss_peer_group* vss_peer;
+#define VSS_PEER_HANDLE_BYTES 64
+VSS_API int vss_peer_create(vss_peer* out, int device, int rank, int world, int64_t num_floats);
+VSS_API int vss_peer_ipc_handle(vss_peer h, void* handle64);
+VSS_API int vss_peer_connect(vss_peer h, const void* all_handles);
+VSS_API float* vss_peer_buffer(vss_peer h);
+VSS_API int64_t vss_peer_num_floats(vss_peer h);
+VSS_API int vss_peer_allreduce(vss_peer h, float* out_sum, void* stream);
+VSS_API int vss_peer_destroy(vss_peer h);
+VSS_API const char* vss_peer_last_error(void);
+
 /* Philox4x32-10 known-answer hook (host side; same code as the device generator). */
 VSS_API void vss_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

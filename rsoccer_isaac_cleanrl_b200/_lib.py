@@ -94,6 +94,14 @@ _SYMBOLS = {
     "vss_clip_adam": (C.c_int, [_VP] * 4 + [C.c_int64, _VP, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                             _VP]),
     "vss_ppo_last_error": (C.c_char_p, []),
+    "vss_peer_create": (C.c_int, [C.POINTER(_VP), C.c_int, C.c_int, C.c_int, C.c_int64]),
+    "vss_peer_ipc_handle": (C.c_int, [_VP, _VP]),
+    "vss_peer_connect": (C.c_int, [_VP, _VP]),
+    "vss_peer_buffer": (_VP, [_VP]),
+    "vss_peer_num_floats": (C.c_int64, [_VP]),
+    "vss_peer_allreduce": (C.c_int, [_VP, _VP, _VP]),
+    "vss_peer_destroy": (C.c_int, [_VP]),
+    "vss_peer_last_error": (C.c_char_p, []),
     "vss_philox4x32_10": (None, [_VP, _VP, _VP]),
     "vss_last_error": (C.c_char_p, []),
     "vss_version": (C.c_char_p, []),

@@ -79,6 +79,9 @@ def parse_args(argv=None):
                    help="tc: hand-written tcgen05 GEMMs (bf16 in, fp32 accumulate); torch: fp32 library GEMMs")
     p.add_argument("--cuda-graph", type=b, default=True, nargs="?", const=True,
                    help="capture the whole T-step rollout (+ critic on terminal obs + GAE) in one CUDA graph")
+    p.add_argument("--grad-allreduce", type=str, default="auto", choices=["auto", "peer", "nccl"],
+                   help="multi-GPU gradient sum: peer = one hand-written kernel per rank over NVLink peer memory "
+                        "(CUDA IPC, one node); nccl = torch.distributed.all_reduce; auto = peer when it can be set up")
     p.add_argument("--quiet", type=b, default=False, nargs="?", const=True)
     p.add_argument("--tensorboard", type=b, default=True, nargs="?", const=True,
                    help="write the reference's scalar tags (losses/*, Charts/SPS, rws/episodic_*) with SummaryWriter")
@@ -142,9 +145,15 @@ class ExtractObsWrapper(ObservationWrapper):
         return obs["obs"]
 
 
-def flatten_parameters(module):
+def flat_size(module):
+    """Floats of the flat parameter buffer of `flatten_parameters` (every tensor padded to a multiple of 4)."""
+    return sum((p.numel() + 3) // 4 * 4 for p in module.parameters())
+
+
+def flatten_parameters(module, grad_buffer=None):
     """Re-home every parameter (and its .grad) as a view of one flat buffer, so the gradient
-    all-reduce, the norm clip and Adam each touch ONE tensor."""
+    all-reduce, the norm clip and Adam each touch ONE tensor. `grad_buffer`: an existing zeroed f32 tensor to
+    hold the flat gradient (e.g. the peer-mapped buffer of `PeerGradients`)."""
     params = list(module.parameters())
     # every tensor starts on a 16-byte boundary (the 1-element biases of the value head would otherwise leave all
     # later tensors at odd offsets: the split-K wgrad reduces with 16-byte vector atomics); the padding words stay
@@ -154,7 +163,7 @@ def flatten_parameters(module):
         starts.append(off)
         off += (p.numel() + 3) // 4 * 4
     flat = torch.zeros(off, device=params[0].device, dtype=params[0].dtype)
-    flat_grad = torch.zeros_like(flat)
+    flat_grad = torch.zeros_like(flat) if grad_buffer is None else grad_buffer[:off]
     for p, o in zip(params, starts):
         n = p.numel()
         flat[o:o + n].copy_(p.data.view(-1))
@@ -324,10 +333,32 @@ def train(args, log=print, hook=None):
     backend = "tc" if args.mlp_backend in ("auto", "tc") else "torch"
     agent = Agent(envs, mlp_backend=backend).to(device)
     torch.manual_seed(args.seed + 1000 * (rank + 1))
-    flat, flat_grad = flatten_parameters(agent)
+    # the flat gradient lives in a buffer the other ranks of the node can read (peer.py) when that can be set up
+    peer_grads = None
+    mode = getattr(args, "grad_allreduce", "auto")
+    if world > 1 and mode != "nccl":
+        one_node = int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) == world
+        try:
+            if not one_node:
+                raise RuntimeError("the ranks span several nodes (CUDA IPC reaches one node)")
+            from .peer import PeerGradients
+            peer_grads = PeerGradients(flat_size(agent), device, rank, world)
+        except Exception as e:
+            if mode == "peer":
+                raise
+            log(f"[rank {rank}] peer-memory gradient all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
+            peer_grads = None
+        # all ranks or none: a rank that failed sends everyone to NCCL
+        flag = torch.tensor([1.0 if peer_grads is not None else 0.0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0.0:
+            peer_grads = None
+    flat, flat_grad = flatten_parameters(agent, None if peer_grads is None else peer_grads.buffer)
     if world > 1:
         dist.broadcast(flat, 0)
-    optimizer = FlatAdam(flat, flat_grad, lr=args.learning_rate, eps=1e-5)
+    # what clip + Adam read: the summed gradient (a local buffer with the peer kernel, flat_grad itself with NCCL)
+    grad_sum = flat_grad if peer_grads is None else torch.zeros_like(flat)
+    optimizer = FlatAdam(flat, grad_sum, lr=args.learning_rate, eps=1e-5)
 
     T, N = args.num_steps, args.num_envs
     oshape, ashape = envs.single_observation_space.shape, envs.single_action_space.shape
@@ -465,21 +496,23 @@ def train(args, log=print, hook=None):
         if fused:
             return optimizer.clip_and_step_fused(args.max_grad_norm, 1.0 / world)
         if world > 1:
-            flat_grad.div_(world)
-        gnorm = torch.linalg.vector_norm(flat_grad)
-        flat_grad.mul_(torch.clamp(args.max_grad_norm / (gnorm + 1e-6), max=1.0))
+            grad_sum.div_(world)
+        gnorm = torch.linalg.vector_norm(grad_sum)
+        grad_sum.mul_(torch.clamp(args.max_grad_norm / (gnorm + 1e-6), max=1.0))
         optimizer.step()
 
     def reduce_gradient():
         """The one collective of the path: sum of the flat gradient over ranks (clip_and_step divides)."""
-        if world > 1:
+        if peer_grads is not None:
+            peer_grads.allreduce(grad_sum)   # one kernel over NVLink peer memory (csrc/peer_reduce.cu)
+        elif world > 1:
             dist.all_reduce(flat_grad)
 
     # Can this process group's all-reduce be recorded into a CUDA graph? (Then the whole minibatch —
     # forward, backward, all-reduce, clip, Adam — is ONE graph replay and the collective no longer sits
     # between two replays with Python in between.) Probed once on a scratch tensor.
     nccl_in_graph = False
-    if world > 1 and args.cuda_graph:
+    if world > 1 and args.cuda_graph and peer_grads is None:
         try:
             probe = torch.zeros(1024, device=device)
             dist.all_reduce(probe)            # (communicator set-up happens outside capture)
@@ -517,7 +550,7 @@ def train(args, log=print, hook=None):
         nonlocal mb_graph, fb_graph, opt_graph
         mb_inds.copy_(inds)
         capture = args.cuda_graph and state["update"] >= 2
-        if world == 1 or nccl_in_graph:
+        if world == 1 or nccl_in_graph or peer_grads is not None:
             if mb_graph is not None:
                 mb_graph.replay()
             elif capture:
@@ -631,6 +664,7 @@ def train(args, log=print, hook=None):
                  final_sps=(global_step / max(time.time() - start_time, 1e-9)))
     stats["mlp_backend"] = "tcgen05-bf16" if backend == "tc" else "torch-fp32"
     stats["nccl_in_graph"] = nccl_in_graph
+    stats["grad_allreduce"] = "none" if world == 1 else ("peer-memory kernel" if peer_grads is not None else "nccl")
     stats["sanitised_fields"] = unwrapped_env.engine.sanitised_count
     if writer is not None:
         writer.close()
