@@ -11,4 +11,4 @@ for N in (4096,65536,196608):
     e0.record()
     for i in range(50): gae(*a,d,to,0.99,0.95,adv,ret)
     e1.record(); torch.cuda.synchronize(); ms=e0.elapsed_time(e1)/50
-    print(os.environ.get("VSS_GAE_BLOCK","64"), N, "%.1f us"%(ms*1e3), "%.0f GB/s"%(28*T*N/ms/1e6), "%.3f"%(28*T*N/ms/1e6/6543.1))
+    print(64, N, "%.1f us"%(ms*1e3), "%.0f GB/s"%(28*T*N/ms/1e6), "%.3f"%(28*T*N/ms/1e6/6543.1))

@@ -9,8 +9,7 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-# VSS_B200_LIB: tuning hook — load an alternative build of the same library (A/B runs of kernel variants)
-LIB_PATH = os.environ.get("VSS_B200_LIB") or os.path.join(_PKG, "libvss_b200.so")
+LIB_PATH = os.path.join(_PKG, "libvss_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 VIEW_SA, VIEW_CMA, VIEW_DMA = 0, 1, 2
