@@ -728,144 +728,6 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
 }
 
-// The weight-gradient GEMM on CTA pairs: dW[n_out, k_in] = dZ^T X over the batch, both operands MN-major
-// (read straight from their row-major [batch, features] buffers), split-K with fp32 red.add into dW.
-// A pair owns a 256 x 256 block of dW for one slice of the batch: CTA r stages 64 batch rows x (its 128 of the
-// 256 dZ columns + its 128 of the 256 X columns) per k-block — 32 KB where the one-CTA 128 x 256 tile needs
-// 48 KB for the same FLOPs; that kernel was bound by what an SM can take in (~42 B/clk).
-constexpr int PW_STAGES = 6;
-struct SmemPairW {
-  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = 128 * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = PW_STAGES * STAGE_BYTES + 256 + 1024;
-};
-__global__ void __launch_bounds__(THREADS, 1)
-k_gemm_pair_wgrad(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const __grid_constant__ GemmArgs g) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PW_STAGES * SmemPairW::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + PW_STAGES;
-  uint64_t* tfull_bar = empty_bar + PW_STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)cluster_ctarank();
-  const bool leader = rank == 0;
-  const int n_tiles = g.N / P2_BN, m_tiles = g.M / (2 * BM);
-  const int tiles_per_split = n_tiles * m_tiles, total_tiles = tiles_per_split * g.splits, total_kb = g.K / BK;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < PW_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer (both CTAs): 64 x 64 boxes of the [batch, features] tensors, inner coordinate = feature
-      uint32_t s = 0, ph = 0;
-      for (int t = pair; t < total_tiles; t += npairs) {
-        const int split = t / tiles_per_split, r = t % tiles_per_split;
-        const int m0 = (r / n_tiles) * (2 * BM) + rank * BM, n0 = (r % n_tiles) * P2_BN + rank * 128;
-        const int kb0 = split * g.k_blocks_per_split, nkb = min(g.k_blocks_per_split, total_kb - kb0);
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * SmemPairW::STAGE_BYTES;
-          uint8_t* sb = sa + SmemPairW::A_BYTES;
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * SmemPairW::STAGE_BYTES);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            tma_load_2d_pair(sa + i * 8192, &map_a, &full_bar[s], m0 + 64 * i, (kb0 + kb) * BK);
-            tma_load_2d_pair(sb + i * 8192, &map_b, &full_bar[s], n0 + 64 * i, (kb0 + kb) * BK);
-          }
-          if (++s == PW_STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && leader) {  // ---- MMA issuer
-      constexpr uint32_t idesc = make_idesc(2 * BM, P2_BN, true);
-      uint32_t s = 0, ph = 0, lt = 0;
-      for (int t = pair; t < total_tiles; t += npairs, ++lt) {
-        const int split = t / tiles_per_split;
-        const int kb0 = split * g.k_blocks_per_split, nkb = min(g.k_blocks_per_split, total_kb - kb0);
-        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-        mbar_wait(&tempty_bar[buf], bph ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * P2_BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * SmemPairW::STAGE_BYTES);
-          const uint64_t adesc = make_desc_mn128(sa), bdesc = make_desc_mn128(sa + SmemPairW::A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)   // +16 batch rows = 2048 B (>> 4 = 128) per K step
-            umma_bf16_pair(tmem_d, adesc + 128ull * k, bdesc + 128ull * k, idesc, (kb | k) != 0);
-          umma_commit_pair(&empty_bar[s]);
-          if (++s == PW_STAGES) { s = 0; ph ^= 1; }
-        }
-        umma_commit_pair(&tfull_bar[buf]);
-      }
-    }
-  } else {  // ---- epilogue (both CTAs): red.add of this CTA's 128 rows x 256 columns into dW
-    const int q = warp & 3;
-    uint32_t lt = 0;
-    for (int t = pair; t < total_tiles; t += npairs, ++lt) {
-      const int r = t % tiles_per_split;
-      const int row = (r / n_tiles) * (2 * BM) + rank * BM + q * 32 + lane, n0 = (r % n_tiles) * P2_BN;
-      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-      mbar_wait(&tfull_bar[buf], bph);
-      tc_fence_after();
-      float* orow = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + n0;
-#pragma unroll 1
-      for (int c = 0; c < P2_BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * P2_BN + (uint32_t)c, v);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          red_add_v4(orow + c + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty_bar[buf]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-  }
-}
-
-static cudaError_t launch_pair_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_pair_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPairW::TOTAL);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  const long long tiles = (long long)(g.M / (2 * BM)) * (g.N / P2_BN) * g.splits;
-  unsigned grid = (unsigned)std::min<long long>(2 * tiles, 148);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SmemPairW::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_gemm_pair_wgrad, ma, mb, g);
-}
-
 template <int EPI>
 static cudaError_t launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mx,
                                const GemmArgs& g, cudaStream_t st) {
