@@ -502,16 +502,21 @@ k_gemm_tn(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 constexpr int P2_BN = 256;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: the leader's copy
-// forward: 5 x 32 KB ring + 2 x 16 KB of output boxes; dgrad: 4 x 32 KB ring + 2 x 16 KB of output boxes + 2 x 16 KB
-// of boxes for the tanh' operand (the activations of the layer below, fetched by TMA one box ahead)
-template <int EPI>
+// Shared memory of the pair kernel. EW = epilogue warps: 4 (one per TMEM lane quarter, all 256 columns) where the
+// mainloop binds (K = 512), 8 (two per quarter, 128 columns each) where the epilogue binds (K <= 256: few MMAs per
+// tile, the same bias + tanh / tanh' + store work). Each epilogue warp owns 32 x 64 staging boxes (128-byte rows,
+// 128B-swizzled tensor-map boxes): two for the output (one being stored, one being filled; one with 8 warps in dgrad)
+// and, in dgrad, two for the tanh' operand (the activations of the layer below, fetched by TMA one box ahead).
+template <int EPI, int EW>
 struct SmemPair {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = 128 * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = EPI == EPI_DTANH_BF16 ? 4 : 5;
-  static constexpr int BOX = 32 * 128;             // 32 rows x 64 bf16: one 128B-swizzled tensor-map box
-  static constexpr int OUT_STAGE = 2 * BOX;        // per epilogue warp: one box being stored, one being filled
+  static constexpr int STAGES = EPI == EPI_DTANH_BF16 ? (EW == 8 ? 3 : 4) : (EW == 8 ? 4 : 5);
+  static constexpr int BOX = 32 * 128;
+  static constexpr int OUT_BOXES = (EPI == EPI_DTANH_BF16 && EW == 8) ? 1 : 2;
+  static constexpr int OUT_STAGE = OUT_BOXES * BOX;
   static constexpr int AUX_STAGE = EPI == EPI_DTANH_BF16 ? 2 * BOX : 0;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_WARPS * (OUT_STAGE + AUX_STAGE) + 256 + 2048 + 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EW * (OUT_STAGE + AUX_STAGE) + 256 + 2048 + 1024;
+  static_assert(TOTAL <= 232448, "dynamic shared memory per CTA");
 };
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c_inner, int c_outer) {
@@ -534,24 +539,25 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive o
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int EPI, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_x,
             const __grid_constant__ GemmArgs g) {
   static_assert(EPI == EPI_BIAS_TANH_BF16 || EPI == EPI_DTANH_BF16, "forward or dgrad epilogue");
-  using SM = SmemPair<EPI>;
-  constexpr int P2_STAGES = SM::STAGES;
+  static_assert(EW == 4 || EW == 8, "one or two epilogue warps per TMEM lane quarter");
+  using SM = SmemPair<EPI, EW>;
+  constexpr int P2_STAGES = SM::STAGES, NTHREADS = 64 + 32 * EW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* out_stage = smem + P2_STAGES * SM::STAGE_BYTES;  // 1024-byte aligned (and so is every box after it)
-  uint8_t* aux_stage = out_stage + EPI_WARPS * SM::OUT_STAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux_stage + EPI_WARPS * SM::AUX_STAGE);
+  uint8_t* aux_stage = out_stage + EW * SM::OUT_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux_stage + EW * SM::AUX_STAGE);
   uint64_t* empty_bar = full_bar + P2_STAGES;
   uint64_t* tfull_bar = empty_bar + P2_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;   // [EPI_WARPS][2] tanh'-operand box landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * EPI_WARPS);
+  uint64_t* aux_bar = tempty_bar + 2;   // [EW][2] tanh'-operand box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * EW);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // forward: bias; dgrad: column sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -562,15 +568,15 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }
-    for (int b = 0; b < 2 * EPI_WARPS; ++b) mbar_init(&aux_bar[b], 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EW); }
+    for (int b = 0; b < 2 * EW; ++b) mbar_init(&aux_bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // the same warp of both CTAs allocates all 512 columns of the pair's tensor memory
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < g.N; i += THREADS)   // N <= 512 (checked by the host)
+  for (int i = threadIdx.x; i < g.N; i += NTHREADS)   // N <= 512 (checked by the host)
     bias_s[i] = EPI == EPI_BIAS_TANH_BF16 ? __ldg(g.bias + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
@@ -617,15 +623,18 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
     }
   } else {
-    // ---- epilogue (both CTAs): this CTA's 128 rows x 256 columns, warp q = TMEM lane quarter
-    const int q = warp & 3;
-    uint8_t* stage = out_stage + q * SM::OUT_STAGE;
-    uint8_t* xstage = aux_stage + q * SM::AUX_STAGE;
-    uint64_t* xbar = aux_bar + 2 * q;
+    // ---- epilogue (both CTAs): this CTA's 128 rows x 256 columns; warp -> TMEM lane quarter q (a warp may only touch
+    // the lanes of quarter warp % 4) and, with 8 warps, the lower or upper 128 columns
+    const int q = warp & 3, ew = warp - 2;
+    constexpr int CHUNKS = (P2_BN / 32) / (EW / 4);     // 32-column chunks per warp and tile
+    const int c0 = (EW == 8 ? (ew >> 2) : 0) * CHUNKS;  // first chunk of this warp
+    uint8_t* stage = out_stage + ew * SM::OUT_STAGE;
+    uint8_t* xstage = aux_stage + ew * SM::AUX_STAGE;
+    uint64_t* xbar = aux_bar + 2 * ew;
     uint32_t lt = 0, xbox = 0;   // xbox: boxes of the tanh' operand consumed so far (buffer = xbox & 1, phase = (xbox >> 1) & 1)
     if (EPI == EPI_DTANH_BF16 && lane == 0 && pair < total_tiles) {   // the first box of the first tile
       mbar_expect_tx(&xbar[0], SM::BOX);
-      tma_load_2d(xstage, &map_x, &xbar[0], (pair % n_tiles) * P2_BN, (pair / n_tiles) * (2 * BM) + rank * BM + q * 32);
+      tma_load_2d(xstage, &map_x, &xbar[0], (pair % n_tiles) * P2_BN + 32 * c0, (pair / n_tiles) * (2 * BM) + rank * BM + q * 32);
     }
     for (int t = pair; t < total_tiles; t += npairs, ++lt) {
       const int m0 = (t / n_tiles) * (2 * BM) + rank * BM + q * 32, n0 = (t % n_tiles) * P2_BN;
@@ -633,15 +642,16 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(&tfull_bar[buf], bph);
       tc_fence_after();
       uint32_t v[2][32];
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * P2_BN;
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * P2_BN + 32u * c0;
       tmem_ld32_issue(t0, v[0]);
 #pragma unroll
-      for (int ci = 0; ci < P2_BN / 32; ++ci) {
+      for (int cj = 0; cj < CHUNKS; ++cj) {
+        const int ci = c0 + cj;   // (c0 is even: cj and ci have the same parity)
         tmem_ld_wait();
-        if (ci + 1 < P2_BN / 32) tmem_ld32_issue(t0 + 32u * (ci + 1), v[(ci + 1) & 1]);
-        uint8_t* box = stage + ((ci >> 1) & 1) * (32 * 128);   // the two boxes alternate
-        if ((ci & 1) == 0) {  // the store that last used this box (two boxes ago) has read it out of shared memory
-          if (lane == 0) tma_store_wait_read1();
+        if (cj + 1 < CHUNKS) tmem_ld32_issue(t0 + 32u * (cj + 1), v[(cj + 1) & 1]);
+        uint8_t* box = stage + ((cj >> 1) % SM::OUT_BOXES) * SM::BOX;   // the output boxes alternate
+        if ((cj & 1) == 0) {  // the store that last used this box has read it out of shared memory
+          if (lane == 0) { if (SM::OUT_BOXES == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
           __syncwarp();
         }
         const int col = n0 + 32 * ci;
@@ -649,10 +659,10 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (EPI == EPI_DTANH_BF16 && (ci & 1) == 0) {
           // request the NEXT box (same tile, or the first box of this warp's next tile) into the other buffer —
           // its previous contents were consumed one box ago — then wait for this one
-          const bool last = ci + 2 >= P2_BN / 32;
+          const bool last = cj + 2 >= CHUNKS;
           const int tn = last ? t + npairs : t;
           if (lane == 0 && tn < total_tiles) {
-            const int cn = last ? (tn % n_tiles) * P2_BN : col + 64;
+            const int cn = last ? (tn % n_tiles) * P2_BN + 32 * c0 : col + 64;
             const int rn = last ? (tn / n_tiles) * (2 * BM) + rank * BM + q * 32 : m0;
             mbar_expect_tx(&xbar[(xbox + 1) & 1], SM::BOX);
             tma_load_2d(xstage + ((xbox + 1) & 1) * SM::BOX, &map_x, &xbar[(xbox + 1) & 1], cn, rn);
@@ -661,8 +671,8 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t* x = &v[ci & 1][8 * j];
-          const int k = (ci & 1) * 4 + j;
+          const uint32_t* x = &v[cj & 1][8 * j];
+          const int k = (cj & 1) * 4 + j;
           float o[8];
           if (EPI == EPI_BIAS_TANH_BF16) {
             const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + 8 * j);
@@ -720,7 +730,7 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   if (EPI == EPI_DTANH_BF16 && g.colsum != nullptr)
-    for (int i = threadIdx.x; i < g.N; i += THREADS) atomicAdd(g.colsum + i, bias_s[i]);
+    for (int i = threadIdx.x; i < g.N; i += NTHREADS) atomicAdd(g.colsum + i, bias_s[i]);
   cluster_sync();  // no CTA leaves while its peer can still signal it or read its shared memory
   if (warp == 1) {
     tc_fence_after();
@@ -728,13 +738,13 @@ k_gemm_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
 }
 
-template <int EPI>
+template <int EPI, int EW>
 static cudaError_t launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mx,
                                const GemmArgs& g, cudaStream_t st) {
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_pair<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPair<EPI>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_pair<EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPair<EPI, EW>::TOTAL);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -744,12 +754,12 @@ static cudaError_t launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, con
   const long long tiles = (long long)((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / P2_BN);
   unsigned grid = (unsigned)std::min<long long>(2 * tiles, sms & ~1);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SmemPair<EPI>::TOTAL; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * EW); cfg.dynamicSmemBytes = SmemPair<EPI, EW>::TOTAL; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_gemm_pair<EPI>, ma, mb, mo, mx, g);
+  return cudaLaunchKernelEx(&cfg, k_gemm_pair<EPI, EW>, ma, mb, mo, mx, g);
 }
 
 // ------------------------------------------------------------------------------- host side
@@ -1058,8 +1068,11 @@ VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int l
     bool ok2 = make_map(&ma2, A, M, K, lda, BM) && make_map(&mb2, B, N, K, ldb, 128) && make_map(&mo2, out, M, N, ldo, 32);
     if (ok2) { if (epilogue == EPI_DTANH_BF16) ok2 = make_map(&mx2, aux, M, N, ld_aux, 32); else mx2 = mo2; }
     if (!ok2) { g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA; }
-    e = epilogue == EPI_BIAS_TANH_BF16 ? launch_pair<EPI_BIAS_TANH_BF16>(ma2, mb2, mo2, mx2, g, st)
-                                       : launch_pair<EPI_DTANH_BF16>(ma2, mb2, mo2, mx2, g, st);
+    // K <= 256: few MMAs per tile, the epilogue binds -> two epilogue warps per TMEM lane quarter
+    if (epilogue == EPI_BIAS_TANH_BF16)
+      e = K <= 256 ? launch_pair<EPI_BIAS_TANH_BF16, 8>(ma2, mb2, mo2, mx2, g, st) : launch_pair<EPI_BIAS_TANH_BF16, 4>(ma2, mb2, mo2, mx2, g, st);
+    else
+      e = K <= 256 ? launch_pair<EPI_DTANH_BF16, 8>(ma2, mb2, mo2, mx2, g, st) : launch_pair<EPI_DTANH_BF16, 4>(ma2, mb2, mo2, mx2, g, st);
     if (e != cudaSuccess) { g_tc_error = std::string("vss_gemm_bf16_tn (pair): ") + cudaGetErrorString(e); return VSS_E_CUDA; }
     return VSS_OK;
   }

@@ -33,19 +33,33 @@ class PeerGradients:
         self.device = torch.device(device)
         self.rank, self.world = int(rank), int(world)
         self._h = C.c_void_p()
-        _check(self.lib, self.lib.vss_peer_create(C.byref(self._h), self.device.index, self.rank, self.world,
-                                                  int(num_floats)))
-        handle = C.create_string_buffer(64)
-        _check(self.lib, self.lib.vss_peer_ipc_handle(self._h, handle))
+        # Every step that can fail locally is followed by an exchange of the outcome, so that either all ranks go on
+        # or all ranks raise (a rank that left early would leave the others waiting in the next collective).
+        err, handle = None, C.create_string_buffer(64)
+        try:
+            _check(self.lib, self.lib.vss_peer_create(C.byref(self._h), self.device.index, self.rank, self.world,
+                                                      int(num_floats)))
+            _check(self.lib, self.lib.vss_peer_ipc_handle(self._h, handle))
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {self.rank}: {e}"
         gathered = [None] * self.world
-        dist.all_gather_object(gathered, handle.raw)
-        blob = b"".join(gathered)
-        assert len(blob) == 64 * self.world
-        _check(self.lib, self.lib.vss_peer_connect(self._h, blob))
+        dist.all_gather_object(gathered, (err, handle.raw))
+        self._raise_if_any([g[0] for g in gathered])
+        try:
+            _check(self.lib, self.lib.vss_peer_connect(self._h, b"".join(g[1] for g in gathered)))
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {self.rank}: {e}"
+        dist.all_gather_object(gathered, err)   # (also: every rank has mapped every buffer before anyone signals into them)
+        self._raise_if_any(gathered)
         n = int(self.lib.vss_peer_num_floats(self._h))
         self._mem = _DeviceMemory(self.lib.vss_peer_buffer(self._h), n)
         self.buffer = torch.as_tensor(self._mem, device=self.device)   # the rank's gradient buffer (n floats, zeroed)
-        dist.barrier()   # every rank has mapped every buffer before anyone's first kernel signals into them
+
+    def _raise_if_any(self, errors):
+        bad = [e for e in errors if e]
+        if bad:
+            self.close()
+            raise RuntimeError("peer-memory group could not be formed: " + "; ".join(bad))
 
     def allreduce(self, out):
         """out[i] = sum over ranks of buffer_rank[i] (all ranks get bit-identical sums). `out`: f32 CUDA tensor of at

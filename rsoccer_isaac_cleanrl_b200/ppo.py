@@ -339,7 +339,7 @@ def train(args, log=print, hook=None):
     if world > 1 and mode != "nccl":
         one_node = int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) == world
         try:
-            if not one_node:
+            if not one_node:   # (the same on every rank)
                 raise RuntimeError("the ranks span several nodes (CUDA IPC reaches one node)")
             from .peer import PeerGradients
             peer_grads = PeerGradients(flat_size(agent), device, rank, world)
@@ -347,12 +347,7 @@ def train(args, log=print, hook=None):
             if mode == "peer":
                 raise
             log(f"[rank {rank}] peer-memory gradient all-reduce unavailable ({type(e).__name__}: {e}); using NCCL")
-            peer_grads = None
-        # all ranks or none: a rank that failed sends everyone to NCCL
-        flag = torch.tensor([1.0 if peer_grads is not None else 0.0], device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if flag.item() == 0.0:
-            peer_grads = None
+            peer_grads = None   # (PeerGradients raises on every rank or on none)
     flat, flat_grad = flatten_parameters(agent, None if peer_grads is None else peer_grads.buffer)
     if world > 1:
         dist.broadcast(flat, 0)
@@ -668,6 +663,14 @@ def train(args, log=print, hook=None):
     stats["sanitised_fields"] = unwrapped_env.engine.sanitised_count
     if writer is not None:
         writer.close()
+    if peer_grads is not None:   # the gradient views point into the peer buffer: drop them before it is freed
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()       # no rank unmaps while another may still be reading
+        for p_ in agent.parameters():
+            p_.grad = None
+        del flat_grad
+        peer_grads.close()
     stats["agent"] = agent
     stats["env"] = unwrapped_env
     return stats

@@ -79,8 +79,8 @@ def test_dgrad_cta_pair_path(M, N_out, K_in):
     assert (colsum.double() - want).abs().max().item() < 2e-3 * want.abs().max().item() + 1e-2
 
 
-# (batch >= 18 944 with both sides of dW multiples of 256 takes the CTA-pair wgrad kernel, which chooses its own
-# batch slices: ragged batch, 1 x 2, 2 x 1 and 2 x 2 blocks of dW)
+# (split-K wgrad, MN-major operands, 128 x 256 / 128 x 64 tiles, vector reductions into dW: ragged batch, one and two
+# column tiles, the minibatch-sized reductions)
 @pytest.mark.parametrize("batch,N_out,K_in,splits", [(4096, 256, 64, 8), (8192, 512, 256, 16), (4000, 512, 512, 7),
                                                      (131072, 256, 512, 32), (131072, 512, 512, 18), (40003, 512, 256, 9),
                                                      (131072, 256, 64, 49)])
