@@ -1068,7 +1068,8 @@ VSS_API int vss_gemm_bf16_tn_colsum(const void* A, int lda, const void* B, int l
     bool ok2 = make_map(&ma2, A, M, K, lda, BM) && make_map(&mb2, B, N, K, ldb, 128) && make_map(&mo2, out, M, N, ldo, 32);
     if (ok2) { if (epilogue == EPI_DTANH_BF16) ok2 = make_map(&mx2, aux, M, N, ld_aux, 32); else mx2 = mo2; }
     if (!ok2) { g_tc_error = "vss_gemm_bf16_tn: cuTensorMapEncodeTiled failed"; return VSS_E_CUDA; }
-    // K <= 256: few MMAs per tile, the epilogue binds -> two epilogue warps per TMEM lane quarter
+    // K <= 256: few MMAs per tile, the epilogue binds -> two epilogue warps per TMEM lane quarter (measured at K = 512:
+    // 67.2 / 42.3 us with eight warps and a 4-stage ring vs 66.8 / 40.0 us with four warps and 5 stages)
     if (epilogue == EPI_BIAS_TANH_BF16)
       e = K <= 256 ? launch_pair<EPI_BIAS_TANH_BF16, 8>(ma2, mb2, mo2, mx2, g, st) : launch_pair<EPI_BIAS_TANH_BF16, 4>(ma2, mb2, mo2, mx2, g, st);
     else
