@@ -184,6 +184,36 @@ VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, fl
                           float* ep_ret, int32_t* ep_len, float* ret_ret, int32_t* ret_len,
                           void* stream);
 
+#define VSS_PACKED_ROW_BYTES 112
+/* The same step for a caller on the HOST side of the PCIe link: one call takes the policy action from pinned
+ * host memory and returns one packed VSS_PACKED_ROW_BYTES-byte row per view env (see vss_set_step_packed) in
+ * pinned host memory — what `SingleAgent/CMA/DMA.step` hands the policy (envs/wrappers.py:108-115). Internally the
+ * fields are cut into `num_ranges` ranges, each with its own H2D copy of its actions, kernel launch and ONE D2H
+ * copy of its rows, alternating over two streams owned by the engine, so that the copies of one range overlap the
+ * kernel of the next; the call orders itself after the work already queued on `stream` and returns when the rows
+ * are in host memory. `dev` holds the view's device buffers exactly as vss_step_view takes them (+ the device
+ * staging for the rows); they keep the ordinary outputs of the step. Results are bit-identical to one vss_step_view
+ * launch over all fields. */
+typedef struct vss_view_buffers {
+  float* policy_action;   /* device copy of the action, (N', act dim) */
+  float* action_buf;
+  int64_t* reset_buf;
+  float* obs_v;
+  float* term_obs_v;
+  float* rews_v;
+  float* reward_v;
+  int64_t* done_v;
+  uint8_t* timeout_v;
+  float* progress_v;
+  float* ep_ret;          /* the four statistics buffers may be NULL together */
+  int32_t* ep_len;
+  float* ret_ret;
+  int32_t* ret_len;
+  void* packed_rows;      /* device staging, N' x VSS_PACKED_ROW_BYTES */
+} vss_view_buffers;
+VSS_API int vss_step_view_host(vss_handle h, int view, const vss_view_buffers* dev, const float* policy_action_host,
+                               void* rows_host, int num_ranges, void* stream);
+
 /* Optional side outputs of the following vss_step_view launches (each may be NULL = off), for a
  * caller that feeds the observation straight into a bf16 tensor-core MLP and the flags into a float
  * GAE (the PPO loop, ppo_continuous_action_isaacgym.py:258-272, 282-296):
@@ -205,7 +235,6 @@ VSS_API int vss_set_step_aux(vss_handle h, void* obs_bf16, float* done_f32, floa
  * range) or pinned host memory (cudaHostAlloc is device-mapped under unified addressing: the kernel then
  * stores straight across PCIe and no copy is issued at all). Host-side state of the handle, like
  * vss_set_step_aux. */
-#define VSS_PACKED_ROW_BYTES 112
 VSS_API int vss_set_step_packed(vss_handle h, void* rows);
 
 /* Restricts the following vss_step / vss_step_view launches to the fields [first_field, first_field +

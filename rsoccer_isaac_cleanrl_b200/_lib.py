@@ -43,6 +43,14 @@ class VssParams(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ViewBuffers(C.Structure):
+    """`vss_view_buffers` of include/vss_b200.h."""
+
+    _fields_ = [(k, C.c_void_p) for k in (
+        "policy_action", "action_buf", "reset_buf", "obs_v", "term_obs_v", "rews_v", "reward_v", "done_v", "timeout_v",
+        "progress_v", "ep_ret", "ep_len", "ret_ret", "ret_len", "packed_rows")]
+
+
 class ConvertJob(C.Structure):
     """`vss_convert_job` of include/vss_b200.h."""
 
@@ -65,6 +73,7 @@ _SYMBOLS = {
     "vss_step": (C.c_int, [_VP] * 9),
     "vss_step_injected": (C.c_int, [_VP] * 10),
     "vss_step_view": (C.c_int, [_VP, C.c_int] + [_VP] * 15),
+    "vss_step_view_host": (C.c_int, [_VP, C.c_int, C.POINTER(ViewBuffers), _VP, _VP, C.c_int, _VP]),
     "vss_set_step_aux": (C.c_int, [_VP, _VP, _VP, _VP]),
     "vss_set_step_packed": (C.c_int, [_VP, _VP]),
     "vss_step_granularity": (C.c_int64, [_VP]),

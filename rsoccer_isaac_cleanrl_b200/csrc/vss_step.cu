@@ -431,6 +431,9 @@ struct vss_engine {
   void* packed_rows;                                            // vss_set_step_packed
   int wpt_override;                                             // vss_set_step_warps_per_tile (0 = automatic)
   int64_t range_first, range_count;                             // vss_set_step_range (count 0 = all fields)
+  cudaStream_t host_stream[2];                                  // vss_step_view_host: the two pipeline streams ...
+  cudaEvent_t host_start, host_done[2];                         // ... and their fork / join events (created on first use)
+  bool host_ready;
 };
 
 static thread_local std::string g_last_error;
@@ -583,7 +586,7 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
   if (!h) return fail(VSS_E_NOMEM, "vss_create: host allocation failed");
   h->device = device; h->n = num_envs; h->ld = (num_envs + 31) / 32 * 32; h->goff = global_env_offset;
   h->aux_obs_bf16 = nullptr; h->aux_done_f = nullptr; h->aux_timeout_f = nullptr; h->packed_rows = nullptr;
-  h->range_first = 0; h->range_count = 0; h->wpt_override = 0;
+  h->range_first = 0; h->range_count = 0; h->wpt_override = 0; h->host_ready = false;
   h->seed = seed; h->d_step = nullptr; h->params = *p; h->dp = derive_params(*p); h->state = nullptr;
   const size_t bytes = sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld;
   e = cudaMalloc(&h->state, bytes);
@@ -598,6 +601,10 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
 
 VSS_API int vss_destroy(vss_handle h) {
   if (!h) return VSS_OK;
+  if (h->host_ready) {
+    for (int i = 0; i < 2; ++i) { cudaStreamDestroy(h->host_stream[i]); cudaEventDestroy(h->host_done[i]); }
+    cudaEventDestroy(h->host_start);
+  }
   cudaFree(h->state);
   cudaFree(h->d_step);
   delete h;
@@ -694,6 +701,65 @@ VSS_API int vss_step_view(vss_handle h, int view, const float* policy_action, fl
     case VSS_VIEW_DMA: return launch_step<VSS_VIEW_DMA, false>(h, a, stream);
     default: return fail(VSS_E_INVALID, "vss_step_view: unknown view");
   }
+}
+
+VSS_API int vss_step_view_host(vss_handle h, int view, const vss_view_buffers* dev, const float* policy_action_host,
+                               void* rows_host, int num_ranges, void* stream) {
+  if (!h || !dev || !policy_action_host || !rows_host || !dev->packed_rows || !dev->policy_action)
+    return fail(VSS_E_INVALID, "vss_step_view_host: null argument");
+  if (view != VSS_VIEW_SA && view != VSS_VIEW_CMA && view != VSS_VIEW_DMA) return fail(VSS_E_INVALID, "vss_step_view_host: unknown view");
+  if (int rc = use_device(h)) return rc;
+  if (!h->host_ready) {
+    for (int i = 0; i < 2; ++i) {
+      VSS_CUDA(cudaStreamCreateWithFlags(&h->host_stream[i], cudaStreamNonBlocking));
+      VSS_CUDA(cudaEventCreateWithFlags(&h->host_done[i], cudaEventDisableTiming));
+    }
+    VSS_CUDA(cudaEventCreateWithFlags(&h->host_start, cudaEventDisableTiming));
+    h->host_ready = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int agents = view == VSS_VIEW_DMA ? 3 : 1, adim = view == VSS_VIEW_CMA ? 6 : 2;
+  const int64_t gran = vss_step_granularity(h);
+  if (num_ranges < 1) num_ranges = 1;
+  int64_t per = (h->n + num_ranges - 1) / num_ranges;
+  per = (per + gran - 1) / gran * gran;
+  void* const saved_packed = h->packed_rows;
+  const int64_t saved_first = h->range_first, saved_count = h->range_count;
+  h->packed_rows = dev->packed_rows;
+  VSS_CUDA(cudaEventRecord(h->host_start, st));
+  int rc = VSS_OK, used = 0;
+  for (int64_t f0 = 0; f0 < h->n && rc == VSS_OK; f0 += per, ++used) {
+    const int64_t cnt = f0 + per <= h->n ? per : h->n - f0;
+    const int64_t v0 = f0 * agents, nv = cnt * agents;
+    cudaStream_t s = h->host_stream[used & 1];
+    cudaError_t e = cudaStreamWaitEvent(s, h->host_start, 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(dev->policy_action + v0 * adim, policy_action_host + v0 * adim, sizeof(float) * nv * adim,
+                          cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { rc = fail(VSS_E_CUDA, "vss_step_view_host: H2D copy", e); break; }
+    h->range_first = f0; h->range_count = (f0 == 0 && cnt == h->n) ? 0 : cnt;
+    rc = vss_step_view(h, view, dev->policy_action, dev->action_buf, dev->reset_buf, dev->obs_v, dev->term_obs_v, dev->rews_v,
+                       dev->reward_v, dev->done_v, dev->timeout_v, dev->progress_v, dev->ep_ret, dev->ep_len, dev->ret_ret,
+                       dev->ret_len, s);
+    if (rc != VSS_OK) break;
+    e = cudaMemcpyAsync(static_cast<char*>(rows_host) + v0 * VSS_PACKED_ROW_BYTES,
+                        static_cast<const char*>(dev->packed_rows) + v0 * VSS_PACKED_ROW_BYTES,
+                        (size_t)nv * VSS_PACKED_ROW_BYTES, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) { rc = fail(VSS_E_CUDA, "vss_step_view_host: D2H copy", e); break; }
+  }
+  h->packed_rows = saved_packed; h->range_first = saved_first; h->range_count = saved_count;
+  for (int i = 0; i < 2 && i < used; ++i) {  // join (also after an error: nothing of this call stays in flight)
+    cudaEventRecord(h->host_done[i], h->host_stream[i]);
+    cudaStreamWaitEvent(st, h->host_done[i], 0);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc != VSS_OK) {  // a step abandoned after some of its range launches: forget the partial CTA count
+    unsigned long long zero = 0;
+    cudaMemcpy(h->d_step + 1, &zero, sizeof(zero), cudaMemcpyHostToDevice);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(VSS_E_CUDA, "vss_step_view_host: synchronize", e);
+  return VSS_OK;
 }
 
 VSS_API int vss_set_step_aux(vss_handle h, void* obs_bf16, float* done_f32, float* timeout_f32) {

@@ -155,6 +155,20 @@ class Engine:
             _ptr(ret_len, torch.int32, nv, "ret_len"), self._stream()))
 
 
+def _engine_step_view_host(self, view, bufs, action_host, rows_host, num_ranges):
+    """`vss_step_view_host`: pinned host action in, packed rows in pinned host memory out, pipelined over field
+    ranges inside the library; returns when the rows are in host memory. `bufs`: _lib.ViewBuffers of device pointers."""
+    if not (action_host.is_pinned() and rows_host.is_pinned()):
+        raise TypeError("step_view_host: action_host and rows_host must be pinned host tensors")
+    if action_host.dtype != torch.float32 or not action_host.is_contiguous():
+        raise TypeError("step_view_host: action_host must be a contiguous float32 tensor")
+    check(self.lib.vss_step_view_host(self._h, int(view), C.byref(bufs), action_host.data_ptr(), rows_host.data_ptr(),
+                                      int(num_ranges), self._stream()))
+
+
+Engine.step_view_host = _engine_step_view_host
+
+
 def gae(rewards, values, next_values, next_dones, next_timeouts, gamma=0.99, gae_lambda=0.95, advantages=None,
         returns=None):
     """Reverse-scan GAE kernel (ppo_continuous_action_isaacgym.py:282-296). All (T,N) f32 CUDA."""

@@ -72,7 +72,7 @@ class _FusedView(Wrapper):
         self.episode_returns = self.episode_lengths = None
         self.returned_episode_returns = self.returned_episode_lengths = None
         self._host = None
-        self._packed_out = None  # set by step_host: where this step's packed rows go
+        self._packed_out = None  # optional: where a step()'s packed rows go (vss_set_step_packed)
 
     # ---- running episode statistics fused into the step epilogue (wrappers.py:50-87)
     def enable_episode_stats(self):
@@ -164,13 +164,32 @@ class _FusedView(Wrapper):
         if not packed and obs_dtype != torch.float32:
             raise ValueError("step_host: obs_dtype must be torch.bfloat16 or torch.float32")
         h = self._host_buffers(packed)
-        act_host = action_host.view(h["act"].shape)
         n, agents = task.num_fields, nv // task.num_fields
         chunks = self.HOST_CHUNKS if n >= self.HOST_CHUNK_MIN_FIELDS else 1
+        if packed:
+            # one C call: the range pipeline (H2D of the range's actions, kernel, ONE D2H of its rows, two streams)
+            # runs inside the library — a Python loop over the ranges cannot keep a 2 ms step fed on a busy host
+            if "bufs" not in h:
+                from .. import _lib
+                p = lambda t: None if t is None else t.data_ptr()
+                h["bufs"] = _lib.ViewBuffers(
+                    p(h["act"]), p(self.action_buf), p(task.reset_buf), p(self._obs), p(self._term_obs), p(self._rews),
+                    p(self._reward), p(self._done), p(self._timeout_u8), p(self._progress), p(self.episode_returns),
+                    p(self.episode_lengths), p(self.returned_episode_returns), p(self.returned_episode_lengths),
+                    p(h["rows_dev"]))
+                h["bufs_stats"] = self.episode_returns is not None
+            assert h["bufs_stats"] == (self.episode_returns is not None), "enable_episode_stats() after the first step_host"
+            act_host = action_host.view(h["act"].shape)
+            if not act_host.is_pinned():
+                h.setdefault("act_pinned", torch.empty(tuple(h["act"].shape), dtype=torch.float32).pin_memory()).copy_(act_host)
+                act_host = h["act_pinned"]
+            task.engine.step_view_host(self.VIEW, h["bufs"], act_host, h["rows"], chunks)
+            task._obs_stale = True
+            return h["obs16"], h["reward_p"], h["done_p"]
+        act_host = action_host.view(h["act"].shape)
         cur = torch.cuda.current_stream(task.device)
         g = task.engine.step_granularity
         per = -(-n // (chunks * g)) * g
-        self._packed_out = h["rows_dev"] if packed else None
         start = torch.cuda.Event()
         start.record(cur)
         ok = False
@@ -188,15 +207,11 @@ class _FusedView(Wrapper):
                     if chunks > 1:
                         task.engine.set_step_range(f0, cnt)
                     obs, reward, done, _ = self.step(h["act"])
-                    if packed:
-                        h["rows"][v0:v1].copy_(h["rows_dev"][v0:v1], non_blocking=True)
-                    else:
-                        h["obs"][v0:v1].copy_(obs["obs"][v0:v1], non_blocking=True)
-                        h["reward"][v0:v1].copy_(reward[v0:v1], non_blocking=True)
-                        h["done"][v0:v1].copy_(done[v0:v1], non_blocking=True)
+                    h["obs"][v0:v1].copy_(obs["obs"][v0:v1], non_blocking=True)
+                    h["reward"][v0:v1].copy_(reward[v0:v1], non_blocking=True)
+                    h["done"][v0:v1].copy_(done[v0:v1], non_blocking=True)
             ok = True
         finally:
-            self._packed_out = None
             if chunks > 1:
                 task.engine.set_step_range(0, 0)
             if not ok:  # a step abandoned after some of its range launches: forget the partial CTA count
@@ -206,8 +221,6 @@ class _FusedView(Wrapper):
             for s in h["streams"]:
                 cur.wait_stream(s)
         cur.synchronize()
-        if packed:
-            return h["obs16"], h["reward_p"], h["done_p"]
         return h["obs"], h["reward"], h["done"]
 
     @property
