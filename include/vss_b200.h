@@ -255,6 +255,15 @@ VSS_API int64_t vss_step_granularity(vss_handle h);
  * them. Changes vss_step_granularity(). Host-side state of the handle. */
 VSS_API int vss_set_step_warps_per_tile(vss_handle h, int warps);
 VSS_API int vss_step_warps_per_tile(vss_handle h);
+
+/* Launch shape of the step kernels, second knob: how many fields form a tile (32, 16 or 8; 0 = chosen from
+ * num_envs). With fewer fields per tile the lanes beyond the tile idle in the per-field phases (and help in
+ * the cooperative observation writes), there are more tiles to spread over the SMs, and the divergent
+ * contact code of a tile - which runs field after field - forms a shorter chain. Bit-identical results for
+ * every value; covered by the same parity tests as vss_set_step_warps_per_tile. Changes
+ * vss_step_granularity(). Host-side state of the handle. */
+VSS_API int vss_set_step_fields_per_tile(vss_handle h, int fields);
+VSS_API int vss_step_fields_per_tile(vss_handle h);
 VSS_API int vss_set_step_range(vss_handle h, int64_t first_field, int64_t num_fields);
 
 /* State access for parity tests and checkpointing: copies the SoA state

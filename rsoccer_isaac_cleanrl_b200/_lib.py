@@ -79,6 +79,8 @@ _SYMBOLS = {
     "vss_step_granularity": (C.c_int64, [_VP]),
     "vss_set_step_warps_per_tile": (C.c_int, [_VP, C.c_int]),
     "vss_step_warps_per_tile": (C.c_int, [_VP]),
+    "vss_set_step_fields_per_tile": (C.c_int, [_VP, C.c_int]),
+    "vss_step_fields_per_tile": (C.c_int, [_VP]),
     "vss_set_step_range": (C.c_int, [_VP, C.c_int64, C.c_int64]),
     "vss_get_state": (C.c_int, [_VP, _VP, _VP]),
     "vss_set_state": (C.c_int, [_VP, _VP, _VP]),

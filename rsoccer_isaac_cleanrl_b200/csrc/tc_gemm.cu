@@ -908,7 +908,7 @@ k_head_fwd(const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict
 //   dZ[m,c] = (sum_j dout[m,j] W[j,c]) * (1 - h[m,c]^2)   (bf16 out)
 //   dW[j,c] += sum_m dout[m,j] h[m,c];   db[j] += sum_m dout[m,j]
 template <int NO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NO <= 2 ? 3 : 1)
 k_head_bwd(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict__ W,
            __nv_bfloat16* __restrict__ dz, int ldz, float* __restrict__ dW, float* __restrict__ db,
            float* __restrict__ dz_colsum, int M) {
@@ -1143,7 +1143,8 @@ VSS_API int vss_head_backward(const float* dout, const void* h, int ldh, const f
   if (!dout || !h || !W || !dz || !dW || !db || M <= 0) { g_tc_error = "vss_head_backward: bad argument"; return VSS_E_INVALID; }
   const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h);
   __nv_bfloat16* zp = reinterpret_cast<__nv_bfloat16*>(dz);
-  const int blocks = std::min((M + 7) / 8, 148 * 2);
+  // resident blocks per SM: 3 (n_out <= 2, <= 85 registers) or 1 (n_out = 6, 162 registers): one wave, more rows in flight
+  const int blocks = std::min((M + 7) / 8, 148 * (n_out <= 2 ? 3 : 1));
   cudaStream_t st = (cudaStream_t)stream;
   if (n_out == 1) tc::k_head_bwd<1><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, dz_colsum, M);
   else if (n_out == 2) tc::k_head_bwd<2><<<blocks, 256, 0, st>>>(dout, hp, ldh, W, zp, ldz, dW, db, dz_colsum, M);

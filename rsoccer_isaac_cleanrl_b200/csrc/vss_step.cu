@@ -210,12 +210,13 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5, W = NW - 1;
   const bool helper = warp == W;
   if (threadIdx.x == 0) ctr[3] = 0u;  // warps of this CTA that have finished
-  const long long env0 = a.env_begin + (long long)blockIdx.x * 32;
+  // a.fpw fields per tile (32, 16 or 8): lanes >= fpw idle in the per-field phases and help in the cooperative ones
+  const long long env0 = a.env_begin + (long long)blockIdx.x * a.fpw;
   float* S = T + lane;
   float* Sh = S + W_SHADOW * LDS;  // the field's shadow column
   const long long env = env0 + lane;
-  const bool active = env < a.n;
-  const int valid = (int)max(0LL, min(32LL, a.n - env0));
+  const bool active = lane < a.fpw && env < a.n;
+  const int valid = (int)max(0LL, min((long long)a.fpw, a.n - env0));
   constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
   const RngKey key = make_key(a, env);
   // 1a. state in (words dealt to the warps), then actions / OU noise per Philox block, progress restart,
@@ -430,6 +431,7 @@ struct vss_engine {
   void* aux_obs_bf16; float* aux_done_f; float* aux_timeout_f;  // vss_set_step_aux
   void* packed_rows;                                            // vss_set_step_packed
   int wpt_override;                                             // vss_set_step_warps_per_tile (0 = automatic)
+  int fpt_override;                                             // vss_set_step_fields_per_tile (0 = automatic)
   int64_t range_first, range_count;                             // vss_set_step_range (count 0 = all fields)
   cudaStream_t host_stream[2];                                  // vss_step_view_host: the two pipeline streams ...
   cudaEvent_t host_start, host_done[2];                         // ... and their fork / join events (created on first use)
@@ -485,16 +487,24 @@ static int auto_wpt(int64_t n) {
   return tiles <= 256 ? 8 : 1;
 }
 
-static LaunchShape launch_shape(int64_t n, bool step_kernel = true, int wpt_override = 0) {
+// Fields per tile of the k_step_cta shape: the smallest tile that still gives at most one CTA per SM. Measured
+// (profiles/r02_ae_step_shapes_fpt.txt, us per launch, full contract, 8 warps per tile, 32 / 16 / 8 fields per tile):
+// 1 024 fields 28.2 / 26.9 / 25.8; 4 096: 32.9 / 34.1 / 35.3; 8 192: 35.1 / 37.0 / 51.7 — smaller tiles only pay
+// while every tile still has an SM to itself (the launch is bound by ONE field's contact chain, not by the number
+// of fields that share a warp).
+static int auto_cta_fields(int64_t n) { return n <= 148 * 8 ? 8 : (n <= 148 * 16 ? 16 : 32); }
+
+static LaunchShape launch_shape(int64_t n, bool step_kernel = true, int wpt_override = 0, int fpt_override = 0) {
   LaunchShape s;
   s.wpt = !step_kernel ? 1 : (wpt_override > 0 ? wpt_override : auto_wpt(n));
   if (s.wpt > 1) {
-    s.wpb = s.wpt; s.fpw = 32; s.sync = true; s.stagger_ns = 0;
-    s.grid = (unsigned)((n + 31) / 32);
+    s.wpb = s.wpt; s.sync = true; s.stagger_ns = 0;
+    s.fpw = fpt_override > 0 ? fpt_override : auto_cta_fields(n);
+    s.grid = (unsigned)((n + s.fpw - 1) / s.fpw);
     s.smem = sizeof(float) * (TAB_WORDS + TILE_CTA_WORDS + CTR_WORDS);
     return s;
   }
-  s.fpw = !step_kernel ? 32 : (n < 148 * 40 ? 8 : (n < 148 * 192 ? 16 : 32));
+  s.fpw = !step_kernel ? 32 : (fpt_override > 0 ? fpt_override : (n < 148 * 40 ? 8 : (n < 148 * 192 ? 16 : 32)));
   const int64_t tiles = (n + s.fpw - 1) / s.fpw;
   s.wpb = tiles < 148 * 2 ? 1 : (tiles < 148 * 20 ? 2 : 4);
   s.sync = s.wpb == 4;
@@ -521,12 +531,12 @@ static StepArgs base_args(vss_handle h) {
 
 template <int VIEW, bool INJECT>
 static int launch_step(vss_handle h, StepArgs a, void* stream) {
-  const LaunchShape ls = launch_shape(h->n, true, h->wpt_override);
+  const LaunchShape ls = launch_shape(h->n, true, h->wpt_override, h->fpt_override);
   a.fpw = ls.fpw; a.stagger_ns = ls.stagger_ns;
   a.grid = ls.grid;  // a step is complete when this many CTAs have finished, over all its range launches
   unsigned grid = ls.grid;
   if (h->range_count > 0) {  // vss_set_step_range: this launch covers [first, first + count) — same CTA shape, fewer CTAs
-    const int64_t per_cta = ls.wpt > 1 ? 32 : (int64_t)ls.wpb * ls.fpw;
+    const int64_t per_cta = ls.wpt > 1 ? ls.fpw : (int64_t)ls.wpb * ls.fpw;
     if (h->range_first % per_cta != 0 || (h->range_count % per_cta != 0 && h->range_first + h->range_count != h->n))
       return fail(VSS_E_INVALID, "step range: first / count must be multiples of vss_step_granularity()");
     a.env_begin = h->range_first;
@@ -586,7 +596,7 @@ VSS_API int vss_create(vss_handle* out, const vss_params* p, int64_t num_envs, i
   if (!h) return fail(VSS_E_NOMEM, "vss_create: host allocation failed");
   h->device = device; h->n = num_envs; h->ld = (num_envs + 31) / 32 * 32; h->goff = global_env_offset;
   h->aux_obs_bf16 = nullptr; h->aux_done_f = nullptr; h->aux_timeout_f = nullptr; h->packed_rows = nullptr;
-  h->range_first = 0; h->range_count = 0; h->wpt_override = 0; h->host_ready = false;
+  h->range_first = 0; h->range_count = 0; h->wpt_override = 0; h->fpt_override = 0; h->host_ready = false;
   h->seed = seed; h->d_step = nullptr; h->params = *p; h->dp = derive_params(*p); h->state = nullptr;
   const size_t bytes = sizeof(float) * VSS_STATE_WORDS * (size_t)h->ld;
   e = cudaMalloc(&h->state, bytes);
@@ -782,13 +792,24 @@ VSS_API int vss_set_step_warps_per_tile(vss_handle h, int warps) {
   return VSS_OK;
 }
 VSS_API int vss_step_warps_per_tile(vss_handle h) {
-  return h ? launch_shape(h->n, true, h->wpt_override).wpt : 0;
+  return h ? launch_shape(h->n, true, h->wpt_override, h->fpt_override).wpt : 0;
+}
+
+VSS_API int vss_set_step_fields_per_tile(vss_handle h, int fields) {
+  if (!h) return fail(VSS_E_INVALID, "vss_set_step_fields_per_tile: null handle");
+  if (fields != 0 && fields != 8 && fields != 16 && fields != 32)
+    return fail(VSS_E_INVALID, "vss_set_step_fields_per_tile: 0 (automatic), 8, 16 or 32");
+  h->fpt_override = fields;
+  return VSS_OK;
+}
+VSS_API int vss_step_fields_per_tile(vss_handle h) {
+  return h ? launch_shape(h->n, true, h->wpt_override, h->fpt_override).fpw : 0;
 }
 
 VSS_API int64_t vss_step_granularity(vss_handle h) {
   if (!h) return 0;
-  const LaunchShape ls = launch_shape(h->n, true, h->wpt_override);
-  return ls.wpt > 1 ? 32 : (int64_t)ls.wpb * ls.fpw;
+  const LaunchShape ls = launch_shape(h->n, true, h->wpt_override, h->fpt_override);
+  return ls.wpt > 1 ? ls.fpw : (int64_t)ls.wpb * ls.fpw;
 }
 
 VSS_API int vss_set_step_range(vss_handle h, int64_t first_field, int64_t num_fields) {

@@ -96,6 +96,15 @@ class Engine:
     def warps_per_tile(self, w):
         check(self.lib.vss_set_step_warps_per_tile(self._h, int(w)))
 
+    @property
+    def fields_per_tile(self):
+        """Fields per tile of the step kernels (include/vss_b200.h: vss_set_step_fields_per_tile); 0 on write = automatic."""
+        return int(self.lib.vss_step_fields_per_tile(self._h))
+
+    @fields_per_tile.setter
+    def fields_per_tile(self, f):
+        check(self.lib.vss_set_step_fields_per_tile(self._h, int(f)))
+
     def set_step_range(self, first_field=0, num_fields=0):
         check(self.lib.vss_set_step_range(self._h, int(first_field), int(num_fields)))
 

@@ -39,6 +39,7 @@ class EmuBackend:
         return cls._lib
 
     wpt = 1   # warps per tile: 1 = the k_step structure, 2..8 = the k_step_cta structure
+    fpt = 32  # fields per tile of the k_step_cta structure (32, 16 or 8)
 
     def __init__(self, n, seed=0, goff=0, params=None):
         from oracle import vss_oracle as orc
@@ -74,7 +75,7 @@ class EmuBackend:
                                  C.c_uint(self.step_count & 0xFFFFFFFF), _p(actions), _p(inject), _p(reset_buf),
                                  _p(obs), _p(term_obs), _p(rew), _p(timeout), _p(progress_f), _p(policy_action),
                                  _p(action_buf), _p(reward_v), _p(done_v), _p(ep_ret), _p(ep_len), _p(ret_ret),
-                                 _p(ret_len), _p(packed), C.c_int(self.wpt))
+                                 _p(ret_len), _p(packed), C.c_int(self.wpt), C.c_int(self.fpt))
         assert rc == 0
         self.step_count += 1
 
@@ -115,6 +116,7 @@ class GpuBackend:
 
     name = "gpu"
     wpt = None   # None = the library's automatic launch shape; 1..8 forces warps per tile
+    fpt = None   # None = automatic; 8 / 16 / 32 forces the fields per tile
 
     def __init__(self, n, seed=0, goff=0, params=None):
         import torch
@@ -129,6 +131,8 @@ class GpuBackend:
         self.eng = R.Engine(n, "cuda:0", seed=seed, global_env_offset=goff, params=p)
         if self.wpt is not None:
             self.eng.warps_per_tile = self.wpt
+        if self.fpt is not None:
+            self.eng.fields_per_tile = self.fpt
         self.ld = self.eng.ld
         self.dev = torch.device("cuda:0")
 
@@ -206,6 +210,9 @@ class GpuBackend:
         return out
 
 
-def with_wpt(Backend, wpt):
-    """The same backend with a forced launch shape (warps per tile)."""
-    return type(f"{Backend.__name__}W{wpt}", (Backend,), {"wpt": wpt})
+def with_wpt(Backend, wpt, fpt=None):
+    """The same backend with a forced launch shape (warps per tile, and optionally fields per tile)."""
+    attrs = {"wpt": wpt}
+    if fpt is not None:
+        attrs["fpt"] = fpt
+    return type(f"{Backend.__name__}W{wpt}F{fpt}", (Backend,), attrs)

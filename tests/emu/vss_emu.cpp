@@ -66,16 +66,16 @@ static void emu_step_t(const StepArgs& a, const DevParams& P) {
 // and a helper warp that computes the resets speculatively into shadow columns): the phases below are the
 // kernel's, each CTA barrier becomes the end of a loop over (warp, lane).
 template <int VIEW, bool INJECT>
-static void emu_step_cta_t(const StepArgs& a, const DevParams& P, int NW) {
+static void emu_step_cta_t(const StepArgs& a, const DevParams& P, int NW, int F) {
   constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
   const int W = NW - 1;
-  const long long tiles = (a.n + 31) / 32;
+  const long long tiles = (a.n + F - 1) / F;  // F = 32, 16 or 8 fields per tile (vss_set_step_fields_per_tile)
 #pragma omp parallel for schedule(static)
   for (long long tile = 0; tile < tiles; ++tile) {
     std::vector<float> Tbuf(TILE_CTA_WORDS, 0.0f);
     float* T = Tbuf.data();
-    const long long env0 = tile * 32;
-    const int valid = (int)std::min(32LL, a.n - env0);
+    const long long env0 = tile * F;
+    const int valid = (int)std::min((long long)F, a.n - env0);
 #define EACH_THREAD for (int warp = 0; warp < NW; ++warp) for (int lane = 0; lane < valid; ++lane)
 #define EACH_BODY_THREAD for (int warp = 0; warp < W; ++warp) for (int lane = 0; lane < valid; ++lane)
     EACH_THREAD load_state_words(T + lane, a.state, a.ld, env0 + lane, warp, NW);
@@ -155,7 +155,7 @@ __attribute__((visibility("default"))) int emu_step(
     unsigned long long seed, unsigned int step, const float* actions, const float* inject, long long* reset_buf,
     float* obs, float* term_obs, float* rew, uint8_t* timeout, float* progress_f, const float* policy_action,
     float* action_buf, float* reward_v, long long* done_v, float* ep_ret, int* ep_len, float* ret_ret,
-    int* ret_len, void* packed, int wpt) {
+    int* ret_len, void* packed, int wpt, int fpt) {
   const DevParams P = derive_params(*p);
   StepArgs a;
   memset(&a, 0, sizeof(a));
@@ -167,11 +167,11 @@ __attribute__((visibility("default"))) int emu_step(
   a.action_buf = action_buf; a.reward_v = reward_v; a.done_v = done_v; a.ep_ret = ep_ret; a.ep_len = ep_len;
   a.ret_ret = ret_ret; a.ret_len = ret_len; a.packed = packed;
   if (wpt > 1) {  // the k_step_cta structure
-    if (wpt > MAX_WPT) return -1;
-    if (view == VIEW_FULL) { if (inject) emu_step_cta_t<VIEW_FULL, true>(a, P, wpt); else emu_step_cta_t<VIEW_FULL, false>(a, P, wpt); }
-    else if (view == VSS_VIEW_SA) emu_step_cta_t<VSS_VIEW_SA, false>(a, P, wpt);
-    else if (view == VSS_VIEW_CMA) emu_step_cta_t<VSS_VIEW_CMA, false>(a, P, wpt);
-    else if (view == VSS_VIEW_DMA) emu_step_cta_t<VSS_VIEW_DMA, false>(a, P, wpt);
+    if (wpt > MAX_WPT || (fpt != 8 && fpt != 16 && fpt != 32)) return -1;
+    if (view == VIEW_FULL) { if (inject) emu_step_cta_t<VIEW_FULL, true>(a, P, wpt, fpt); else emu_step_cta_t<VIEW_FULL, false>(a, P, wpt, fpt); }
+    else if (view == VSS_VIEW_SA) emu_step_cta_t<VSS_VIEW_SA, false>(a, P, wpt, fpt);
+    else if (view == VSS_VIEW_CMA) emu_step_cta_t<VSS_VIEW_CMA, false>(a, P, wpt, fpt);
+    else if (view == VSS_VIEW_DMA) emu_step_cta_t<VSS_VIEW_DMA, false>(a, P, wpt, fpt);
     else return -1;
     return 0;
   }

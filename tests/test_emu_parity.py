@@ -78,10 +78,10 @@ def test_packed_host_rows(view):
 
 
 # ---- the k_step_cta structure (one tile shared by W warps, bodies dealt to the warps)
-@pytest.mark.parametrize("wpt", [2, 3, 5, 8])
+@pytest.mark.parametrize("wpt", [2, 3, 5, 8, (8, 8), (4, 16)])
 def test_cta_structure_matches_oracle(wpt):
     from backends import with_wpt
-    B = with_wpt(EmuBackend, wpt)
+    B = with_wpt(EmuBackend, *wpt) if isinstance(wpt, tuple) else with_wpt(EmuBackend, wpt)
     pc.check_reset(B, n=300)
     assert pc.check_injected(B, n=300, steps=3) > 0
     pc.check_rollout(B, n=500, steps=12)
@@ -90,13 +90,14 @@ def test_cta_structure_matches_oracle(wpt):
         pc.check_packed_rows(B, view, n=200, steps=3)
 
 
-@pytest.mark.parametrize("wpt", [2, 8])
+@pytest.mark.parametrize("wpt", [2, 8, (8, 8), (3, 16)])
 def test_cta_structure_is_bit_identical_to_the_lane_structure(wpt):
     """Same per-body code in the same order per field: every output word equal, over a contact-heavy rollout."""
     import numpy as np
     from backends import with_wpt
     n = 777
-    a, b = EmuBackend(n, seed=3, goff=9), with_wpt(EmuBackend, wpt)(n, seed=3, goff=9)
+    B = with_wpt(EmuBackend, *wpt) if isinstance(wpt, tuple) else with_wpt(EmuBackend, wpt)
+    a, b = EmuBackend(n, seed=3, goff=9), B(n, seed=3, goff=9)
     rb_a, rb_b = np.ones(n, np.int64), np.ones(n, np.int64)
     oa, ob = a.reset_dones(rb_a), b.reset_dones(rb_b)
     assert np.array_equal(pc.bits(oa), pc.bits(ob))

@@ -296,9 +296,10 @@ def test_every_launch_shape_is_bit_identical(Gpu):
     and the three views), on a size that is ragged against the 32-field tiles, over contact-heavy steps."""
     from backends import with_wpt
     n = 4097
-    shapes = [1, 2, 4, 7, 8]
-    bes = [with_wpt(Gpu, w)(n, seed=3, goff=9) for w in shapes]
-    assert [b.eng.warps_per_tile for b in bes] == shapes
+    shapes = [1, 2, 4, 7, 8, (8, 16), (8, 8), (3, 8), (1, 32), (1, 8)]   # warps per tile or (warps, fields) per tile
+    bes = [(with_wpt(Gpu, *w) if isinstance(w, tuple) else with_wpt(Gpu, w))(n, seed=3, goff=9) for w in shapes]
+    assert [b.eng.warps_per_tile for b in bes] == [w[0] if isinstance(w, tuple) else w for w in shapes]
+    assert [b.eng.fields_per_tile for b in bes[5:]] == [16, 8, 8, 32, 8]
     rbs = [np.ones(n, np.int64) for _ in bes]
     obs = [b.reset_dones(rb) for b, rb in zip(bes, rbs)]
     for rb in rbs:
@@ -331,10 +332,11 @@ def test_every_launch_shape_is_bit_identical(Gpu):
         assert all(b.step_count == 3 for b in bes)
 
 
-@pytest.mark.parametrize("wpt,n", [(7, 4096), (4, 21845), (2, 65536), (8, 1000), (2, 131072)])
+@pytest.mark.parametrize("wpt,n", [(7, 4096), (4, 21845), (2, 65536), (8, 1000), (2, 131072), ((8, 8), 4096),
+                                   ((8, 16), 16384), ((5, 8), 1001)])
 def test_cta_launch_shapes_track_oracle(Gpu, wpt, n):
     from backends import with_wpt
-    B = with_wpt(Gpu, wpt)
+    B = with_wpt(Gpu, *wpt) if isinstance(wpt, tuple) else with_wpt(Gpu, wpt)
     r = pc.check_rollout(B, n=n, steps=4, seed=n % 97)
     assert r["dones"] > 0 and r["timeouts"] > 0 and r["goals"] > 0
     assert pc.check_injected(B, n=min(n, 20000), steps=2) > 0
