@@ -329,6 +329,33 @@ VSS_API int vss_head_forward(const void* h, int ldh, const float* W, const float
 VSS_API int vss_head_backward(const float* dout, const void* h, int ldh, const float* W, void* dz, int ldz,
                               float* dW, float* db, float* dz_colsum, int M, int n_out, void* stream);
 
+/* The whole Agent MLP forward in ONE launch (csrc/mlp_fused.cu): for each of n_nets (1 or 2) networks that share the
+ * input rows - the actor mean and the critic value of the same observations, Agent.get_action_and_value,
+ * ppo...:155-164 called once per rollout step at ppo...:259-261 -
+ *   out [M, n_out] f32 = Linear(256, n_out)(tanh-MLP(x)),  MLP = obs -> 256 -> 512 -> 512 -> 256 (ppo...:130-152).
+ * x16 [M, 64] bf16: the observations zero-padded to 64 columns (what vss_set_step_aux's obs_bf16 output and
+ * vss_gather_pad_bf16 produce), row stride ldx elements. w[l] bf16 row-major [256,64], [512,256], [512,512], [256,512]
+ * (nn.Linear layout, the first K-padded to 64), b[l] f32; head_w f32 [n_out, 256], head_b f32 [n_out]; n_out in
+ * {1, 2, 6}. The hidden activations never leave the SM (shared memory / TMEM); same per-element arithmetic as four
+ * vss_gemm_bf16_tn(EPI_BIAS_TANH_BF16) + vss_head_forward. epilogue_warps: 0 (default), 4 or 8 - a tuning knob with
+ * identical results. All pointers 16-byte aligned. */
+typedef struct vss_mlp_net {
+  const void* w[4];
+  const float* b[4];
+  const float* head_w;
+  const float* head_b;
+  float* out;
+  int32_t n_out;
+  int32_t reserved;
+} vss_mlp_net;
+VSS_API int vss_mlp_forward_fused(const void* x16, int ldx, int M, const vss_mlp_net* nets, int n_nets,
+                                  int epilogue_warps, void* stream);
+/* The same launch with a profiling hook: the first CTA records 11 %globaltimer stamps (ns) at its phase boundaries
+ * into stamps (device memory, NULL = none): [0] entry, [1] barriers + TMEM ready, [2 + 2l] accumulator of hidden
+ * layer l complete, [3 + 2l] epilogue of layer l done, [10] exit. */
+VSS_API int vss_mlp_forward_fused_timed(const void* x16, int ldx, int M, const vss_mlp_net* nets, int n_nets,
+                                        int epilogue_warps, unsigned long long* stamps, void* stream);
+
 /* ---- the small pieces of the PPO loop, one launch each (ppo_continuous_action_isaacgym.py) ------
  * Normal(mean, exp(logstd)).sample() and .log_prob(action).sum(1) of Agent.get_action_and_value
  * (ppo...:155-164). mean/action (M,A) f32, logstd (A), logprob (M); A in {2,6}. Normals come from

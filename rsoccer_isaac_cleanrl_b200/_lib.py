@@ -60,6 +60,14 @@ class ConvertJob(C.Structure):
 
 MAX_CONVERT_JOBS = 8
 
+
+class MlpNet(C.Structure):
+    """`vss_mlp_net` of include/vss_b200.h."""
+
+    _fields_ = [("w", C.c_void_p * 4), ("b", C.c_void_p * 4), ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+                ("out", C.c_void_p), ("n_out", C.c_int32), ("reserved", C.c_int32)]
+
+
 # every symbol include/vss_b200.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
 _SYMBOLS = {
@@ -94,6 +102,8 @@ _SYMBOLS = {
                                          _VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_gemm_last_error": (C.c_char_p, []),
     "vss_head_forward": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
+    "vss_mlp_forward_fused": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(MlpNet), C.c_int, C.c_int, _VP]),
+    "vss_mlp_forward_fused_timed": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(MlpNet), C.c_int, C.c_int, _VP, _VP]),
     "vss_head_backward": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
     "vss_colsum_bf16": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_gather_pad_bf16": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),

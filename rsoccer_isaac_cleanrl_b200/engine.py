@@ -277,6 +277,39 @@ def head_forward(h, W, b, out=None):
     return out
 
 
+def mlp_forward_fused(x16, nets, epilogue_warps=0, stamps=None):
+    """The whole MLP forward of 1 or 2 networks over the same rows in one launch (include/vss_b200.h:
+    vss_mlp_forward_fused). x16 [M,64] bf16; nets = [(w16 list of 4 bf16 matrices, b list of 4 f32 vectors, head_w,
+    head_b, out [M,n_out] f32), ...]. Returns the list of `out` tensors."""
+    lib = _lib.load_library()
+    M = x16.shape[0]
+    assert x16.dtype == torch.bfloat16 and x16.shape[1] == 64 and x16.stride(1) == 1
+    shapes = [(256, 64), (512, 256), (512, 512), (256, 512)]
+    arr = (_lib.MlpNet * len(nets))()
+    outs = []
+    for a, (w16, bs, head_w, head_b, out) in zip(arr, nets):
+        for l in range(4):
+            assert w16[l].dtype == torch.bfloat16 and tuple(w16[l].shape) == shapes[l] and w16[l].is_contiguous()
+            assert bs[l].dtype == torch.float32 and bs[l].is_contiguous() and bs[l].numel() == shapes[l][0]
+            a.w[l], a.b[l] = w16[l].data_ptr(), bs[l].data_ptr()
+        n_out = head_w.shape[0]
+        assert head_w.dtype == torch.float32 and head_w.is_contiguous() and head_w.shape[1] == 256
+        assert head_b.dtype == torch.float32 and head_b.is_contiguous()
+        if out is None:
+            out = torch.empty((M, n_out), device=x16.device, dtype=torch.float32)
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == M * n_out
+        a.head_w, a.head_b, a.out, a.n_out = head_w.data_ptr(), head_b.data_ptr(), out.data_ptr(), n_out
+        outs.append(out)
+    if stamps is not None:  # profiling hook: 11 int64 globaltimer stamps of the first CTA
+        assert stamps.dtype == torch.int64 and stamps.is_cuda and stamps.numel() >= 11 and stamps.is_contiguous()
+    rc = lib.vss_mlp_forward_fused_timed(x16.data_ptr(), x16.stride(0), M, arr, len(nets), int(epilogue_warps),
+                                         None if stamps is None else stamps.data_ptr(),
+                                         torch.cuda.current_stream(x16.device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(lib.vss_gemm_last_error().decode())
+    return outs
+
+
 def head_backward(dout, h, W, dW=None, db=None, dz_colsum=None):
     """(dz [M,256] bf16, dW [n_out,256] f32, db [n_out] f32) of the head, tanh' of h fused into dz.
     dW / db, when given, are accumulated into (contiguous f32 buffers such as the .grad views)."""

@@ -135,3 +135,55 @@ def test_tc_mlp_matches_fp32_agent_forward_and_backward():
         num = (g0[k] - g1[k]).norm().item()
         den = g0[k].norm().item() + 1e-12
         assert num / den < 0.06, (k, num / den)
+
+
+def _mlp_pair(n_act, seed):
+    """Actor-shaped and critic-shaped tanh MLPs with non-trivial heads, plus their bf16 operand copies."""
+    from rsoccer_isaac_cleanrl_b200.tc_mlp import MlpWeights
+    torch.manual_seed(seed)
+    def seq(n_out):
+        dims = [52, 256, 512, 512, 256]
+        layers = []
+        for i in range(4):
+            layers += [torch.nn.Linear(dims[i], dims[i + 1]), torch.nn.Tanh()]
+        layers.append(torch.nn.Linear(256, n_out))
+        s = torch.nn.Sequential(*layers).cuda()
+        with torch.no_grad():
+            for m in s:
+                if isinstance(m, torch.nn.Linear):
+                    m.weight.mul_(2.0); m.bias.normal_(0, 0.3)
+        return s
+    return MlpWeights(seq(n_act)), MlpWeights(seq(1))
+
+
+@pytest.mark.parametrize("M,n_act,ew", [(4096, 2, 8), (4096, 2, 4), (1000, 6, 8), (128, 2, 8), (77, 6, 4), (65535, 2, 8),
+                                        (16384, 6, 8)])
+def test_fused_mlp_forward_matches_the_layer_by_layer_path(M, n_act, ew):
+    """include/vss_b200.h vss_mlp_forward_fused (csrc/mlp_fused.cu) against four vss_gemm_bf16_tn launches + the head
+    kernel: the hidden activations are the same bits (same accumulation order, same epilogue arithmetic), the 256-term
+    head sum only differs in summation order -> |diff| <= 2e-5 * (sum |w| + |out|); and both against fp32 torch on
+    the bf16-rounded weights (bf16 activations: 3e-2 of the output scale)."""
+    from rsoccer_isaac_cleanrl_b200.engine import gather_pad_bf16, mlp_forward_fused
+    from rsoccer_isaac_cleanrl_b200.tc_mlp import forward_explicit
+    actor, critic = _mlp_pair(n_act, seed=M % 13)
+    x = torch.randn(M, 52, device="cuda")
+    x16 = gather_pad_bf16(x, None, 64)
+    ref_a, _ = forward_explicit(actor, x16)
+    ref_c, _ = forward_explicit(critic, x16)
+    nets = [(mw.w16, [b.detach() for b in mw.bs], mw.head_w.detach(), mw.head_b.detach(), None) for mw in (actor, critic)]
+    out_a, out_c = mlp_forward_fused(x16, nets, epilogue_warps=ew)
+    torch.cuda.synchronize()
+    for out, ref, mw in ((out_a, ref_a, actor), (out_c, ref_c, critic)):
+        assert out.shape == ref.shape and torch.isfinite(out).all()
+        bound = 2e-5 * (mw.head_w.detach().abs().sum(1).max().item() + ref.abs().max().item())
+        assert (out - ref).abs().max().item() <= bound, ((out - ref).abs().max().item(), bound)
+        with torch.no_grad():
+            h = x16[:, :52].float()
+            for l in range(4):
+                h = torch.tanh(h @ mw.w16[l][:, :h.shape[1]].float().t() + mw.bs[l])
+            fp32 = h @ mw.head_w.t() + mw.head_b
+        assert (out - fp32).abs().max().item() < 3e-2 * fp32.abs().max().item() + 1e-2
+    # one network alone, and a second call (barrier phases, TMEM release) give the same numbers
+    only_c, = mlp_forward_fused(x16, nets[1:], epilogue_warps=ew)
+    again_a, again_c = mlp_forward_fused(x16, nets, epilogue_warps=ew)
+    assert torch.equal(only_c, out_c) and torch.equal(again_a, out_a) and torch.equal(again_c, out_c)
