@@ -348,13 +348,28 @@ typedef struct vss_mlp_net {
   int32_t n_out;
   int32_t reserved;
 } vss_mlp_net;
+/* Optional: draw the action in the same launch (network 0 = the actor mean, n_out = action width 2 or 6):
+ * action = Normal(out_0, exp(logstd)).sample(), logprob = log_prob(action).sum(1) - the arithmetic and the Philox stream
+ * of vss_policy_sample, with call index *counter + call_offset. The launch does NOT advance *counter: a caller that
+ * captures T steps in a CUDA graph passes call_offset = 0..T-1 and adds T to the counter once per rollout.
+ * nets[0].out may then be NULL (the mean is not stored). */
+typedef struct vss_mlp_sampling {
+  const float* logstd;      /* f32 [n_out] */
+  const uint32_t* counter;  /* device word */
+  uint64_t seed;
+  uint32_t call_offset;
+  uint32_t reserved;
+  float* action;            /* f32 [M, n_out] */
+  float* logprob;           /* f32 [M] */
+} vss_mlp_sampling;
 VSS_API int vss_mlp_forward_fused(const void* x16, int ldx, int M, const vss_mlp_net* nets, int n_nets,
-                                  int epilogue_warps, void* stream);
+                                  const vss_mlp_sampling* sampling, int epilogue_warps, void* stream);
 /* The same launch with a profiling hook: the first CTA records 11 %globaltimer stamps (ns) at its phase boundaries
- * into stamps (device memory, NULL = none): [0] entry, [1] barriers + TMEM ready, [2 + 2l] accumulator of hidden
- * layer l complete, [3 + 2l] epilogue of layer l done, [10] exit. */
+ * into stamps (device memory, NULL = none): [0] entry, [1] barriers + TMEM ready, [2 + 2l] first accumulator chunk of
+ * hidden layer l complete, [3 + 2l] epilogue of layer l done (one epilogue warp's view), [10] exit. */
 VSS_API int vss_mlp_forward_fused_timed(const void* x16, int ldx, int M, const vss_mlp_net* nets, int n_nets,
-                                        int epilogue_warps, unsigned long long* stamps, void* stream);
+                                        const vss_mlp_sampling* sampling, int epilogue_warps,
+                                        unsigned long long* stamps, void* stream);
 
 /* ---- the small pieces of the PPO loop, one launch each (ppo_continuous_action_isaacgym.py) ------
  * Normal(mean, exp(logstd)).sample() and .log_prob(action).sum(1) of Agent.get_action_and_value

@@ -61,6 +61,13 @@ class ConvertJob(C.Structure):
 MAX_CONVERT_JOBS = 8
 
 
+class MlpSampling(C.Structure):
+    """`vss_mlp_sampling` of include/vss_b200.h."""
+
+    _fields_ = [("logstd", C.c_void_p), ("counter", C.c_void_p), ("seed", C.c_uint64), ("call_offset", C.c_uint32),
+                ("reserved", C.c_uint32), ("action", C.c_void_p), ("logprob", C.c_void_p)]
+
+
 class MlpNet(C.Structure):
     """`vss_mlp_net` of include/vss_b200.h."""
 
@@ -102,8 +109,10 @@ _SYMBOLS = {
                                          _VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_gemm_last_error": (C.c_char_p, []),
     "vss_head_forward": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
-    "vss_mlp_forward_fused": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(MlpNet), C.c_int, C.c_int, _VP]),
-    "vss_mlp_forward_fused_timed": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(MlpNet), C.c_int, C.c_int, _VP, _VP]),
+    "vss_mlp_forward_fused": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(MlpNet), C.c_int, C.POINTER(MlpSampling),
+                                        C.c_int, _VP]),
+    "vss_mlp_forward_fused_timed": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(MlpNet), C.c_int,
+                                              C.POINTER(MlpSampling), C.c_int, _VP, _VP]),
     "vss_head_backward": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
     "vss_colsum_bf16": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_gather_pad_bf16": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),

@@ -26,6 +26,7 @@
 #include <string>
 
 #include "../../include/vss_b200.h"
+#include "ppo_sample.cuh"
 #include "tc_common.cuh"
 
 namespace tc {
@@ -35,7 +36,7 @@ constexpr int FM_STAGE_BYTES = FM_NCHUNK * BK * 2;  // 32 KB
 constexpr int FM_STAGES = 3;
 constexpr int FM_BLOCK_BYTES = BM * BK * 2;         // one 128 x 64 k-block of the activation buffer: 16 KB
 constexpr int FM_ACT_BYTES = 8 * FM_BLOCK_BYTES;    // 128 rows x 512 columns bf16
-constexpr int FM_SMEM = FM_ACT_BYTES + FM_STAGES * FM_STAGE_BYTES + 128 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int FM_SMEM = FM_ACT_BYTES + FM_STAGES * FM_STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 constexpr int FM_MAX_NETS = 2;
 
 __host__ __device__ constexpr int fm_k(int l) { return l == 0 ? 64 : (l == 1 ? 256 : 512); }
@@ -54,6 +55,12 @@ struct FusedArgs {
   CUtensorMap x;          // bf16 [M, 64] (observations, zero-padded to 64 columns), box 64 x 128
   FusedNet net[FM_MAX_NETS];
   int M;
+  // optional, network 0 only: sample the action from Normal(out, exp(logstd)) in the same launch (null action = off)
+  const float* logstd;
+  const uint32_t* counter;   // device word: call index of the sampling stream (the caller advances it)
+  uint32_t call_offset, seed_lo, seed_hi;
+  float* action;             // f32 [M, n_out]
+  float* logprob;            // f32 [M]
   unsigned long long* stamps;  // profiling (vss_mlp_forward_fused_timed): CTA (0,0) records globaltimer at its phase boundaries
 };
 
@@ -117,6 +124,21 @@ __device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float*
   }
 }
 
+// ---- the schedule ---------------------------------------------------------------------------------------------
+// Six accumulator tasks t = 0..5: (layer, chunk of 256 output columns) = (0,0) (1,0) (1,1) (2,0) (2,1) (3,0); task t
+// accumulates in TMEM half t & 1 (columns [256 (t & 1), +256)), so the MMAs of task t + 1 run while the epilogue
+// drains task t. The activation buffer has 8 k-blocks (128 rows x 64 columns); the input of layer l lives in
+//   layer 0: block 0 (the observation tile);   layer 1: logical k-block j -> block j;
+//   layers 2, 3: logical k-block j -> block (j + 4) % 8
+// so that the epilogue of a chunk always writes blocks the MMAs still in flight do not read - except task (2,0),
+// whose output replaces the blocks task (2,1) is reading: it waits per block (blk_free) for those reads to retire.
+// The MMAs of the next layer start on a k-block as soon as the epilogue has written it (blk_ready per block).
+__host__ __device__ constexpr int fm_task_layer(int t) { return t == 0 ? 0 : (t <= 2 ? 1 : (t <= 4 ? 2 : 3)); }
+__host__ __device__ constexpr int fm_task_chunk(int t) { return (t == 2 || t == 4) ? 1 : 0; }
+__device__ __forceinline__ int fm_phys(int layer, int kb) { return layer <= 1 ? kb : ((kb + 4) & 7); }
+// does layer l read block p?
+__device__ __forceinline__ int fm_reads(int l, int p) { return l == 0 ? (p == 0) : (l == 1 ? (p < 4) : 1); }
+
 template <int EW>  // epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, half of the columns each)
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 k_mlp_fwd(const __grid_constant__ FusedArgs g) {
@@ -126,10 +148,12 @@ k_mlp_fwd(const __grid_constant__ FusedArgs g) {
   uint8_t* ring = smem + FM_ACT_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + FM_STAGES * FM_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + FM_STAGES;
-  uint64_t* x_full = empty_bar + FM_STAGES;   // the observation tile has landed in k-block 0
-  uint64_t* acc_full = x_full + 1;            // all MMAs of the current layer have retired (phase = layer & 1)
-  uint64_t* act_ready = acc_full + 1;         // the epilogue has written the next layer's A operand (phase = layer & 1)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 1);
+  uint64_t* x_full = empty_bar + FM_STAGES;   // the observation tile has landed in block 0
+  uint64_t* acc_full = x_full + 1;            // [2] every MMA of the task in this TMEM half has retired
+  uint64_t* acc_free = acc_full + 2;          // [2] every epilogue warp has read this TMEM half out
+  uint64_t* blk_ready = acc_free + 2;         // [8] the epilogue has written this block (next layer's A operand)
+  uint64_t* blk_free = blk_ready + 8;         // [8] the MMAs of the layer that read this block have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(blk_free + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const FusedNet& net = g.net[blockIdx.y];
@@ -138,7 +162,9 @@ k_mlp_fwd(const __grid_constant__ FusedArgs g) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < FM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(x_full, 1); mbar_init(acc_full, 1); mbar_init(act_ready, EW);
+    mbar_init(x_full, 1);
+    for (int h = 0; h < 2; ++h) { mbar_init(&acc_full[h], 1); mbar_init(&acc_free[h], EW); }
+    for (int b = 0; b < 8; ++b) { mbar_init(&blk_ready[b], EW); mbar_init(&blk_free[b], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -149,20 +175,19 @@ k_mlp_fwd(const __grid_constant__ FusedArgs g) {
   if (threadIdx.x == 64) stamp(g, 1);
 
   if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer: the observation tile, then every weight stage of the four layers in order
+    if (lane == 0) {  // ---- TMA producer: the observation tile, then every weight stage in the order the MMAs consume them
       mbar_expect_tx(x_full, FM_BLOCK_BYTES);
       tma_load_2d(act, &g.x, x_full, 0, m0);
       uint32_t s = 0, ph = 0;
 #pragma unroll 1
-      for (int l = 0; l < 4; ++l) {
-        const int chunks = fm_n(l) / FM_NCHUNK, kbs = fm_k(l) / BK;
-        for (int ch = 0; ch < chunks; ++ch)
-          for (int kb = 0; kb < kbs; ++kb) {
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_expect_tx(&full_bar[s], FM_STAGE_BYTES);
-            tma_load_2d(ring + s * FM_STAGE_BYTES, &net.w[l], &full_bar[s], kb * BK, ch * FM_NCHUNK);
-            if (++s == FM_STAGES) { s = 0; ph ^= 1; }
-          }
+      for (int t = 0; t < 6; ++t) {
+        const int l = fm_task_layer(t), ch = fm_task_chunk(t), kbs = fm_k(l) / BK;
+        for (int kb = 0; kb < kbs; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], FM_STAGE_BYTES);
+          tma_load_2d(ring + s * FM_STAGE_BYTES, &net.w[l], &full_bar[s], kb * BK, ch * FM_NCHUNK);
+          if (++s == FM_STAGES) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -171,64 +196,92 @@ k_mlp_fwd(const __grid_constant__ FusedArgs g) {
       const uint32_t act_addr = smem_u32(act), ring_addr = smem_u32(ring);
       uint32_t s = 0, ph = 0;
 #pragma unroll 1
-      for (int l = 0; l < 4; ++l) {
-        if (l == 0) mbar_wait(x_full, 0); else mbar_wait(act_ready, (uint32_t)(l - 1) & 1u);
+      for (int t = 0; t < 6; ++t) {
+        const int l = fm_task_layer(t), ch = fm_task_chunk(t), kbs = fm_k(l) / BK, h = t & 1;
+        const bool last_chunk = (ch + 1) * FM_NCHUNK == fm_n(l);
+        // the epilogue has drained the task that used this TMEM half before (t - 2); passes at once for t < 2
+        mbar_wait(&acc_free[h], (((uint32_t)t >> 1) & 1u) ^ 1u);
+        if (l == 0) mbar_wait(x_full, 0);
         tc_fence_after();
-        const int chunks = fm_n(l) / FM_NCHUNK, kbs = fm_k(l) / BK;
-        for (int ch = 0; ch < chunks; ++ch) {
-          const uint32_t tmem_d = tmem_base + (uint32_t)(ch * FM_NCHUNK);
-          for (int kb = 0; kb < kbs; ++kb) {
-            mbar_wait(&full_bar[s], ph);
-            tc_fence_after();
-            const uint64_t adesc = make_desc_k128(act_addr + kb * FM_BLOCK_BYTES);
-            const uint64_t bdesc = make_desc_k128(ring_addr + s * FM_STAGE_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(&empty_bar[s]);  // frees the ring stage when these MMAs retire
-            if (++s == FM_STAGES) { s = 0; ph ^= 1; }
+        const uint32_t tmem_d = tmem_base + (uint32_t)(h * FM_NCHUNK);
+        for (int kb = 0; kb < kbs; ++kb) {
+          const int p = fm_phys(l, kb);
+          if (l > 0) {  // written by the epilogue of layer l - 1: completion number l (blocks 0-3) or l - 1 (blocks 4-7)
+            mbar_wait(&blk_ready[p], (uint32_t)((p < 4 ? l : l - 1) - 1) & 1u);
           }
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = make_desc_k128(act_addr + p * FM_BLOCK_BYTES);
+          const uint64_t bdesc = make_desc_k128(ring_addr + s * FM_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[s]);                 // frees the ring stage when these MMAs retire
+          if (last_chunk) umma_commit(&blk_free[p]);  // ... and the activation block: no later MMA of this layer reads it
+          if (++s == FM_STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(acc_full);  // the layer's accumulator is complete, and the activation buffer is no longer read
+        umma_commit(&acc_full[h]);
       }
     }
   } else {
-    // ---- epilogue: this thread owns row q * 32 + lane of the block (TMEM lane), warp half h takes columns [h * N / 2 ...)
+    // ---- epilogue: this thread owns row q * 32 + lane of the block (TMEM lane). All epilogue warps work on the SAME
+    // 64-column k-block at a time (EW = 8: the two warps of a lane quarter take 32 columns of it each; EW = 4: one warp
+    // takes both halves), so the blocks become ready one after the other in the order the next layer's MMAs consume
+    // them, and only the last block's MMAs remain when the epilogue of a chunk ends.
+    constexpr int CPB = 8 / EW;          // 32-column TMEM loads per k-block per warp
+    constexpr int NLD = 4 * CPB;         // ... per 256-column chunk
     const int q = warp & 3, half = (warp - 2) >> 2, row = q * 32 + lane;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int col_of_warp = CPB == 1 ? 32 * half : 0;
     float hacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int l = 0; l < 4; ++l) {
-      const int per_warp = fm_n(l) / (EW / 4), c_begin = half * per_warp, c_end = c_begin + per_warp;
+    for (int t = 0; t < 6; ++t) {
+      const int l = fm_task_layer(t), ch = fm_task_chunk(t), h = t & 1;
+      const int c0 = ch * FM_NCHUNK + col_of_warp;  // output column of this warp's first load in this task
       const float* __restrict__ bias = net.bias[l];
-      mbar_wait(acc_full, (uint32_t)l & 1u);
+      mbar_wait(&acc_full[h], ((uint32_t)t >> 1) & 1u);
       tc_fence_after();
-      if (threadIdx.x == 64) stamp(g, 2 + 2 * l);
-      uint32_t va[32], vb[32];
-      tmem_ld32_issue(t_row + (uint32_t)c_begin, va);
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; c += 64) {
+      if (threadIdx.x == 64 && ch == 0) stamp(g, 2 + 2 * l);
+      const uint32_t tc0 = t_row + (uint32_t)(h * FM_NCHUNK + col_of_warp);
+      constexpr int STEP = CPB == 1 ? 64 : 32;   // column distance between this warp's consecutive loads
+      uint32_t v[2][32];
+      tmem_ld32_issue(tc0, v[0]);
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) {
         tmem_ld_wait();
-        tmem_ld32_issue(t_row + (uint32_t)(c + 32), vb);
-        if (l < 3) store_act_chunk(va, bias, act, row, c);
-        else if (net.n_out == 1) head_chunk<1>(va, bias, net.head_w, c, hacc);
-        else if (net.n_out == 2) head_chunk<2>(va, bias, net.head_w, c, hacc);
-        else head_chunk<6>(va, bias, net.head_w, c, hacc);
-        tmem_ld_wait();
-        if (c + 64 < c_end) tmem_ld32_issue(t_row + (uint32_t)(c + 64), va);
-        if (l < 3) store_act_chunk(vb, bias, act, row, c + 32);
-        else if (net.n_out == 1) head_chunk<1>(vb, bias, net.head_w, c + 32, hacc);
-        else if (net.n_out == 2) head_chunk<2>(vb, bias, net.head_w, c + 32, hacc);
-        else head_chunk<6>(vb, bias, net.head_w, c + 32, hacc);
+        if (i + 1 < NLD) {
+          tmem_ld32_issue(tc0 + (uint32_t)(STEP * (i + 1)), v[(i + 1) & 1]);
+        } else {  // this warp has read its share of the TMEM half: hand it back before the arithmetic
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_free[h]);
+        }
+        const int c = c0 + STEP * i;
+        if (l < 3) {
+          const int p = fm_phys(l + 1, c >> 6);
+          if (i % CPB == 0) {
+            // the layers up to l that read block p have all retired their MMAs (completion number n; n = 0: never read)
+            int n = 0;
+            for (int l2 = 0; l2 <= l; ++l2) n += fm_reads(l2, p);
+            mbar_wait(&blk_free[p], (uint32_t)(n - 1) & 1u);
+          }
+          uint32_t packed[16];
+          bias_tanh_pack(v[i & 1], bias + c, packed);
+          uint8_t* base = act + p * FM_BLOCK_BYTES + row * 128;
+          const int j0 = (c & 63) >> 3, sw = row & 7;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(base + (((j0 + j) ^ sw) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          if (i % CPB == CPB - 1) {  // this warp's share of the block is written: generic-proxy writes -> visible to the tensor core
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&blk_ready[p]);
+          }
+        } else if (net.n_out == 1) head_chunk<1>(v[i & 1], bias, net.head_w, c, hacc);
+        else if (net.n_out == 2) head_chunk<2>(v[i & 1], bias, net.head_w, c, hacc);
+        else head_chunk<6>(v[i & 1], bias, net.head_w, c, hacc);
       }
-      if (l < 3) {
-        // generic-proxy writes -> visible to the tensor core's (async proxy) reads; TMEM reads done before the
-        // next layer's MMAs overwrite the accumulator
-        tc_fence_before();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(act_ready);
-      }
-      if (threadIdx.x == 64) stamp(g, 3 + 2 * l);
+      if (threadIdx.x == 64 && (ch + 1) * FM_NCHUNK == fm_n(l)) stamp(g, 3 + 2 * l);
     }
     // head: combine the column halves (the activation buffer is free: every MMA has retired), add the bias, store
     if (EW == 8) {
@@ -244,8 +297,31 @@ k_mlp_fwd(const __grid_constant__ FusedArgs g) {
       }
     }
     if (half == 0 && m0 + row < g.M) {
-      float* o = net.out + (size_t)(m0 + row) * net.n_out;
-      for (int a = 0; a < net.n_out; ++a) o[a] = hacc[a] + __ldg(net.head_b + a);
+      const long long i = m0 + row;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+        if (a < net.n_out) hacc[a] += __ldg(net.head_b + a);
+      if (net.out) {
+        float* o = net.out + (size_t)i * net.n_out;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+          if (a < net.n_out) o[a] = hacc[a];
+      }
+      if (blockIdx.y == 0 && g.action) {  // Agent.get_action_and_value: probs.sample(), log_prob(action).sum(1)
+        const uint32_t call = __ldg(g.counter) + g.call_offset;
+        if (net.n_out == 2) {
+          const float mu[2] = {hacc[0], hacc[1]};
+          float act[2];
+          g.logprob[i] = ppo::sample_row<2>(mu, g.logstd, i, call, g.seed_lo, g.seed_hi, act);
+          *reinterpret_cast<float2*>(g.action + 2 * i) = make_float2(act[0], act[1]);
+        } else {
+          const float mu[6] = {hacc[0], hacc[1], hacc[2], hacc[3], hacc[4], hacc[5]};
+          float act[6];
+          g.logprob[i] = ppo::sample_row<6>(mu, g.logstd, i, call, g.seed_lo, g.seed_hi, act);
+#pragma unroll
+          for (int a = 0; a < 6; ++a) g.action[6 * i + a] = act[a];
+        }
+      }
     }
   }
   tc_fence_before();
@@ -265,16 +341,17 @@ extern "C" {
 
 // The whole MLP forward for up to two networks that share the input rows (actor mean and critic value of the
 // same observations): out_i [M, n_out_i] f32 = head_i(tanh-MLP_i(x)). See include/vss_b200.h.
-VSS_API int vss_mlp_forward_fused(const void* x16, int ldx, int M, const vss_mlp_net* nets, int n_nets, int epilogue_warps,
-                                  void* stream) {
-  return vss_mlp_forward_fused_timed(x16, ldx, M, nets, n_nets, epilogue_warps, nullptr, stream);
+VSS_API int vss_mlp_forward_fused(const void* x16, int ldx, int M, const vss_mlp_net* nets, int n_nets,
+                                  const vss_mlp_sampling* sampling, int epilogue_warps, void* stream) {
+  return vss_mlp_forward_fused_timed(x16, ldx, M, nets, n_nets, sampling, epilogue_warps, nullptr, stream);
 }
 
 // The same launch; the first CTA also records 11 globaltimer stamps (ns) at its phase boundaries into `stamps`
 // (device memory): [0] entry, [1] barriers + TMEM ready, [2 + 2l] accumulator of layer l complete, [3 + 2l] epilogue of
 // layer l done (one epilogue warp's view), [10] exit. A profiling hook: profiles/mlp_fused_bench.py.
 VSS_API int vss_mlp_forward_fused_timed(const void* x16, int ldx, int M, const vss_mlp_net* nets, int n_nets,
-                                        int epilogue_warps, unsigned long long* stamps, void* stream) {
+                                        const vss_mlp_sampling* sampling, int epilogue_warps, unsigned long long* stamps,
+                                        void* stream) {
   using namespace tc;
   if (!x16 || !nets || M <= 0 || n_nets < 1 || n_nets > FM_MAX_NETS || ldx < 64 || (ldx & 7)) {
     g_tc_error = "vss_mlp_forward_fused: bad argument (x16 [M, 64] bf16 with ldx >= 64, 1 or 2 networks)";
@@ -289,8 +366,8 @@ VSS_API int vss_mlp_forward_fused_timed(const void* x16, int ldx, int M, const v
   if (!make_map(&a.x, x16, M, 64, ldx, BM)) { g_tc_error = "vss_mlp_forward_fused: cuTensorMapEncodeTiled failed (x)"; return VSS_E_CUDA; }
   for (int i = 0; i < n_nets; ++i) {
     const vss_mlp_net& s = nets[i];
-    if (!s.head_w || !s.head_b || !s.out || (s.n_out != 1 && s.n_out != 2 && s.n_out != 6)) {
-      g_tc_error = "vss_mlp_forward_fused: bad network (head 256 -> 1, 2 or 6)";
+    if (!s.head_w || !s.head_b || (!s.out && !(i == 0 && sampling)) || (s.n_out != 1 && s.n_out != 2 && s.n_out != 6)) {
+      g_tc_error = "vss_mlp_forward_fused: bad network (head 256 -> 1, 2 or 6; out may be NULL only for a sampled network 0)";
       return VSS_E_INVALID;
     }
     for (int l = 0; l < 4; ++l) {
@@ -306,6 +383,16 @@ VSS_API int vss_mlp_forward_fused_timed(const void* x16, int ldx, int M, const v
     }
     if (reinterpret_cast<uintptr_t>(s.head_w) & 15u) { g_tc_error = "vss_mlp_forward_fused: head_w must be 16-byte aligned"; return VSS_E_INVALID; }
     a.net[i].head_w = s.head_w; a.net[i].head_b = s.head_b; a.net[i].out = s.out; a.net[i].n_out = s.n_out;
+  }
+  if (sampling) {
+    if (!sampling->logstd || !sampling->counter || !sampling->action || !sampling->logprob ||
+        (nets[0].n_out != 2 && nets[0].n_out != 6) || (reinterpret_cast<uintptr_t>(sampling->action) & 7u)) {
+      g_tc_error = "vss_mlp_forward_fused: sampling needs logstd, counter, action (8-byte aligned), logprob and an action width of 2 or 6";
+      return VSS_E_INVALID;
+    }
+    a.logstd = sampling->logstd; a.counter = sampling->counter; a.call_offset = sampling->call_offset;
+    a.seed_lo = (uint32_t)sampling->seed; a.seed_hi = (uint32_t)(sampling->seed >> 32);
+    a.action = sampling->action; a.logprob = sampling->logprob;
   }
   static bool configured = false;
   if (!configured) {

@@ -15,19 +15,18 @@
 #include <string>
 
 #include "../../include/vss_b200.h"
+#include "ppo_sample.cuh"
 #include "vss_lane.cuh"
 
 namespace ppo {
 
 using vss::U4;
 
-constexpr float HALF_LOG_2PI = 0.9189385332046727f;
 
 __global__ void k_bump32(uint32_t* ctr) { *ctr += 1u; }
 
 // ---- action sampling ----------------------------------------------------------------------
-// One thread per row. Philox4x32-10, counter = (row, call index, stream), key = seed: the stream
-// of normals depends only on (seed, call, row), not on the launch shape.
+// One thread per row (the arithmetic lives in ppo_sample.cuh, shared with the fused MLP forward).
 template <int A>
 __global__ void __launch_bounds__(256)
 k_policy_sample(const float* __restrict__ mean, const float* __restrict__ logstd, long long M, uint32_t seed_lo,
@@ -35,31 +34,12 @@ k_policy_sample(const float* __restrict__ mean, const float* __restrict__ logstd
                 float* __restrict__ logprob) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
-  const uint32_t call = *counter;
-  float z[(A + 3) / 4 * 4];
+  float mu[A], act[A];
 #pragma unroll
-  for (int b = 0; b < (A + 3) / 4; ++b) {
-    const U4 g = vss::philox4x32_10(U4{(uint32_t)i, (uint32_t)(i >> 32), call, 0x50504f00u + b}, seed_lo, seed_hi);
-    const uint32_t u[4] = {g.x, g.y, g.z, g.w};
+  for (int a = 0; a < A; ++a) mu[a] = mean[i * A + a];
+  logprob[i] = sample_row<A>(mu, logstd, i, *counter, seed_lo, seed_hi, act);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float rad = sqrtf(-2.0f * logf(vss::u01_open(u[2 * h])));
-      float sn, cs;
-      sincosf(6.283185307179586f * vss::u01(u[2 * h + 1]), &sn, &cs);
-      z[4 * b + 2 * h] = rad * cs;
-      z[4 * b + 2 * h + 1] = rad * sn;
-    }
-  }
-  float lp = 0.0f;
-#pragma unroll
-  for (int a = 0; a < A; ++a) {
-    const float ls = logstd[a], sd = expf(ls), mu = mean[i * A + a];
-    const float act = mu + sd * z[a];
-    const float d = act - mu;
-    lp += -(d * d) / (2.0f * sd * sd) - ls - HALF_LOG_2PI;
-    action[i * A + a] = act;
-  }
-  logprob[i] = lp;
+  for (int a = 0; a < A; ++a) action[i * A + a] = act[a];
 }
 
 // ---- minibatch loss + gradients -----------------------------------------------------------

@@ -277,17 +277,19 @@ def head_forward(h, W, b, out=None):
     return out
 
 
-def mlp_forward_fused(x16, nets, epilogue_warps=0, stamps=None):
+def mlp_forward_fused(x16, nets, epilogue_warps=0, stamps=None, sampling=None):
     """The whole MLP forward of 1 or 2 networks over the same rows in one launch (include/vss_b200.h:
     vss_mlp_forward_fused). x16 [M,64] bf16; nets = [(w16 list of 4 bf16 matrices, b list of 4 f32 vectors, head_w,
-    head_b, out [M,n_out] f32), ...]. Returns the list of `out` tensors."""
+    head_b, out [M,n_out] f32 or None), ...]. sampling = dict(logstd, counter (uint32/int32 device word), seed,
+    call_offset, action [M,A] f32, logprob [M] f32): also draws the action from network 0's output (then its `out`
+    may be False = not stored). Returns the list of `out` tensors."""
     lib = _lib.load_library()
     M = x16.shape[0]
     assert x16.dtype == torch.bfloat16 and x16.shape[1] == 64 and x16.stride(1) == 1
     shapes = [(256, 64), (512, 256), (512, 512), (256, 512)]
     arr = (_lib.MlpNet * len(nets))()
     outs = []
-    for a, (w16, bs, head_w, head_b, out) in zip(arr, nets):
+    for k, (a, (w16, bs, head_w, head_b, out)) in enumerate(zip(arr, nets)):
         for l in range(4):
             assert w16[l].dtype == torch.bfloat16 and tuple(w16[l].shape) == shapes[l] and w16[l].is_contiguous()
             assert bs[l].dtype == torch.float32 and bs[l].is_contiguous() and bs[l].numel() == shapes[l][0]
@@ -295,14 +297,29 @@ def mlp_forward_fused(x16, nets, epilogue_warps=0, stamps=None):
         n_out = head_w.shape[0]
         assert head_w.dtype == torch.float32 and head_w.is_contiguous() and head_w.shape[1] == 256
         assert head_b.dtype == torch.float32 and head_b.is_contiguous()
-        if out is None:
+        if out is False:
+            assert k == 0 and sampling is not None
+            out = None
+        elif out is None:
             out = torch.empty((M, n_out), device=x16.device, dtype=torch.float32)
-        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == M * n_out
-        a.head_w, a.head_b, a.out, a.n_out = head_w.data_ptr(), head_b.data_ptr(), out.data_ptr(), n_out
+        if out is not None:
+            assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == M * n_out
+        a.head_w, a.head_b, a.n_out = head_w.data_ptr(), head_b.data_ptr(), n_out
+        a.out = None if out is None else out.data_ptr()
         outs.append(out)
+    samp = None
+    if sampling is not None:
+        A = nets[0][2].shape[0]
+        act, lp, ls, ctr = sampling["action"], sampling["logprob"], sampling["logstd"], sampling["counter"]
+        assert act.dtype == torch.float32 and act.is_contiguous() and act.numel() == M * A
+        assert lp.dtype == torch.float32 and lp.is_contiguous() and lp.numel() == M
+        assert ls.dtype == torch.float32 and ls.is_contiguous() and ls.numel() == A and ctr.element_size() == 4
+        samp = _lib.MlpSampling(ls.data_ptr(), ctr.data_ptr(), int(sampling["seed"]) & (2 ** 64 - 1),
+                                int(sampling.get("call_offset", 0)), 0, act.data_ptr(), lp.data_ptr())
     if stamps is not None:  # profiling hook: 11 int64 globaltimer stamps of the first CTA
         assert stamps.dtype == torch.int64 and stamps.is_cuda and stamps.numel() >= 11 and stamps.is_contiguous()
-    rc = lib.vss_mlp_forward_fused_timed(x16.data_ptr(), x16.stride(0), M, arr, len(nets), int(epilogue_warps),
+    rc = lib.vss_mlp_forward_fused_timed(x16.data_ptr(), x16.stride(0), M, arr, len(nets),
+                                         None if samp is None else C.byref(samp), int(epilogue_warps),
                                          None if stamps is None else stamps.data_ptr(),
                                          torch.cuda.current_stream(x16.device).cuda_stream)
     if rc != 0:

@@ -298,6 +298,30 @@ def _find_fused(env):
     return None
 
 
+class _EpisodeReturns(dict):
+    """`infos["r"]` of RecordEpisodeStatisticsTorch.step (envs/wrappers.py:76-83): the four reward components of the
+    last finished episode are views of the statistics buffer; their sum ("return") is computed when it is read, not
+    once per step (one launch less inside the captured rollout)."""
+
+    def __init__(self, r):
+        super().__init__(goal=r[:, 0], grad=r[:, 1], move=r[:, 2], energy=r[:, 3])
+        self._r = r
+
+    def __missing__(self, key):
+        if key == "return":
+            return self._r.sum(1)
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return key == "return" or super().__contains__(key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def keys(self):
+        return list(super().keys()) + ["return"]
+
+
 class RecordEpisodeStatisticsTorch(Wrapper):
     """Per-env running sums of the 4 reward components and the episode length
     (wrappers.py:50-87). Over a fused view the sums are maintained by the step kernel;
@@ -335,7 +359,6 @@ class RecordEpisodeStatisticsTorch(Wrapper):
             self.returned_episode_lengths[:] = self.episode_lengths
             self.episode_returns *= 1 - dones.unsqueeze(1)
             self.episode_lengths *= 1 - dones
-        r = self.returned_episode_returns
-        infos["r"] = {"goal": r[:, 0], "grad": r[:, 1], "move": r[:, 2], "energy": r[:, 3], "return": r.sum(1)}
+        infos["r"] = _EpisodeReturns(self.returned_episode_returns)
         infos["l"] = self.returned_episode_lengths
         return observations, rewards, dones, infos

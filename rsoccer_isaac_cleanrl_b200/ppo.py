@@ -366,7 +366,7 @@ def train(args, log=print, hook=None):
 
     fused = backend == "tc"
     if fused:
-        from .engine import gather_pad_bf16, policy_sample, ppo_loss
+        from .engine import gather_pad_bf16, mlp_forward_fused, ppo_loss
         from .tc_mlp import MlpWeights, backward_explicit, forward_explicit
         mw_actor, mw_critic = MlpWeights(agent.actor_mean), MlpWeights(agent.critic)
         sample_ctr = torch.zeros(1, device=device, dtype=torch.int32)
@@ -398,24 +398,36 @@ def train(args, log=print, hook=None):
         x16_buf = [torch.zeros((N, k0), device=device, dtype=torch.bfloat16) for _ in range(2)]
 
     def rollout_fused(first_obs):
-        """rollout() with every per-step piece as one launch: 2 x (4 tcgen05 GEMMs + head), the sampling
-        kernel writing action and log-prob into the rollout slabs, the critic head writing values[step],
-        the env step writing obs / reward / done / timeout slabs and the next bf16 MLP input."""
+        """rollout() as two launches per step: the fused MLP forward (both networks' four tcgen05 layers + heads,
+        action sample and log-prob written into the rollout slabs, the critic's value into values[step]) and the env
+        step (obs / reward / done / timeout slabs and the next bf16 MLP input)."""
         with torch.no_grad():
             obs_all[0] = first_obs
             x16_buf[0].copy_(gather_pad_bf16(obs_all[0], None, k0))
             mw_actor.refresh(); mw_critic.refresh()
+            nets = [(mw.w16, mw.bs, mw.head_w, mw.head_b) for mw in (mw_actor, mw_critic)]
+            # One launch covers both networks while its CTAs (one per 128 rows and network) fit the SMs at once; with
+            # more rows the critic gets its own launch on the side stream and runs beside the env step.
+            one_launch = 2 * ((N + 127) // 128) <= torch.cuda.get_device_properties(device).multi_processor_count
             for step in range(T):
+                # actor mean + action sample + log-prob (and the critic's value) in ONE launch (csrc/mlp_fused.cu); the
+                # sampling stream's call index is counter + step, the counter advances by T once per rollout
                 x16 = x16_buf[step & 1]
-                critic_out = on_side(lambda: forward_explicit(mw_critic, x16, out=values[step]))
-                mean, _ = forward_explicit(mw_actor, x16)
-                policy_sample(mean, logstd_flat, sample_seed, sample_ctr, action=actions[step], logprob=logprobs[step])
+                samp = dict(logstd=logstd_flat, counter=sample_ctr, seed=sample_seed, call_offset=step,
+                            action=actions[step], logprob=logprobs[step])
+                if one_launch:
+                    mlp_forward_fused(x16, [nets[0] + (False,), nets[1] + (values[step],)], sampling=samp)
+                else:
+                    on_side(lambda: mlp_forward_fused(x16, [nets[1] + (values[step],)]))
+                    mlp_forward_fused(x16, [nets[0] + (False,)], sampling=samp)
                 envs.step(actions[step], obs_out=obs_all[step + 1], term_obs_out=term_obs_all[step],
                           reward_out=rewards[step], obs_bf16_out=x16_buf[(step + 1) & 1],
                           done_f_out=next_dones[step], timeout_f_out=next_timeouts[step])
-                join_side()
-                del critic_out
-            forward_explicit(mw_critic, gather_pad_bf16(term_obs_all.view(T * N, -1), None, k0), out=next_values)
+                if not one_launch:
+                    join_side()
+            sample_ctr.add_(T)
+            # V(terminal observation) of the whole rollout in one launch of the same kernel (critic only)
+            mlp_forward_fused(gather_pad_bf16(term_obs_all.view(T * N, -1), None, k0), [nets[1] + (next_values,)])
             gae_kernel(rewards, values, next_values, next_dones, next_timeouts, args.gamma, args.gae_lambda,
                        advantages, returns)
         return obs_all[T]

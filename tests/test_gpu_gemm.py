@@ -187,3 +187,35 @@ def test_fused_mlp_forward_matches_the_layer_by_layer_path(M, n_act, ew):
     only_c, = mlp_forward_fused(x16, nets[1:], epilogue_warps=ew)
     again_a, again_c = mlp_forward_fused(x16, nets, epilogue_warps=ew)
     assert torch.equal(only_c, out_c) and torch.equal(again_a, out_a) and torch.equal(again_c, out_c)
+
+
+@pytest.mark.parametrize("M,n_act", [(4096, 2), (1000, 6)])
+def test_fused_mlp_forward_samples_like_policy_sample(M, n_act):
+    """vss_mlp_sampling: the action and log-prob drawn inside the fused launch are those of vss_policy_sample on the
+    same mean with call index counter + call_offset (same arithmetic, same Philox stream); the counter is not advanced;
+    the mean need not be stored."""
+    from rsoccer_isaac_cleanrl_b200.engine import gather_pad_bf16, mlp_forward_fused, policy_sample
+    actor, critic = _mlp_pair(n_act, seed=3)
+    x16 = gather_pad_bf16(torch.randn(M, 52, device="cuda"), None, 64)
+    nets = [(mw.w16, [b.detach() for b in mw.bs], mw.head_w.detach(), mw.head_b.detach()) for mw in (actor, critic)]
+    logstd = torch.linspace(-0.7, 0.2, n_act, device="cuda")
+    ctr = torch.full((1,), 5, device="cuda", dtype=torch.int32)
+    act, lp = torch.empty((M, n_act), device="cuda"), torch.empty(M, device="cuda")
+    samp = dict(logstd=logstd, counter=ctr, seed=1234567, call_offset=3, action=act, logprob=lp)
+    mean, value = mlp_forward_fused(x16, [nets[0] + (None,), nets[1] + (None,)], sampling=samp)
+    assert int(ctr.item()) == 5
+    ctr2 = torch.full((1,), 8, device="cuda", dtype=torch.int32)
+    act_ref, lp_ref = policy_sample(mean, logstd, 1234567, ctr2)
+    assert int(ctr2.item()) == 9
+    assert torch.equal(act, act_ref) and torch.equal(lp, lp_ref)
+    # without storing the mean: same draws, same value
+    act2, lp2 = torch.empty_like(act), torch.empty_like(lp)
+    samp.update(action=act2, logprob=lp2)
+    none, value2 = mlp_forward_fused(x16, [nets[0] + (False,), nets[1] + (None,)], sampling=samp)
+    assert none is None and torch.equal(act2, act) and torch.equal(lp2, lp) and torch.equal(value2, value)
+    # a different call index gives different noise; the statistics are those of N(mean, exp(logstd))
+    samp.update(call_offset=4)
+    mlp_forward_fused(x16, [nets[0] + (False,), nets[1] + (None,)], sampling=samp)
+    assert not torch.equal(act2, act)
+    zs = (act - mean) / logstd.exp()
+    assert abs(zs.mean().item()) < 5 / (M * n_act) ** 0.5 and abs(zs.std().item() - 1) < 5 / (2 * M * n_act) ** 0.5
