@@ -199,6 +199,21 @@ __device__ __forceinline__ void body_barrier(int W) {
   asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
 }
 
+// Profiling build only (-DVSS_PHASE_PROFILE, profiles/step_phase_profile.py): per-CTA clock totals of the phases of
+// k_step_cta as seen by warp 0 after the barrier that ends each phase (= the slowest warp of the phase), plus one
+// extra barrier after the wall phase so that its imbalance is not booked on the next integrate. Not in the product.
+#ifdef VSS_PHASE_PROFILE
+__device__ unsigned long long g_phase_prof[65536 * 8];
+#define PROF_DECL unsigned long long pf_t = clock64(), pf_acc[7] = {0, 0, 0, 0, 0, 0, 0}; const unsigned long long pf_t0 = pf_t;
+#define PROF_MARK(i) do { const unsigned long long pf_n = clock64(); pf_acc[i] += pf_n - pf_t; pf_t = pf_n; } while (0)
+#define PROF_STORE do { if (threadIdx.x == 0 && blockIdx.x < 65536) { pf_acc[6] = clock64() - pf_t0; \
+    for (int i = 0; i < 7; ++i) g_phase_prof[blockIdx.x * 8 + i] = pf_acc[i]; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_STORE
+#endif
+
 template <int VIEW, bool INJECT>
 __global__ void __launch_bounds__(32 * MAX_WPT)
 k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams P) {
@@ -219,6 +234,7 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
   const int valid = (int)max(0LL, min((long long)a.fpw, a.n - env0));
   constexpr int PER_FIELD = ViewShape<VIEW>::F4_PER;
   const RngKey key = make_key(a, env);
+  PROF_DECL
   // 1a. state in (words dealt to the warps), then actions / OU noise per Philox block, progress restart,
   //     prev_* clones per body
   if (active) load_state_words(S, a.state, a.ld, env, warp, NW);
@@ -229,6 +245,7 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
     for (int b = warp; b < 7; b += W) prev_term_body(S, b, P);
   }
   __syncthreads();
+  PROF_MARK(0);
   // physics (replaces gym.simulate) on the body warps, which synchronise among themselves (body_barrier);
   // speculative resets on the helper warp meanwhile.
   if (helper && active) {
@@ -244,6 +261,7 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
         if (active)
           for (int b = warp; b < 7; b += W) { if (b < 6) integrate_robot(S, b, P); else integrate_ball(S, P); }
         body_barrier(W);
+        PROF_MARK(1);
         {
           uint32_t m = 0u;
           if (active)
@@ -251,14 +269,20 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
           S[(W_SCR + warp) * LDS] = bitsf(m);
         }
         body_barrier(W);
+        PROF_MARK(2);
         if (active && lane % W == warp) {
           uint32_t m = 0u;
           for (int j = 0; j < W; ++j) m |= fbits(S[(W_SCR + j) * LDS]);
           if (m) contacts_task(S, m, P);
         }
         body_barrier(W);
+        PROF_MARK(3);
         if (active)
           for (int b = warp; b < 7; b += W) walls_body(S, b, P);  // (the next integrate of a body is by the same thread)
+#ifdef VSS_PHASE_PROFILE
+        body_barrier(W);
+        PROF_MARK(4);
+#endif
       }
     }
   }
@@ -306,6 +330,8 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
     if (warp == 0 && ((ended_mask >> lane) & 1u)) zero_action_row(env, a);  // wrappers.py:105-107
     step_done(a, ctr);
   }
+  PROF_MARK(5);
+  PROF_STORE;
 }
 
 // reset_dones() + compute_observations(): vss.py:72-73, 267-333, 205-216
@@ -805,6 +831,12 @@ VSS_API int vss_set_step_fields_per_tile(vss_handle h, int fields) {
 VSS_API int vss_step_fields_per_tile(vss_handle h) {
   return h ? launch_shape(h->n, true, h->wpt_override, h->fpt_override).fpw : 0;
 }
+
+#ifdef VSS_PHASE_PROFILE
+VSS_API int vss_prof_read(unsigned long long* out, int ctas) {  // profiling build only: out[ctas][8] clock totals
+  return cudaMemcpyFromSymbol(out, vss::g_phase_prof, sizeof(unsigned long long) * 8 * (size_t)ctas) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 VSS_API int64_t vss_step_granularity(vss_handle h) {
   if (!h) return 0;
