@@ -7,7 +7,11 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rsoccer_isaac_cleanrl_b200 import _lib  # noqa: E402
 from rsoccer_isaac_cleanrl_b200.envs import VSS, SingleAgent, load_cfg  # noqa: E402
+
+if os.environ.get("VSS_AB_LIB"):  # A/B runs of experimental builds on the SAME box (box-to-box spread is ~10 %): this
+    _lib.LIB_PATH = os.path.abspath(os.environ["VSS_AB_LIB"])  # script only - the product never reads the environment
 
 
 def time_us(fn, reps=300, warm=30):
