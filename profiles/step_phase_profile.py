@@ -18,11 +18,17 @@ NAMES = ["load+actions", "integrate", "broadphase", "contacts", "walls", "output
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    if os.environ.get("VSS_AB_LIB"):  # the profiling build as a second file (this script only)
+        _lib.LIB_PATH = os.path.abspath(os.environ["VSS_AB_LIB"])
     lib = _lib.load_library()
     assert hasattr(lib, "vss_prof_read"), "not the profiling build"
     cfg = load_cfg()
     cfg["env"]["numEnvs"] = n
     task = VSS(cfg, "cuda:0", "cuda:0", 0, True, seed=1)
+    if len(sys.argv) > 2:
+        task.engine.fields_per_tile = int(sys.argv[2])
+    if len(sys.argv) > 3:
+        task.engine.warps_per_tile = int(sys.argv[3])
     view = SingleAgent(task)
     view.reset()
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -49,6 +55,12 @@ def main():
     order = np.argsort(-last[:, 6])[:5]
     print("slowest CTAs of that launch: " + "; ".join(
         f"#{i}: " + " ".join(f"{int(last[i, k])}" for k in range(7)) for i in order))
+    if hasattr(lib, "vss_prof_read_integrate"):
+        ib = np.zeros((ctas, 16), np.uint64)
+        assert lib.vss_prof_read_integrate(ib.ctypes.data_as(C.c_void_p), ctas) == 0
+        ib = ib.astype(np.float64)
+        print("integrate, per warp (cycles per step, mean over CTAs): compute " + " ".join(f"{x:.0f}" for x in ib[:, :8].mean(0)) +
+              " | wait at the barrier " + " ".join(f"{x:.0f}" for x in ib[:, 8:].mean(0)))
     print("mean over launches of the per-launch MAX total:", end=" ")
     print("(per-phase mean over CTAs and launches) " + " ".join(f"{NAMES[k]}={acc[:, k].mean():.0f}" for k in range(7)))
 

@@ -204,6 +204,7 @@ __device__ __forceinline__ void body_barrier(int W) {
 // extra barrier after the wall phase so that its imbalance is not booked on the next integrate. Not in the product.
 #ifdef VSS_PHASE_PROFILE
 __device__ unsigned long long g_phase_prof[65536 * 8];
+__device__ unsigned long long g_integ_prof[4096 * 16];  // per CTA: [warp] integrate compute, [8 + warp] wait at its barrier
 #define PROF_DECL unsigned long long pf_t = clock64(), pf_acc[7] = {0, 0, 0, 0, 0, 0, 0}; const unsigned long long pf_t0 = pf_t;
 #define PROF_MARK(i) do { const unsigned long long pf_n = clock64(); pf_acc[i] += pf_n - pf_t; pf_t = pf_n; } while (0)
 #define PROF_STORE do { if (threadIdx.x == 0 && blockIdx.x < 65536) { pf_acc[6] = clock64() - pf_t0; \
@@ -258,9 +259,23 @@ k_step_cta(const __grid_constant__ StepArgs a, const __grid_constant__ DevParams
     if (!helper) {
 #pragma unroll 1
       for (int it = 0; it < P.substeps; ++it) {
+#ifdef VSS_PHASE_PROFILE
+        const unsigned long long ig0 = clock64();
+#endif
         if (active)
           for (int b = warp; b < 7; b += W) { if (b < 6) integrate_robot(S, b, P); else integrate_ball(S, P); }
+#ifdef VSS_PHASE_PROFILE
+        const unsigned long long ig1 = clock64();
+#endif
         body_barrier(W);
+#ifdef VSS_PHASE_PROFILE
+        if (lane == 0 && blockIdx.x < 4096) {
+          const unsigned long long ig2 = clock64();
+          if (it == 0) { g_integ_prof[blockIdx.x * 16 + warp] = 0; g_integ_prof[blockIdx.x * 16 + 8 + warp] = 0; }
+          g_integ_prof[blockIdx.x * 16 + warp] += ig1 - ig0;
+          g_integ_prof[blockIdx.x * 16 + 8 + warp] += ig2 - ig1;
+        }
+#endif
         PROF_MARK(1);
         {
           uint32_t m = 0u;
@@ -833,6 +848,9 @@ VSS_API int vss_step_fields_per_tile(vss_handle h) {
 }
 
 #ifdef VSS_PHASE_PROFILE
+VSS_API int vss_prof_read_integrate(unsigned long long* out, int ctas) {  // out[ctas][16]
+  return cudaMemcpyFromSymbol(out, vss::g_integ_prof, sizeof(unsigned long long) * 16 * (size_t)ctas) == cudaSuccess ? 0 : -1;
+}
 VSS_API int vss_prof_read(unsigned long long* out, int ctas) {  // profiling build only: out[ctas][8] clock totals
   return cudaMemcpyFromSymbol(out, vss::g_phase_prof, sizeof(unsigned long long) * 8 * (size_t)ctas) == cudaSuccess ? 0 : -1;
 }
