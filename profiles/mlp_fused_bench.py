@@ -8,7 +8,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from rsoccer_isaac_cleanrl_b200 import _lib  # noqa: E402
 from rsoccer_isaac_cleanrl_b200.engine import gather_pad_bf16, mlp_forward_fused  # noqa: E402
+
+if os.environ.get("VSS_AB_LIB"):  # A/B runs of experimental builds on the same box (this script only)
+    _lib.LIB_PATH = os.path.abspath(os.environ["VSS_AB_LIB"])
 from rsoccer_isaac_cleanrl_b200.tc_mlp import forward_explicit  # noqa: E402
 from test_gpu_gemm import _mlp_pair  # noqa: E402
 
@@ -41,7 +45,7 @@ def graph_time_us(fn):
 
 def main():
     sizes = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "1024,4096,16384,65535,131072".split(","))]
-    for n_act in (2, 6):
+    for n_act in ((2,) if os.environ.get("VSS_AB_LIB") else (2, 6)):
         actor, critic = _mlp_pair(n_act, 0)
         for M in sizes:
             x16 = gather_pad_bf16(torch.randn(M, 52, device="cuda"), None, 64)
