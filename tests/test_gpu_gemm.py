@@ -219,3 +219,29 @@ def test_fused_mlp_forward_samples_like_policy_sample(M, n_act):
     assert not torch.equal(act2, act)
     zs = (act - mean) / logstd.exp()
     assert abs(zs.mean().item()) < 5 / (M * n_act) ** 0.5 and abs(zs.std().item() - 1) < 5 / (2 * M * n_act) ** 0.5
+
+
+def test_fused_mlp_forward_is_bit_stable_under_load():
+    """The barrier protocol of csrc/mlp_fused.cu (TMEM halves, per-block ready / free mbarriers, generic -> async proxy
+    fences) under timing perturbation: 60 launches over several waves of CTAs, while another stream keeps the SMs and
+    the L2 busy with large GEMMs and copies, give the same bits every time, for both epilogue shapes."""
+    from rsoccer_isaac_cleanrl_b200.engine import gather_pad_bf16, mlp_forward_fused
+    actor, critic = _mlp_pair(6, seed=5)
+    M = 40000 + 77
+    x16 = gather_pad_bf16(torch.randn(M, 52, device="cuda"), None, 64)
+    nets = [(mw.w16, [b.detach() for b in mw.bs], mw.head_w.detach(), mw.head_b.detach(), None) for mw in (actor, critic)]
+    ref_a, ref_c = mlp_forward_fused(x16, nets, epilogue_warps=8)
+    ref4_a, ref4_c = mlp_forward_fused(x16, nets, epilogue_warps=4)
+    assert torch.equal(ref_a, ref4_a) and torch.equal(ref_c, ref4_c)
+    side = torch.cuda.Stream()
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    big = torch.empty(64 << 20, device="cuda")
+    for it in range(60):
+        with torch.cuda.stream(side):
+            if it % 3 == 0:
+                a @ a
+            elif it % 3 == 1:
+                big.copy_(big.flip(0))
+        out_a, out_c = mlp_forward_fused(x16, nets, epilogue_warps=8 if it % 2 == 0 else 4)
+        assert torch.equal(out_a, ref_a) and torch.equal(out_c, ref_c), it
+    torch.cuda.synchronize()
