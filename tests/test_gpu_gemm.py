@@ -213,6 +213,12 @@ def test_fused_mlp_forward_samples_like_policy_sample(M, n_act):
     samp.update(action=act2, logprob=lp2)
     none, value2 = mlp_forward_fused(x16, [nets[0] + (False,), nets[1] + (None,)], sampling=samp)
     assert none is None and torch.equal(act2, act) and torch.equal(lp2, lp) and torch.equal(value2, value)
+    # the actor alone (how the rollout launches it when the critic runs on the side stream): same draws again
+    act3, lp3 = torch.empty_like(act), torch.empty_like(lp)
+    samp.update(action=act3, logprob=lp3)
+    mlp_forward_fused(x16, [nets[0] + (False,)], sampling=samp)
+    assert torch.equal(act3, act) and torch.equal(lp3, lp)
+    samp.update(action=act2, logprob=lp2)
     # a different call index gives different noise; the statistics are those of N(mean, exp(logstd))
     samp.update(call_offset=4)
     mlp_forward_fused(x16, [nets[0] + (False,), nets[1] + (None,)], sampling=samp)

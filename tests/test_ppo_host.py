@@ -86,3 +86,19 @@ def test_flat_parameters_and_adam_match_torch():
         opt_a.step(); opt_b.step()
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         np.testing.assert_allclose(pa.detach().numpy(), pb.detach().numpy(), rtol=2e-5, atol=2e-6, err_msg=k)
+
+
+def test_episode_returns_mapping_matches_the_reference_dict():
+    """envs/wrappers.py:76-83 of the reference: infos["r"] = {goal, grad, move, energy, return = sum(1)}; here the four
+    components are views and "return" is computed when read."""
+    import torch
+    from rsoccer_isaac_cleanrl_b200.envs.wrappers import _EpisodeReturns
+    r = torch.arange(12, dtype=torch.float32).view(3, 4)
+    m = _EpisodeReturns(r)
+    assert set(m.keys()) == {"goal", "grad", "move", "energy", "return"} and "return" in m and "nope" not in m
+    assert torch.equal(m["goal"], r[:, 0]) and torch.equal(m["energy"], r[:, 3])
+    assert torch.equal(m["return"], r.sum(1)) and torch.equal(m.get("return"), r.sum(1)) and m.get("nope") is None
+    r[0, 0] = 100.0   # views of the live statistics buffer, like the reference's slices
+    assert float(m["goal"][0]) == 100.0 and float(m["return"][0]) == 100.0 + 1 + 2 + 3
+    with __import__("pytest").raises(KeyError):
+        m["nope"]
