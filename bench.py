@@ -56,7 +56,7 @@ def parse():
                     help="env-id:agents-per-GPU of the PPO legs (BASELINE configs[1-3])")
     ap.add_argument("--ppo-updates", type=int, default=0,
                     help="updates per PPO leg (1 eager + 1 capturing + steady); 0 = about 2e7 samples per GPU and leg, "
-                         "at least 5 and at most 40 updates, so that the reference's own SPS metric (global_step / wall, "
+                         "at least 8 and at most 40 updates, so that the reference's own SPS metric (global_step / wall, "
                          "start-up included) is not dominated by the two start-up updates")
     return ap.parse_args()
 
@@ -513,7 +513,7 @@ def run_native(args):
         ppo_res = []
         for leg in args.ppo_legs.split(","):
             env_id, agents = leg.split(":")
-            updates = args.ppo_updates or max(5, min(40, int(2.1e7 // (int(agents) * 128))))
+            updates = args.ppo_updates or max(8, min(40, int(2.1e7 // (int(agents) * 128))))
             ppo_res.append(run_ppo_leg(torch, world, env_id, int(agents), updates))
 
     ref_torch = None
