@@ -378,6 +378,14 @@ VSS_API int vss_mlp_forward_fused_timed(const void* x16, int ldx, int M, const v
  * (stream-ordered, so CUDA-graph replays draw fresh noise). */
 VSS_API int vss_policy_sample(const float* mean, const float* logstd, int64_t M, int A, uint64_t seed,
                               uint32_t* counter, float* action, float* logprob, void* stream);
+/* The rows of a rollout whose step ended an episode, as a compact list (any order): list[k] = index of the k-th
+ * non-zero entry of flags[0..n), *count = their number (device words; *count may exceed cap - entries beyond cap are
+ * dropped and the caller must check). And its inverse for per-row results: dst[list[k]] = src[k], k < min(*count, cap).
+ * Used for V(terminal_observation) (ppo...:272): for a row that did NOT end an episode the terminal observation IS the
+ * next observation, whose value the per-step critic pass has already produced, so only the listed rows need the critic. */
+VSS_API int vss_compact_nonzero(const float* flags, int64_t n, int64_t* list, int cap, int* count, void* stream);
+VSS_API int vss_scatter_rows_f32(float* dst, const int64_t* list, const float* src, const int* count, int cap,
+                                 void* stream);
 /* One PPO minibatch loss and its gradient w.r.t. the network outputs (ppo...:314-352):
  *   j = inds[i] (or i when inds is NULL) gathers the rollout arrays b_* (flattened (T*N,...) f32);
  *   mean (B,A) / value (B) are the fresh network outputs for those rows; logstd (A).

@@ -117,6 +117,8 @@ _SYMBOLS = {
     "vss_colsum_bf16": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_gather_pad_bf16": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "vss_policy_sample": (C.c_int, [_VP, _VP, C.c_int64, C.c_int, C.c_uint64, _VP, _VP, _VP, _VP]),
+    "vss_compact_nonzero": (C.c_int, [_VP, C.c_int64, _VP, C.c_int, _VP, _VP]),
+    "vss_scatter_rows_f32": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, _VP]),
     "vss_ppo_loss": (C.c_int, [_VP] * 9 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int] +
                      [_VP] * 6),
     "vss_convert_bf16_batch": (C.c_int, [C.POINTER(ConvertJob), C.c_int, _VP]),

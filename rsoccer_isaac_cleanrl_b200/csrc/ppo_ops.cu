@@ -42,6 +42,32 @@ k_policy_sample(const float* __restrict__ mean, const float* __restrict__ logstd
   for (int a = 0; a < A; ++a) action[i * A + a] = act[a];
 }
 
+// ---- rows of the rollout that ended an episode ---------------------------------------------
+// list[k] = index of the k-th non-zero flag (any order), *count = how many there are (may exceed cap: the caller
+// checks), for flags[0 .. n). One warp-aggregated atomic per warp.
+__global__ void __launch_bounds__(256)
+k_compact_nonzero(const float* __restrict__ flags, long long n, long long* __restrict__ list, int cap, int* count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = i < n && flags[i] != 0.0f;
+  const unsigned m = __ballot_sync(0xffffffffu, on);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs((int)m) - 1) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs((int)m) - 1);
+  if (on) {
+    const int k = base + __popc(m & ((1u << lane) - 1u));
+    if (k < cap) list[k] = i;
+  }
+}
+// dst[list[k]] = src[k] for k < min(*count, cap)
+__global__ void __launch_bounds__(256)
+k_scatter_rows(float* __restrict__ dst, const long long* __restrict__ list, const float* __restrict__ src,
+               const int* __restrict__ count, int cap) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < min(*count, cap)) dst[list[k]] = src[k];
+}
+
 // ---- minibatch loss + gradients -----------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -284,6 +310,21 @@ VSS_API int vss_policy_sample(const float* mean, const float* logstd, int64_t M,
   else return ppo::bad("vss_policy_sample: action width must be 2 or 6");
   ppo::k_bump32<<<1, 1, 0, st>>>(counter);
   return ppo::check_launch("vss_policy_sample");
+}
+
+VSS_API int vss_compact_nonzero(const float* flags, int64_t n, int64_t* list, int cap, int* count, void* stream) {
+  if (!flags || !list || !count || n <= 0 || cap <= 0) return ppo::bad("vss_compact_nonzero: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(count, 0, sizeof(int), st) != cudaSuccess) return ppo::check_launch("vss_compact_nonzero: memset");
+  ppo::k_compact_nonzero<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(flags, n, reinterpret_cast<long long*>(list), cap, count);
+  return ppo::check_launch("vss_compact_nonzero");
+}
+
+VSS_API int vss_scatter_rows_f32(float* dst, const int64_t* list, const float* src, const int* count, int cap, void* stream) {
+  if (!dst || !list || !src || !count || cap <= 0) return ppo::bad("vss_scatter_rows_f32: bad argument");
+  ppo::k_scatter_rows<<<(unsigned)((cap + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      dst, reinterpret_cast<const long long*>(list), src, count, cap);
+  return ppo::check_launch("vss_scatter_rows_f32");
 }
 
 VSS_API int vss_ppo_loss(const float* mean, const float* value, const float* logstd, const float* b_action,

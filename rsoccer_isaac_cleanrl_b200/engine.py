@@ -373,6 +373,26 @@ def policy_sample(mean, logstd, seed, counter, action=None, logprob=None):
     return action, logprob
 
 
+def compact_nonzero(flags, index_list, count):
+    """index_list[k] = flat index of the k-th non-zero entry of `flags` (f32, any order), count[0] = how many there are
+    (include/vss_b200.h: vss_compact_nonzero). Static shapes: index_list (int64, capacity rows) and count (int32, 1)
+    are caller-owned; the caller checks count <= capacity."""
+    lib = _lib.load_library()
+    assert flags.dtype == torch.float32 and flags.is_contiguous() and index_list.dtype == torch.int64
+    assert index_list.is_contiguous() and count.dtype == torch.int32 and count.numel() == 1
+    _ppo_check(lib, lib.vss_compact_nonzero(flags.data_ptr(), flags.numel(), index_list.data_ptr(), index_list.numel(),
+                                            count.data_ptr(), torch.cuda.current_stream(flags.device).cuda_stream))
+
+
+def scatter_rows(dst, index_list, src, count):
+    """dst.view(-1)[index_list[k]] = src[k] for k < min(count, capacity) (vss_scatter_rows_f32)."""
+    lib = _lib.load_library()
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and src.dtype == torch.float32 and src.is_contiguous()
+    assert src.numel() >= index_list.numel() and index_list.dtype == torch.int64 and count.dtype == torch.int32
+    _ppo_check(lib, lib.vss_scatter_rows_f32(dst.data_ptr(), index_list.data_ptr(), src.data_ptr(), count.data_ptr(),
+                                             index_list.numel(), torch.cuda.current_stream(dst.device).cuda_stream))
+
+
 PPO_STATS = ("pg_loss", "v_loss", "entropy", "old_approx_kl", "approx_kl", "clipfrac", "loss")
 
 

@@ -366,7 +366,7 @@ def train(args, log=print, hook=None):
 
     fused = backend == "tc"
     if fused:
-        from .engine import gather_pad_bf16, mlp_forward_fused, ppo_loss
+        from .engine import compact_nonzero, gather_pad_bf16, mlp_forward_fused, ppo_loss, scatter_rows
         from .tc_mlp import MlpWeights, backward_explicit, forward_explicit
         mw_actor, mw_critic = MlpWeights(agent.actor_mean), MlpWeights(agent.critic)
         sample_ctr = torch.zeros(1, device=device, dtype=torch.int32)
@@ -396,6 +396,12 @@ def train(args, log=print, hook=None):
         # no conversion launches between the steps. Two buffers: step t reads one, writes the other.
         assert k0 == 64, k0
         x16_buf = [torch.zeros((N, k0), device=device, dtype=torch.bfloat16) for _ in range(2)]
+        # V(terminal observation) (ppo…:272) is only computed where it differs from the next step's value: the rows
+        # whose step ended an episode, compacted into a list of fixed capacity (1/8 of the rollout; checked per update)
+        term_cap = max(128, (T * N // 8 + 127) // 128 * 128)
+        term_list = torch.zeros(term_cap, device=device, dtype=torch.int64)
+        term_count = torch.zeros(1, device=device, dtype=torch.int32)
+        term_values = torch.zeros(term_cap, device=device, dtype=torch.float32)
 
     def rollout_fused(first_obs):
         """rollout() as two launches per step: the fused MLP forward (both networks' four tcgen05 layers + heads,
@@ -426,8 +432,17 @@ def train(args, log=print, hook=None):
                 if not one_launch:
                     join_side()
             sample_ctr.add_(T)
-            # V(terminal observation) of the whole rollout in one launch of the same kernel (critic only)
-            mlp_forward_fused(gather_pad_bf16(term_obs_all.view(T * N, -1), None, k0), [nets[1] + (next_values,)])
+            # V(terminal observation) (ppo…:272). Where the step did not end an episode the terminal observation IS the
+            # next observation (the step kernel writes both from the same registers), so its value is the next step's
+            # critic output, bit for bit (every row of the fused forward is computed independently of its neighbours):
+            # a shifted copy. Left to the critic: the observation after the last step and the rows that ended an
+            # episode — one launch on a compacted list of fixed capacity instead of one over all T x N rows.
+            if T > 1:
+                next_values[:T - 1].copy_(values[1:])
+            mlp_forward_fused(x16_buf[T & 1], [nets[1] + (next_values[T - 1],)])
+            compact_nonzero(next_dones, term_list, term_count)
+            mlp_forward_fused(gather_pad_bf16(term_obs_all.view(T * N, -1), term_list, k0), [nets[1] + (term_values,)])
+            scatter_rows(next_values, term_list, term_values, term_count)
             gae_kernel(rewards, values, next_values, next_dones, next_timeouts, args.gamma, args.gae_lambda,
                        advantages, returns)
         return obs_all[T]
@@ -624,6 +639,9 @@ def train(args, log=print, hook=None):
         torch.cuda.synchronize()
         tu0 = time.time()
         t_roll += tu0 - tr0
+        if fused and int(term_count.item()) > term_cap:
+            raise RuntimeError(f"{int(term_count.item())} of {T * N} rollout rows ended an episode: more than the "
+                               f"{term_cap} rows the terminal-value list holds")
 
         clipfrac_sum.zero_()
         n_mb, n_ep = update_policy(args, args.batch_size, lambda n_: torch.randperm(n_, device=device), run_minibatch,

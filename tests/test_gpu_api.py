@@ -267,3 +267,63 @@ def test_outputs_stay_inside_their_buffers(n):
             inner = sl[:, :52] if k == "x16" else sl
             assert not torch.any(inner == SENT), (k, "unwritten rows")
         assert torch.all(bufs["x16"][1][:, 52:] == SENT)
+
+
+def test_terminal_values_come_from_the_next_step_or_the_compacted_critic_pass(tmp_path):
+    """ppo…:272 `next_values[step] = agent.get_value(info["terminal_observation"])`: the rollout only runs the critic on
+    the rows that ended an episode (and on the observation after the last step) and copies values[t + 1] elsewhere.
+    With a zero learning rate (weights unchanged by the update) the result must equal, bit for bit, the critic applied to
+    EVERY terminal observation — in the eager first update and in the captured-graph replays. Episodes of 20 steps: every
+    env ends at least once per 24-step rollout, some on its last step."""
+    import yaml
+    from rsoccer_isaac_cleanrl_b200 import ppo
+    from rsoccer_isaac_cleanrl_b200.engine import gather_pad_bf16, mlp_forward_fused
+    from rsoccer_isaac_cleanrl_b200.envs import load_cfg
+    from rsoccer_isaac_cleanrl_b200.tc_mlp import MlpWeights
+    T, N = 24, 700
+    cfg = load_cfg()
+    cfg["env"]["maxEpisodeLength"] = 20
+    path = tmp_path / "vss_short.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    args = ppo.parse_args(["--env-id", "sa", "--num-envs", str(N), "--num-steps", str(T), "--total-timesteps",
+                           str(T * N * 4), "--update-epochs", "1", "--quiet", "--seed", "3", "--learning-rate", "0"])
+    args.cfg_path = str(path)
+    seen = []
+
+    def hook(update, t):
+        mw = MlpWeights(t["agent"].critic)
+        x16 = gather_pad_bf16(t["term_obs"].view(T * N, -1), None, 64)
+        full, = mlp_forward_fused(x16, [(mw.w16, [b.detach() for b in mw.bs], mw.head_w.detach(), mw.head_b.detach(), None)])
+        nv, v, d = t["next_values"], t["values"], t["next_dones"]
+        assert torch.equal(nv.view(-1), full.view(-1)), (update, int((nv.view(-1) != full.view(-1)).sum()))
+        assert torch.equal(nv[:-1][d[:-1] == 0], v[1:][d[:-1] == 0])   # the shifted copy where no episode ended
+        seen.append((int(d.sum()), int(d[-1].sum())))
+
+    stats = ppo.train(args, hook=hook)
+    assert stats["updates"] == 4 and len(seen) == 4
+    assert all(n_done >= N for n_done, _ in seen) and sum(last for _, last in seen) > 0
+
+
+def test_compact_nonzero_and_scatter_rows():
+    """include/vss_b200.h vss_compact_nonzero / vss_scatter_rows_f32 against torch.nonzero, below and above capacity."""
+    from rsoccer_isaac_cleanrl_b200.engine import compact_nonzero, scatter_rows
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 100003
+    flags = (torch.rand(n, device="cuda", generator=g) < 0.01).float()
+    want = torch.nonzero(flags).view(-1)
+    for cap in (4096, 128):
+        lst = torch.full((cap,), -1, device="cuda", dtype=torch.int64)
+        cnt = torch.full((1,), 99, device="cuda", dtype=torch.int32)
+        compact_nonzero(flags, lst, cnt)
+        assert int(cnt.item()) == want.numel()
+        k = min(cap, want.numel())
+        got = lst[:k]
+        if cap >= want.numel():
+            assert torch.equal(torch.sort(got).values, want) and bool((lst[k:] == -1).all())
+        else:
+            assert bool(flags[got].bool().all()) and got.unique().numel() == k
+        dst = torch.zeros(n, device="cuda")
+        src = torch.arange(1, cap + 1, device="cuda", dtype=torch.float32)
+        lst_ok = lst.clamp(min=0)
+        scatter_rows(dst, lst_ok, src, cnt)
+        assert int((dst != 0).sum().item()) == k and torch.equal(dst[got], src[:k])
