@@ -9,11 +9,12 @@
 //     K-major 128-byte-swizzled layout tcgen05.mma reads as its A operand (what TMA would have produced);
 //   * warp 0 streams the weights (1.06 MB per network, L2-resident) through a 3 x 32 KB ring with TMA, running
 //     ahead across layer boundaries;
-//   * warp 1: one elected thread issues tcgen05.mma (M = 128, N = 256, K = 16); a layer's accumulator
-//     (128 x 256 / 512 fp32) is the whole TMEM (512 columns);
+//   * warp 1: one elected thread issues tcgen05.mma (M = 128, N = 256, K = 16); accumulators of 256 columns alternate
+//     between the two halves of the TMEM (512 columns), so a chunk's MMAs run while the previous chunk is drained;
 //   * warps 2..: epilogue — tcgen05.ld (software-pipelined), + bias, tanh.approx, bf16, written back INTO the
-//     activation buffer as the next layer's A operand (fence.proxy.async, mbarrier to the MMA thread);
-//     the last hidden layer feeds the 256 -> {1, 2, 6} head from registers, so only (rows, n_out) floats go to HBM.
+//     activation buffer as the next layer's A operand (fence.proxy.async, one mbarrier per 64-column block, so the next
+//     layer's MMAs start block by block); the last hidden layer feeds the 256 -> {1, 2, 6} head from registers and, for
+//     the actor, the action sample (ppo_sample.cuh), so only (rows, n_out) floats, actions and log-probs go to HBM.
 // Same arithmetic per element as the one-GEMM-per-launch path (tc_gemm.cu: fp32 accumulation over K in the same
 // order, (acc + bias) -> tanh.approx.f32 -> bf16 round-to-nearest), so the hidden activations are the same bits; the
 // head sums its 256 products in a different order (fp32).
@@ -88,20 +89,6 @@ __device__ __forceinline__ void bias_tanh_pack(const uint32_t (&v)[32], const fl
     packed[2 * j] = *reinterpret_cast<uint32_t*>(&p);
     packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&q);
   }
-}
-
-// Hidden layer: 32 columns [c, c + 32) of this thread's row into the activation buffer (K-major SWIZZLE_128B:
-// k-block c / 64, row pitch 128 B, 16-byte piece j of a row stored at piece j ^ (row % 8)).
-__device__ __forceinline__ void store_act_chunk(const uint32_t (&v)[32], const float* __restrict__ bias, uint8_t* act,
-                                                int row, int c) {
-  uint32_t packed[16];
-  bias_tanh_pack(v, bias + c, packed);
-  uint8_t* base = act + (c >> 6) * FM_BLOCK_BYTES + row * 128;
-  const int j0 = (c & 63) >> 3, sw = row & 7;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<uint4*>(base + (((j0 + j) ^ sw) << 4)) =
-        make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
 }
 
 // Last hidden layer: the same values (rounded to bf16 like the stored activations of the unfused path) times the
